@@ -1,0 +1,140 @@
+/*
+ * lightdock_b200.h — C ABI of the B200-native (sm_100a) LightDock scoring library.
+ *
+ * This is the drop-in boundary for ONE path of lightdock-rust v0.3.2: evaluating the DFIRE and
+ * DNA/pyDock energy of every glowworm pose of a swarm at each GSO step.  The reference has no FFI
+ * today; its plug-in boundary is the Rust trait
+ *
+ *     trait Score { fn energy(&self, translation:&[f64], rotation:&Quaternion,
+ *                             rec_nmodes:&[f64], lig_nmodes:&[f64]) -> f64 }      src/scoring.rs:11-19
+ *
+ * implemented by DFIRE (src/dfire.rs:265-362), DNA (src/dna.rs:411-529) and PYDOCK
+ * (src/pydock.rs:426-544) and called once per glowworm per step from
+ * Glowworm::compute_luciferin (src/glowworm.rs:61-72) <- Swarm::update_luciferin
+ * (src/swarm.rs:66-70).  The entry points below are what a Rust `extern "C"` block (or cgo/ctypes)
+ * binds to replace those three `energy` bodies; INTEGRATION.md shows the binding.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success and a negative
+ * LD_E* code on failure, with a thread-local message in ld_last_error().  Nothing unwinds across
+ * the ABI.  There is NO CPU fallback: without a CUDA device ld_create fails.
+ * A handle is used by one host thread at a time; different handles may be used concurrently.
+ */
+#ifndef LIGHTDOCK_B200_H
+#define LIGHTDOCK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LD_OK 0
+#define LD_EINVAL (-1)   /* bad argument / malformed descriptor (the reference would panic) */
+#define LD_ECUDA (-2)    /* CUDA runtime error (message carries cudaGetErrorString)          */
+#define LD_ENOMEM (-3)   /* host or device allocation failed                                */
+#define LD_ELIMIT (-4)   /* complex too large for the shared-memory staging of this build   */
+
+/* enum Method, src/scoring.rs:5-9.  PYDOCK shares the DNA kernel: only the host-side atom
+ * parameterisation differs (src/pydock.rs:332-345). */
+#define LD_METHOD_DFIRE 0
+#define LD_METHOD_DNA 1
+#define LD_METHOD_PYDOCK 2
+
+/* 169*169*20 entries are read from DCparams (src/dfire.rs:254). */
+#define LD_DFIRE_TABLE_LEN 571220
+
+/* One docking partner: the numeric content of DFIREDockingModel (src/dfire.rs:103-111) /
+ * DNADockingModel (src/dna.rs:235-246).  All arrays are caller-owned and copied by ld_create. */
+typedef struct ld_molecule_desc {
+  int32_t n_atoms;
+  const double *coords;        /* [n_atoms][3] AoS f64, atom order of the model                 */
+  const int32_t *dfire_type;   /* [n_atoms] DFIRE atom type 0..168 (src/dfire.rs:177-183); DFIRE */
+  const double *ele_charge;    /* [n_atoms] src/dna.rs:245 ; DNA/PYDOCK                          */
+  const double *vdw_energy;    /* [n_atoms] "vdw_charges" src/dna.rs:244 ; DNA/PYDOCK            */
+  const double *vdw_radius;    /* [n_atoms] src/dna.rs:243 ; DNA/PYDOCK                          */
+  int32_t n_modes;             /* num_anm (setup.anm_rec / anm_lig)                              */
+  const double *modes;         /* [n_modes][n_atoms][3] flat f64 (src/dfire.rs:292-293) or NULL  */
+  int32_t n_restraints;        /* ACTIVE restraint residues found in the structure               */
+  const int32_t *rst_offsets;  /* [n_restraints+1] CSR offsets into rst_atoms                    */
+  const int32_t *rst_atoms;    /* atom indices of each restraint residue (src/dfire.rs:151-162)  */
+  int32_t n_membrane;          /* MMB.BJ bead count (src/dfire.rs:146-149)                       */
+  const int32_t *membrane;     /* [n_membrane] atom indices                                      */
+} ld_molecule_desc;
+
+typedef struct ld_complex_desc {
+  int32_t method;              /* LD_METHOD_*                                                     */
+  int32_t use_anm;             /* setup.use_anm: pose rows carry n_modes extents per partner      */
+  ld_molecule_desc receptor;
+  ld_molecule_desc ligand;
+  const double *dfire_potential; /* [LD_DFIRE_TABLE_LEN] f64, DFIRE only                          */
+  int32_t device;              /* CUDA device ordinal                                             */
+  int32_t reserved;
+} ld_complex_desc;
+
+/* Quantities the reference computes inside energy() but does not return; the parity tests compare
+ * the integer ones bit-exact against the oracle. */
+typedef struct ld_pose_detail {
+  double raw_sum;              /* DFIRE: sum of table values (src/dfire.rs:338); DNA: total_elec  */
+  double raw_sum2;             /* DNA: total_vdw (src/dna.rs:503)                                 */
+  int64_t n_in_cutoff;         /* DFIRE: dist<=225 (src/dfire.rs:334); DNA: d2<=900               */
+  int64_t n_in_cutoff2;        /* DNA: d2<=100 (src/dna.rs:494)                                   */
+  int64_t n_interface_pairs;   /* pairs passing the interface test                                */
+  int64_t bin_hist[21];        /* DFIRE: histogram of dfire_bin (src/dfire.rs:337)                */
+  int32_t rec_rst_hit;         /* satisfied receptor restraint residues (src/scoring.rs:21-36)    */
+  int32_t lig_rst_hit;
+  int32_t membrane_hit;        /* beads at the interface (src/scoring.rs:38-47)                   */
+  int32_t reserved;
+} ld_pose_detail;
+
+/* Work counters of the last ld_score_batch* call (what the GPU actually executed). */
+typedef struct ld_batch_stats {
+  int64_t n_poses;
+  int64_t pair_evals_bruteforce; /* n_poses * n_rec * n_lig: the reference's loop count           */
+  int32_t kernel_launches;       /* CUDA kernels launched by the call                             */
+  int32_t rec_splits;            /* receptor tile ranges per pose (CTAs per pose)                 */
+  double device_ms;              /* device time of the call (CUDA events); host-buffer calls only */
+} ld_batch_stats;
+
+typedef struct ld_handle ld_handle;
+
+/* Builds the device-resident scoring object.  Replaces DFIRE::new / DNA::new / PYDOCK::new
+ * (src/dfire.rs:201-234, src/dna.rs:375-407, src/pydock.rs:391-422) after the host has typed the
+ * atoms. */
+int ld_create(const ld_complex_desc *desc, ld_handle **out);
+int ld_destroy(ld_handle *h);
+
+/* Doubles per pose row: 7 (+ receptor.n_modes + ligand.n_modes when use_anm).
+ * Row = tx,ty,tz, qw,qx,qy,qz, receptor extents..., ligand extents...  (src/swarm.rs:33-51). */
+int ld_pose_len(const ld_handle *h);
+
+/* Score::energy for n_poses poses in ONE batched launch sequence; host buffers, synchronous.
+ * Replaces the loop of Swarm::update_luciferin over Score::energy (src/swarm.rs:66-70). */
+int ld_score_batch(ld_handle *h, int64_t n_poses, const double *poses, double *energies);
+
+/* Same, with device-resident poses/energies on a caller-provided CUDA stream (cudaStream_t passed
+ * as void*; NULL = the handle's own stream).  Asynchronous with respect to the host. */
+int ld_score_batch_device(ld_handle *h, int64_t n_poses, const double *d_poses, double *d_energies,
+                          void *stream);
+
+/* Same as ld_score_batch plus the per-pose diagnostics.  iface_rec [n_poses][n_rec] and iface_lig
+ * [n_poses][n_lig] (0/1 bytes, ORIGINAL atom order; src/dfire.rs:322-323) may be NULL. */
+int ld_score_batch_detail(ld_handle *h, int64_t n_poses, const double *poses, double *energies,
+                          ld_pose_detail *detail, uint8_t *iface_rec, uint8_t *iface_lig);
+
+/* The pose transform alone (src/dfire.rs:282-320): coordinates of both partners as the pair loop
+ * sees them, ORIGINAL atom order, [n_poses][n_atoms][3].  Either output may be NULL. */
+int ld_transform_batch(ld_handle *h, int64_t n_poses, const double *poses, double *rec_coords,
+                       double *lig_coords);
+
+int ld_get_stats(const ld_handle *h, ld_batch_stats *out);
+
+/* Tuning knob for benchmarks/tests: force the number of receptor splits (0 = automatic). */
+int ld_set_rec_splits(ld_handle *h, int32_t splits);
+
+const char *ld_last_error(void);
+const char *ld_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGHTDOCK_B200_H */

@@ -1,0 +1,572 @@
+// ld_capi.cu — C-ABI implementation (include/lightdock_b200.h): builds the device-resident complex,
+// owns device/pinned buffers and the stream, and launches the three kernels per batch.
+// There is no CPU fallback anywhere in this file: every entry point either runs the CUDA kernels
+// or returns an error.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "ld_kernels.cuh"
+
+using namespace ldb200;
+
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                    \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      return fail(LD_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + \
+                                std::to_string(__LINE__) + ")");                                    \
+  } while (0)
+
+extern "C" const char *ld_last_error(void) { return g_err.c_str(); }
+extern "C" const char *ld_version(void) { return "lightdock_b200 0.1 (sm_100a)"; }
+
+// ---------------------------------------------------------------------------------------------
+struct ld_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  DeviceComplex cx{};
+  std::vector<void *> owned;  // device allocations of the complex
+  std::vector<int> rec_perm, lig_perm;  // sorted position -> original atom index
+  std::vector<double> rec_xyz_orig;     // original receptor coordinates (for ld_transform_batch)
+  int use_anm = 0;
+  int forced_splits = 0;
+  size_t lig_block = 0, rec_block = 0;
+  // work buffers
+  int64_t cap_poses = 0;   // capacity of poses/energies/detail buffers
+  int64_t cap_chunk = 0;   // capacity (poses) of block/partial/bitmap buffers
+  int cap_splits = 0;
+  double *d_poses = nullptr, *d_energies = nullptr;
+  ld_pose_detail *d_detail = nullptr;
+  unsigned char *d_lig_blocks = nullptr, *d_rec_blocks = nullptr;
+  double *d_partials = nullptr;
+  unsigned *d_iface_rec = nullptr, *d_iface_lig = nullptr;
+  double *h_poses = nullptr, *h_energies = nullptr;  // pinned
+  int64_t cap_pinned = 0;
+  int max_smem_optin = 0;
+  int sm_count = 0;
+  ld_batch_stats stats{};
+};
+
+template <typename T>
+static int upload(ld_handle *h, const std::vector<T> &v, const T **out) {
+  *out = nullptr;
+  if (v.empty()) return LD_OK;
+  void *d = nullptr;
+  CU(cudaMalloc(&d, v.size() * sizeof(T)));
+  h->owned.push_back(d);
+  CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<const T *>(d);
+  return LD_OK;
+}
+
+// Spatial tiling: recursive bisection along the longest axis, cutting at a multiple of `tile`, so
+// that consecutive runs of `tile` atoms are compact.  Returns perm[sorted position] = original index.
+static void bisect(std::vector<int> &idx, int lo, int hi, const double *xyz, int tile) {
+  const int n = hi - lo;
+  if (n <= tile) return;
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+  for (int i = lo; i < hi; ++i)
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = std::min(mn[d], xyz[3 * idx[i] + d]);
+      mx[d] = std::max(mx[d], xyz[3 * idx[i] + d]);
+    }
+  int ax = 0;
+  for (int d = 1; d < 3; ++d)
+    if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
+  const int tiles = (n + tile - 1) / tile;
+  const int mid = lo + (tiles / 2) * tile;
+  std::nth_element(idx.begin() + lo, idx.begin() + mid, idx.begin() + hi, [&](int a, int b) {
+    const double va = xyz[3 * a + ax], vb = xyz[3 * b + ax];
+    return va < vb || (va == vb && a < b);
+  });
+  bisect(idx, lo, mid, xyz, tile);
+  bisect(idx, mid, hi, xyz, tile);
+}
+static std::vector<int> spatial_order(const double *xyz, int n, int tile) {
+  std::vector<int> idx(n);
+  std::iota(idx.begin(), idx.end(), 0);
+  bisect(idx, 0, n, xyz, tile);
+  return idx;
+}
+
+static int check_molecule(const ld_molecule_desc &m, int method, int use_anm, const char *who) {
+  const std::string w(who);
+  if (m.n_atoms < 0) return fail(LD_EINVAL, w + ": negative atom count");
+  if (m.n_atoms > 0 && !m.coords) return fail(LD_EINVAL, w + ": coords is NULL");
+  if (method == LD_METHOD_DFIRE) {
+    if (m.n_atoms > 0 && !m.dfire_type) return fail(LD_EINVAL, w + ": dfire_type is NULL");
+    for (int i = 0; i < m.n_atoms; ++i)
+      if (m.dfire_type[i] < 0 || m.dfire_type[i] > 167)
+        return fail(LD_EINVAL, w + ": DFIRE atom type out of range (the reference would index past the table)");
+  } else if (m.n_atoms > 0 && (!m.ele_charge || !m.vdw_energy || !m.vdw_radius)) {
+    return fail(LD_EINVAL, w + ": DNA/pyDock parameters are NULL");
+  }
+  if (use_anm && m.n_modes > 0 && m.n_atoms > 0 && !m.modes) return fail(LD_EINVAL, w + ": modes is NULL");
+  if (m.n_modes < 0 || m.n_modes > 64) return fail(LD_EINVAL, w + ": unsupported number of ANM modes");
+  if (m.n_restraints < 0 || m.n_membrane < 0) return fail(LD_EINVAL, w + ": negative count");
+  if (m.n_restraints > 0) {
+    if (!m.rst_offsets || !m.rst_atoms) return fail(LD_EINVAL, w + ": restraint CSR is NULL");
+    for (int r = 0; r < m.n_restraints; ++r)
+      if (m.rst_offsets[r] > m.rst_offsets[r + 1]) return fail(LD_EINVAL, w + ": restraint offsets not monotone");
+    for (int k = m.rst_offsets[0]; k < m.rst_offsets[m.n_restraints]; ++k)
+      if (m.rst_atoms[k] < 0 || m.rst_atoms[k] >= m.n_atoms)
+        return fail(LD_EINVAL, w + ": restraint atom index out of range");
+  }
+  for (int k = 0; k < m.n_membrane; ++k)
+    if (!m.membrane || m.membrane[k] < 0 || m.membrane[k] >= m.n_atoms)
+      return fail(LD_EINVAL, w + ": membrane index out of range");
+  return LD_OK;
+}
+
+struct SortedMol {
+  std::vector<int> perm, inv;
+  std::vector<double> x, y, z, q, eps, rad, modes;
+  std::vector<int> toff;
+  std::vector<unsigned short> tb20;
+  std::vector<int> rst_off, rst_idx, mem_idx;
+  int n = 0, n_pad = 0, n_tiles = 0;
+};
+static SortedMol sort_molecule(const ld_molecule_desc &m, int method, int tile, double pad, int n_modes_eff) {
+  SortedMol s;
+  s.n = m.n_atoms;
+  s.n_tiles = (m.n_atoms + tile - 1) / tile;
+  s.n_pad = s.n_tiles * tile;
+  s.perm = spatial_order(m.coords, m.n_atoms, tile);
+  s.inv.assign(m.n_atoms, 0);
+  for (int i = 0; i < m.n_atoms; ++i) s.inv[s.perm[i]] = i;
+  s.x.assign(s.n_pad, pad); s.y.assign(s.n_pad, pad); s.z.assign(s.n_pad, pad);
+  for (int i = 0; i < s.n; ++i) {
+    const int o = s.perm[i];
+    s.x[i] = m.coords[3 * o]; s.y[i] = m.coords[3 * o + 1]; s.z[i] = m.coords[3 * o + 2];
+  }
+  if (method == LD_METHOD_DFIRE) {
+    s.toff.assign(s.n_pad, 0);
+    s.tb20.assign(s.n_pad, 0);
+    for (int i = 0; i < s.n; ++i) {
+      s.toff[i] = m.dfire_type[s.perm[i]] * DFIRE_ROW;
+      s.tb20[i] = (unsigned short)(m.dfire_type[s.perm[i]] * 20);
+    }
+  } else {
+    s.q.assign(s.n_pad, 0.0); s.eps.assign(s.n_pad, 0.0); s.rad.assign(s.n_pad, 0.0);
+    for (int i = 0; i < s.n; ++i) {
+      const int o = s.perm[i];
+      s.q[i] = m.ele_charge[o]; s.eps[i] = m.vdw_energy[o]; s.rad[i] = m.vdw_radius[o];
+    }
+  }
+  if (n_modes_eff > 0) {  // [k][atom][3] -> [k][3][sorted atom]
+    s.modes.assign((size_t)n_modes_eff * 3 * s.n_pad, 0.0);
+    for (int k = 0; k < n_modes_eff; ++k)
+      for (int i = 0; i < s.n; ++i)
+        for (int d = 0; d < 3; ++d)
+          s.modes[((size_t)k * 3 + d) * s.n_pad + i] = m.modes[((size_t)k * m.n_atoms + s.perm[i]) * 3 + d];
+  }
+  s.rst_off.assign(1, 0);
+  for (int r = 0; r < m.n_restraints; ++r) {
+    for (int k = m.rst_offsets[r]; k < m.rst_offsets[r + 1]; ++k) s.rst_idx.push_back(s.inv[m.rst_atoms[k]]);
+    s.rst_off.push_back((int)s.rst_idx.size());
+  }
+  for (int k = 0; k < m.n_membrane; ++k) s.mem_idx.push_back(s.inv[m.membrane[k]]);
+  return s;
+}
+
+extern "C" int ld_destroy(ld_handle *h) {
+  if (!h) return LD_OK;
+  cudaSetDevice(h->device);
+  for (void *p : h->owned) cudaFree(p);
+  cudaFree(h->d_poses); cudaFree(h->d_energies); cudaFree(h->d_detail);
+  cudaFree(h->d_lig_blocks); cudaFree(h->d_rec_blocks); cudaFree(h->d_partials);
+  cudaFree(h->d_iface_rec); cudaFree(h->d_iface_lig);
+  cudaFreeHost(h->h_poses); cudaFreeHost(h->h_energies);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return LD_OK;
+}
+
+static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
+  const int method = desc->method == LD_METHOD_DFIRE ? 0 : 1;
+  h->device = desc->device;
+  h->use_anm = desc->use_anm ? 1 : 0;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(LD_ECUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                              (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (desc->device < 0 || desc->device >= ndev) return fail(LD_EINVAL, "device ordinal out of range");
+  CU(cudaSetDevice(desc->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major < 10)
+    return fail(LD_ECUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+                              "; this library is built for sm_100a only");
+  h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  h->sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+
+  const int nrm = h->use_anm ? desc->receptor.n_modes : 0, nlm = h->use_anm ? desc->ligand.n_modes : 0;
+  SortedMol R = sort_molecule(desc->receptor, desc->method == LD_METHOD_DFIRE ? LD_METHOD_DFIRE : LD_METHOD_DNA,
+                              REC_TILE, REC_PAD, nrm);
+  SortedMol L = sort_molecule(desc->ligand, desc->method == LD_METHOD_DFIRE ? LD_METHOD_DFIRE : LD_METHOD_DNA,
+                              LIG_TILE, LIG_PAD, nlm);
+  h->rec_perm = R.perm;
+  h->lig_perm = L.perm;
+  h->rec_xyz_orig.assign(desc->receptor.coords, desc->receptor.coords + (size_t)3 * desc->receptor.n_atoms);
+
+  DeviceComplex &cx = h->cx;
+  cx.method = method;
+  cx.n_rec = R.n; cx.n_lig = L.n;
+  cx.n_rec_pad = R.n_pad; cx.n_lig_pad = L.n_pad;
+  cx.n_rec_tiles = R.n_tiles; cx.n_lig_tiles = L.n_tiles;
+  cx.n_rec_modes = nrm; cx.n_lig_modes = nlm;
+  cx.pose_len = 7 + nrm + nlm;
+  int rc;
+#define UP(vec, field) \
+  if ((rc = upload(h, vec, &cx.field)) != LD_OK) return rc
+  UP(R.x, rec_x); UP(R.y, rec_y); UP(R.z, rec_z);
+  UP(R.toff, rec_toff); UP(R.q, rec_q); UP(R.eps, rec_eps); UP(R.rad, rec_rad); UP(R.modes, rec_modes);
+  UP(L.x, lig_x); UP(L.y, lig_y); UP(L.z, lig_z);
+  UP(L.tb20, lig_tb20); UP(L.q, lig_q); UP(L.eps, lig_eps); UP(L.rad, lig_rad); UP(L.modes, lig_modes);
+  UP(R.rst_off, rec_rst_off); UP(R.rst_idx, rec_rst_idx); UP(L.rst_off, lig_rst_off); UP(L.rst_idx, lig_rst_idx);
+  UP(R.mem_idx, membrane_idx);
+  cx.n_rec_rst = desc->receptor.n_restraints;
+  cx.n_lig_rst = desc->ligand.n_restraints;
+  cx.n_membrane = desc->receptor.n_membrane;
+  std::vector<float4> sph(R.n_tiles);
+  for (int t = 0; t < R.n_tiles; ++t)
+    sph[t] = tile_sphere(R.x.data(), R.y.data(), R.z.data(), t * REC_TILE, std::min((t + 1) * REC_TILE, R.n));
+  UP(sph, rec_sphere);
+  if (method == 0) {
+    std::vector<double> pot(desc->dfire_potential, desc->dfire_potential + LD_DFIRE_TABLE_LEN);
+    UP(pot, pot);
+  }
+#undef UP
+  h->lig_block = block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  h->rec_block = nrm > 0 ? block_bytes(cx.n_rec_pad, cx.n_rec_tiles) : 0;
+  if (h->lig_block >= (1u << 20)) return fail(LD_ELIMIT, "ligand too large for one bulk copy");
+
+  // the pair kernels need opt-in dynamic shared memory; check the worst case (one split) fits
+  const int lig_words = (cx.n_lig_pad + 31) / 32;
+  const size_t need = pair_smem_bytes(method, cx.n_lig_pad, cx.n_lig_tiles, lig_words, cx.n_rec_tiles);
+  if (need > (size_t)h->max_smem_optin)
+    return fail(LD_ELIMIT, "ligand of " + std::to_string(cx.n_lig) + " atoms needs " + std::to_string(need) +
+                               " B of shared memory per CTA; limit is " + std::to_string(h->max_smem_optin));
+  CU(cudaFuncSetAttribute(dfire_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CU(cudaFuncSetAttribute(dfire_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CU(cudaFuncSetAttribute(dna_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CU(cudaFuncSetAttribute(dna_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  return LD_OK;
+}
+
+extern "C" int ld_create(const ld_complex_desc *desc, ld_handle **out) {
+  if (!desc || !out) return fail(LD_EINVAL, "ld_create: NULL argument");
+  *out = nullptr;
+  if (desc->method != LD_METHOD_DFIRE && desc->method != LD_METHOD_DNA && desc->method != LD_METHOD_PYDOCK)
+    return fail(LD_EINVAL, "method not supported");  // src/bin/lightdock-rust.rs:111-114
+  if (desc->method == LD_METHOD_DFIRE && !desc->dfire_potential)
+    return fail(LD_EINVAL, "DFIRE needs the DCparams table (src/dfire.rs:236-257)");
+  int rc;
+  if ((rc = check_molecule(desc->receptor, desc->method, desc->use_anm, "receptor")) != LD_OK) return rc;
+  if ((rc = check_molecule(desc->ligand, desc->method, desc->use_anm, "ligand")) != LD_OK) return rc;
+  ld_handle *h = new (std::nothrow) ld_handle();
+  if (!h) return fail(LD_ENOMEM, "out of host memory");
+  rc = create_impl(desc, h);
+  if (rc != LD_OK) {
+    std::string keep = g_err;
+    ld_destroy(h);
+    g_err = keep;
+    return rc;
+  }
+  *out = h;
+  return LD_OK;
+}
+
+extern "C" int ld_pose_len(const ld_handle *h) { return h ? h->cx.pose_len : LD_EINVAL; }
+
+extern "C" int ld_set_rec_splits(ld_handle *h, int32_t splits) {
+  if (!h || splits < 0) return fail(LD_EINVAL, "ld_set_rec_splits: bad argument");
+  h->forced_splits = splits;
+  return LD_OK;
+}
+
+extern "C" int ld_get_stats(const ld_handle *h, ld_batch_stats *out) {
+  if (!h || !out) return fail(LD_EINVAL, "ld_get_stats: NULL argument");
+  *out = h->stats;
+  return LD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static int regrow(T **p, size_t count) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  if (count == 0) return LD_OK;
+  CU(cudaMalloc(reinterpret_cast<void **>(p), count * sizeof(T)));
+  return LD_OK;
+}
+
+static int choose_splits(const ld_handle *h, int64_t n) {
+  const int tiles = std::max(1, h->cx.n_rec_tiles);
+  if (h->forced_splits > 0) return std::min(h->forced_splits, tiles);
+  const int64_t target = (int64_t)h->sm_count * 4;  // CTAs wanted to fill the machine with 2 waves of 2 CTA/SM
+  if (n >= target) return 1;
+  int64_t s = (target + n - 1) / std::max<int64_t>(n, 1);
+  // keep at least 4 tiles per CTA so the ligand staging is amortised
+  s = std::min<int64_t>(s, std::max(1, tiles / 4));
+  return (int)std::max<int64_t>(1, s);
+}
+
+static int64_t chunk_limit(const ld_handle *h) {
+  const size_t per_pose = h->lig_block + h->rec_block + 64;
+  int64_t c = (int64_t)((size_t)1 << 30) / (int64_t)per_pose;  // <= 1 GiB of coordinate blocks in flight
+  return std::max<int64_t>(1, std::min<int64_t>(c, 16384));
+}
+
+static int ensure_chunk(ld_handle *h, int64_t chunk, int splits) {
+  if (chunk <= h->cap_chunk && splits <= h->cap_splits) return LD_OK;
+  chunk = std::max(chunk, h->cap_chunk);
+  splits = std::max(splits, h->cap_splits);
+  const int lig_words = (h->cx.n_lig_pad + 31) / 32;
+  int rc;
+  if ((rc = regrow(&h->d_lig_blocks, (size_t)chunk * h->lig_block)) != LD_OK) return rc;
+  if ((rc = regrow(&h->d_rec_blocks, (size_t)chunk * h->rec_block)) != LD_OK) return rc;
+  if ((rc = regrow(&h->d_partials, (size_t)chunk * splits * 2)) != LD_OK) return rc;
+  if ((rc = regrow(&h->d_iface_rec, (size_t)chunk * std::max(1, h->cx.n_rec_tiles))) != LD_OK) return rc;
+  if ((rc = regrow(&h->d_iface_lig, (size_t)chunk * splits * std::max(1, lig_words))) != LD_OK) return rc;
+  h->cap_chunk = chunk;
+  h->cap_splits = splits;
+  return LD_OK;
+}
+
+static int ensure_poses(ld_handle *h, int64_t n, bool detail) {
+  if (n > h->cap_poses) {
+    int rc;
+    if ((rc = regrow(&h->d_poses, (size_t)n * h->cx.pose_len)) != LD_OK) return rc;
+    if ((rc = regrow(&h->d_energies, (size_t)n)) != LD_OK) return rc;
+    if (h->d_detail) { cudaFree(h->d_detail); h->d_detail = nullptr; }
+    h->cap_poses = n;
+  }
+  if (detail && !h->d_detail) {
+    int rc;
+    if ((rc = regrow(&h->d_detail, (size_t)h->cap_poses)) != LD_OK) return rc;
+  }
+  if (n > h->cap_pinned) {
+    cudaFreeHost(h->h_poses); cudaFreeHost(h->h_energies);
+    h->h_poses = h->h_energies = nullptr;
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&h->h_poses), (size_t)n * h->cx.pose_len * sizeof(double),
+                     cudaHostAllocDefault));
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&h->h_energies), (size_t)n * sizeof(double), cudaHostAllocDefault));
+    h->cap_pinned = n;
+  }
+  return LD_OK;
+}
+
+// Launches transform -> pair -> finalize for poses [0, n) living on the device.
+// If host_iface_* are given (detail mode) the bitmaps of each chunk are copied back as they are produced.
+static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_energies, cudaStream_t st,
+                      ld_pose_detail *d_detail, std::vector<unsigned> *host_ifr, std::vector<unsigned> *host_ifl) {
+  const DeviceComplex &cx = h->cx;
+  h->stats = ld_batch_stats{};
+  h->stats.n_poses = n;
+  h->stats.pair_evals_bruteforce = n * (int64_t)cx.n_rec * (int64_t)cx.n_lig;
+  if (n == 0) return LD_OK;
+  const int64_t climit = chunk_limit(h);
+  const int lig_words = (cx.n_lig_pad + 31) / 32;
+  const bool detail = d_detail != nullptr;
+  int launches = 0;
+  for (int64_t p0 = 0; p0 < n; p0 += climit) {
+    const int64_t nc = std::min(climit, n - p0);
+    const int splits = choose_splits(h, nc);
+    int rc;
+    if ((rc = ensure_chunk(h, nc, splits)) != LD_OK) return rc;
+    BatchBuffers bb{};
+    bb.poses = d_poses + (size_t)p0 * cx.pose_len;
+    bb.lig_blocks = h->d_lig_blocks;
+    bb.rec_blocks = h->d_rec_blocks;
+    bb.partials = h->d_partials;
+    bb.iface_rec = h->d_iface_rec;
+    bb.iface_lig = h->d_iface_lig;
+    bb.energies = d_energies + p0;
+    bb.detail = detail ? (void *)(d_detail + p0) : nullptr;
+    bb.rec_splits = splits;
+    bb.tiles_per_split = (std::max(1, cx.n_rec_tiles) + splits - 1) / splits;
+    bb.lig_words = lig_words;
+    h->stats.rec_splits = splits;
+    transform_kernel<<<(unsigned)nc, 256, 0, st>>>(cx, bb, (int)nc);
+    ++launches;
+    if (cx.n_rec_tiles > 0) {
+      const size_t smem = pair_smem_bytes(cx.method, cx.n_lig_pad, cx.n_lig_tiles, lig_words, bb.tiles_per_split);
+      const unsigned grid = (unsigned)(nc * splits);
+      if (cx.method == 0) {
+        if (detail) dfire_pair_kernel<true><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
+        else dfire_pair_kernel<false><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
+      } else {
+        if (detail) dna_pair_kernel<true><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
+        else dna_pair_kernel<false><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
+      }
+      ++launches;
+    } else {
+      CU(cudaMemsetAsync(h->d_partials, 0, (size_t)nc * splits * 2 * sizeof(double), st));
+      CU(cudaMemsetAsync(h->d_iface_lig, 0, (size_t)nc * splits * std::max(1, lig_words) * sizeof(unsigned), st));
+    }
+    const unsigned fgrid = (unsigned)((nc + 3) / 4);
+    if (detail) finalize_kernel<true><<<fgrid, 128, 0, st>>>(cx, bb, (int)nc);
+    else finalize_kernel<false><<<fgrid, 128, 0, st>>>(cx, bb, (int)nc);
+    ++launches;
+    CU(cudaGetLastError());
+    if (host_ifr) {
+      // detail mode: fetch this chunk's bitmaps (OR over splits for the ligand) before they are overwritten
+      std::vector<unsigned> lig_tmp((size_t)nc * splits * lig_words);
+      CU(cudaMemcpyAsync(host_ifr->data() + (size_t)p0 * cx.n_rec_tiles, h->d_iface_rec,
+                         (size_t)nc * cx.n_rec_tiles * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+      CU(cudaMemcpyAsync(lig_tmp.data(), h->d_iface_lig, lig_tmp.size() * sizeof(unsigned), cudaMemcpyDeviceToHost,
+                         st));
+      CU(cudaStreamSynchronize(st));
+      for (int64_t p = 0; p < nc; ++p)
+        for (int c = 0; c < splits; ++c)
+          for (int w = 0; w < lig_words; ++w)
+            (*host_ifl)[(size_t)(p0 + p) * lig_words + w] |= lig_tmp[((size_t)p * splits + c) * lig_words + w];
+    }
+  }
+  h->stats.kernel_launches = launches;
+  return LD_OK;
+}
+
+extern "C" int ld_score_batch_device(ld_handle *h, int64_t n_poses, const double *d_poses, double *d_energies,
+                                     void *stream) {
+  if (!h || n_poses < 0 || (n_poses > 0 && (!d_poses || !d_energies)))
+    return fail(LD_EINVAL, "ld_score_batch_device: bad argument");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  return run_device(h, n_poses, d_poses, d_energies, st, nullptr, nullptr, nullptr);
+}
+
+static int score_host(ld_handle *h, int64_t n, const double *poses, double *energies, ld_pose_detail *detail,
+                      uint8_t *iface_rec, uint8_t *iface_lig) {
+  if (!h || n < 0 || (n > 0 && (!poses || !energies))) return fail(LD_EINVAL, "ld_score_batch: bad argument");
+  CU(cudaSetDevice(h->device));
+  if (n == 0) {
+    h->stats = ld_batch_stats{};
+    return LD_OK;
+  }
+  const DeviceComplex &cx = h->cx;
+  const bool want_detail = detail != nullptr;
+  int rc;
+  if ((rc = ensure_poses(h, n, want_detail)) != LD_OK) return rc;
+  const size_t pose_bytes = (size_t)n * cx.pose_len * sizeof(double);
+  std::memcpy(h->h_poses, poses, pose_bytes);
+  CU(cudaEventRecord(h->ev0, h->stream));
+  CU(cudaMemcpyAsync(h->d_poses, h->h_poses, pose_bytes, cudaMemcpyHostToDevice, h->stream));
+  if (want_detail) CU(cudaMemsetAsync(h->d_detail, 0, (size_t)n * sizeof(ld_pose_detail), h->stream));
+  const int lig_words = (cx.n_lig_pad + 31) / 32;
+  std::vector<unsigned> ifr, ifl;
+  const bool want_iface = want_detail && (iface_rec || iface_lig);
+  if (want_iface) {
+    ifr.assign((size_t)n * std::max(1, cx.n_rec_tiles), 0u);
+    ifl.assign((size_t)n * std::max(1, lig_words), 0u);
+  }
+  rc = run_device(h, n, h->d_poses, h->d_energies, h->stream, want_detail ? h->d_detail : nullptr,
+                  want_iface ? &ifr : nullptr, want_iface ? &ifl : nullptr);
+  if (rc != LD_OK) return rc;
+  CU(cudaMemcpyAsync(h->h_energies, h->d_energies, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (want_detail)
+    CU(cudaMemcpyAsync(detail, h->d_detail, (size_t)n * sizeof(ld_pose_detail), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaEventRecord(h->ev1, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->stats.device_ms = ms;
+  std::memcpy(energies, h->h_energies, (size_t)n * sizeof(double));
+  if (want_iface) {
+    for (int64_t p = 0; p < n; ++p) {
+      if (iface_rec)
+        for (int i = 0; i < cx.n_rec; ++i)
+          iface_rec[(size_t)p * cx.n_rec + h->rec_perm[i]] =
+              (ifr[(size_t)p * cx.n_rec_tiles + (i >> 5)] >> (i & 31)) & 1u;
+      if (iface_lig)
+        for (int j = 0; j < cx.n_lig; ++j)
+          iface_lig[(size_t)p * cx.n_lig + h->lig_perm[j]] = (ifl[(size_t)p * lig_words + (j >> 5)] >> (j & 31)) & 1u;
+    }
+  }
+  return LD_OK;
+}
+
+extern "C" int ld_score_batch(ld_handle *h, int64_t n_poses, const double *poses, double *energies) {
+  return score_host(h, n_poses, poses, energies, nullptr, nullptr, nullptr);
+}
+
+extern "C" int ld_score_batch_detail(ld_handle *h, int64_t n_poses, const double *poses, double *energies,
+                                     ld_pose_detail *detail, uint8_t *iface_rec, uint8_t *iface_lig) {
+  if (!detail) return fail(LD_EINVAL, "ld_score_batch_detail: detail is NULL");
+  return score_host(h, n_poses, poses, energies, detail, iface_rec, iface_lig);
+}
+
+extern "C" int ld_transform_batch(ld_handle *h, int64_t n, const double *poses, double *rec_coords,
+                                  double *lig_coords) {
+  if (!h || n < 0 || (n > 0 && !poses)) return fail(LD_EINVAL, "ld_transform_batch: bad argument");
+  CU(cudaSetDevice(h->device));
+  if (n == 0) return LD_OK;
+  const DeviceComplex &cx = h->cx;
+  int rc;
+  if ((rc = ensure_poses(h, n, false)) != LD_OK) return rc;
+  CU(cudaMemcpyAsync(h->d_poses, poses, (size_t)n * cx.pose_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const int64_t climit = chunk_limit(h);
+  std::vector<unsigned char> lb, rb;
+  for (int64_t p0 = 0; p0 < n; p0 += climit) {
+    const int64_t nc = std::min(climit, n - p0);
+    if ((rc = ensure_chunk(h, nc, 1)) != LD_OK) return rc;
+    BatchBuffers bb{};
+    bb.poses = h->d_poses + (size_t)p0 * cx.pose_len;
+    bb.lig_blocks = h->d_lig_blocks;
+    bb.rec_blocks = h->d_rec_blocks;
+    transform_kernel<<<(unsigned)nc, 256, 0, h->stream>>>(cx, bb, (int)nc);
+    CU(cudaGetLastError());
+    lb.resize((size_t)nc * h->lig_block);
+    CU(cudaMemcpyAsync(lb.data(), h->d_lig_blocks, lb.size(), cudaMemcpyDeviceToHost, h->stream));
+    if (h->rec_block) {
+      rb.resize((size_t)nc * h->rec_block);
+      CU(cudaMemcpyAsync(rb.data(), h->d_rec_blocks, rb.size(), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    for (int64_t p = 0; p < nc; ++p) {
+      if (lig_coords) {
+        const double *x = reinterpret_cast<const double *>(lb.data() + (size_t)p * h->lig_block);
+        const double *y = x + cx.n_lig_pad, *z = y + cx.n_lig_pad;
+        double *o = lig_coords + (size_t)(p0 + p) * cx.n_lig * 3;
+        for (int j = 0; j < cx.n_lig; ++j) {
+          const int a = h->lig_perm[j];
+          o[3 * a] = x[j]; o[3 * a + 1] = y[j]; o[3 * a + 2] = z[j];
+        }
+      }
+      if (rec_coords) {
+        double *o = rec_coords + (size_t)(p0 + p) * cx.n_rec * 3;
+        if (h->rec_block) {
+          const double *x = reinterpret_cast<const double *>(rb.data() + (size_t)p * h->rec_block);
+          const double *y = x + cx.n_rec_pad, *z = y + cx.n_rec_pad;
+          for (int i = 0; i < cx.n_rec; ++i) {
+            const int a = h->rec_perm[i];
+            o[3 * a] = x[i]; o[3 * a + 1] = y[i]; o[3 * a + 2] = z[i];
+          }
+        } else {
+          std::memcpy(o, h->rec_xyz_orig.data(), (size_t)cx.n_rec * 3 * sizeof(double));
+        }
+      }
+    }
+  }
+  return LD_OK;
+}

@@ -1,0 +1,70 @@
+// ld_device.cuh — device-side data layout shared by the kernels and the C-ABI host code.
+//
+// HBM layout (all immutable per complex, built once in ld_create):
+//   receptor, sorted into spatial tiles of REC_TILE=32 atoms (one atom per lane of a warp):
+//     SoA f64 x[], y[], z[] padded to a tile multiple (pads at +1e30), per-atom DFIRE table row offset
+//     (type*3380) or DNA charge/eps/radius, one float4 bounding sphere per tile.
+//   ligand, sorted into spatial tiles of LIG_TILE=8 atoms: local-frame SoA f64 coordinates, per-atom
+//     DFIRE column offset (type*20, u16) or DNA parameters.
+//   ANM modes re-ordered to [mode][xyz][sorted atom] so a warp reads them coalesced.
+//   DFIRE potential: 571,220 f64 (4.57 MB) — stays resident in the 126 MB L2.
+// Per batch: one "ligand block" per pose (transformed SoA f64 coordinates + tile spheres, contiguous,
+//   16-byte aligned) written by the transform kernel and pulled into shared memory by the pair kernel
+//   with ONE cp.async.bulk (TMA) copy; a "receptor block" per pose only when receptor ANM is active.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ldb200 {
+
+constexpr int REC_TILE = 32;  // receptor atoms per tile = lanes of a warp
+constexpr int LIG_TILE = 8;   // ligand atoms per tile (unit of sphere culling)
+constexpr int PAIR_THREADS = 512;
+constexpr int DFIRE_ROW = 169 * 20;  // src/dfire.rs:338  atoma*169*20
+constexpr double REC_PAD = 1.0e30;   // coordinates of padding atoms: never within any cut-off
+constexpr double LIG_PAD = -1.0e30;
+
+struct DeviceComplex {
+  int method;  // 0 DFIRE, 1 DNA/pyDock
+  int n_rec, n_lig;
+  int n_rec_pad, n_lig_pad;
+  int n_rec_tiles, n_lig_tiles;
+  int n_rec_modes, n_lig_modes;  // effective (0 when use_anm is false)
+  int pose_len;
+  // receptor (sorted order)
+  const double *rec_x, *rec_y, *rec_z;
+  const int *rec_toff;                      // DFIRE: type * 3380
+  const double *rec_q, *rec_eps, *rec_rad;  // DNA
+  const float4 *rec_sphere;                 // static tile spheres (used when n_rec_modes == 0)
+  const double *rec_modes;                  // [k][3][n_rec_pad]
+  // ligand (sorted order, local frame)
+  const double *lig_x, *lig_y, *lig_z;
+  const unsigned short *lig_tb20;           // DFIRE: type * 20
+  const double *lig_q, *lig_eps, *lig_rad;  // DNA
+  const double *lig_modes;                  // [k][3][n_lig_pad]
+  const double *pot;                        // DFIRE table
+  // restraints (sorted atom positions) and membrane beads
+  int n_rec_rst, n_lig_rst, n_membrane;
+  const int *rec_rst_off, *rec_rst_idx, *lig_rst_off, *lig_rst_idx, *membrane_idx;
+};
+
+// bytes of one transformed-coordinate block: x,y,z f64 [n_pad] followed by float4 spheres [n_tiles]
+__host__ __device__ inline size_t block_bytes(int n_pad, int n_tiles) {
+  return (size_t)n_pad * 24 + (size_t)n_tiles * 16;
+}
+
+struct BatchBuffers {
+  const double *poses;      // [n][pose_len]
+  unsigned char *lig_blocks;  // [n][lig_block_bytes]
+  unsigned char *rec_blocks;  // [n][rec_block_bytes] (receptor ANM only)
+  double *partials;         // [n][rec_splits][2]
+  unsigned *iface_rec;      // [n][n_rec_tiles]
+  unsigned *iface_lig;      // [n][rec_splits][lig_words]
+  double *energies;         // [n]
+  void *detail;             // ld_pose_detail[n] or nullptr
+  int rec_splits;
+  int tiles_per_split;
+  int lig_words;
+};
+
+}  // namespace ldb200

@@ -1,0 +1,578 @@
+// ld_kernels.cuh — hand-written sm_100a kernels for the LightDock scoring hot path.
+//
+// Three kernels per batch of poses (all on one stream):
+//   1. transform_kernel   — Quaternion::rotate + translation + ANM displacement for every ligand
+//                           atom (and ANM for the receptor), bit-exact operation order of
+//                           src/qt.rs:57-61,174-185 and src/dfire.rs:282-320; writes one SoA block per
+//                           pose plus conservative float4 bounding spheres per spatial tile.
+//   2. dfire_pair_kernel / dna_pair_kernel
+//                         — the cut-off pair loop (src/dfire.rs:325-345, src/dna.rs:471-512).  One CTA per
+//                           (pose, receptor tile range).  The pose's ligand block is staged into shared
+//                           memory with one cp.async.bulk (TMA) copy completing on an mbarrier; each warp
+//                           owns receptor tiles (one atom per lane, coordinates in registers), culls
+//                           ligand tiles 32-at-a-time with an FP32 sphere test + ballot, and evaluates the
+//                           surviving pairs in exact, never-fused FP64.  Energies: per-lane FP64 accumulators
+//                           -> fixed-order warp-shuffle tree -> per-tile slot in shared memory -> ordered CTA
+//                           sum (bit-reproducible run to run).  Interface flags: ballot words / shared-memory
+//                           bitmaps.
+//   3. finalize_kernel    — restraint fractions, membrane fraction and the score algebra
+//                           (src/dfire.rs:347-361, src/dna.rs:513-528, src/scoring.rs:21-47).
+//
+// Everything that feeds a discrete decision (cut-off tests, bin index, interface test) is computed
+// with __dadd_rn/__dsub_rn/__dmul_rn/__dsqrt_rn so the compiler can never contract it into an FMA.
+#pragma once
+#include "ld_device.cuh"
+#include "../../include/lightdock_b200.h"
+
+namespace ldb200 {
+
+// ---------------------------------------------------------------------------------------------
+// small PTX wrappers (mbarrier + bulk async copy = TMA 1-D)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LD_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LD_DONE_%=;\n"
+      "bra LD_WAIT_%=;\n"
+      "LD_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Quaternion product, src/qt.rs:174-185 — four terms per component, summed left to right, no FMA.
+struct Quat {
+  double w, x, y, z;
+};
+__device__ __forceinline__ Quat qmul(const Quat &a, const Quat &b) {
+  Quat r;
+  r.w = __dsub_rn(__dsub_rn(__dsub_rn(__dmul_rn(a.w, b.w), __dmul_rn(a.x, b.x)), __dmul_rn(a.y, b.y)),
+                  __dmul_rn(a.z, b.z));
+  r.x = __dsub_rn(__dadd_rn(__dadd_rn(__dmul_rn(a.w, b.x), __dmul_rn(a.x, b.w)), __dmul_rn(a.y, b.z)),
+                  __dmul_rn(a.z, b.y));
+  r.y = __dadd_rn(__dadd_rn(__dsub_rn(__dmul_rn(a.w, b.y), __dmul_rn(a.x, b.z)), __dmul_rn(a.y, b.w)),
+                  __dmul_rn(a.z, b.x));
+  r.z = __dadd_rn(__dsub_rn(__dadd_rn(__dmul_rn(a.w, b.z), __dmul_rn(a.x, b.y)), __dmul_rn(a.y, b.x)),
+                  __dmul_rn(a.z, b.w));
+  return r;
+}
+
+// Conservative bounding sphere of atoms [a, b) of an SoA block: centre = box centre rounded to f32,
+// radius = max f64 distance to that f32 centre, inflated so the f32 value is never too small.
+__host__ __device__ inline float4 tile_sphere(const double *x, const double *y, const double *z, int a, int b) {
+  double lox = x[a], hix = x[a], loy = y[a], hiy = y[a], loz = z[a], hiz = z[a];
+  for (int i = a + 1; i < b; ++i) {
+    lox = x[i] < lox ? x[i] : lox; hix = x[i] > hix ? x[i] : hix;
+    loy = y[i] < loy ? y[i] : loy; hiy = y[i] > hiy ? y[i] : hiy;
+    loz = z[i] < loz ? z[i] : loz; hiz = z[i] > hiz ? z[i] : hiz;
+  }
+  float4 s;
+  s.x = (float)(0.5 * (lox + hix));
+  s.y = (float)(0.5 * (loy + hiy));
+  s.z = (float)(0.5 * (loz + hiz));
+  double r2 = 0.0;
+  for (int i = a; i < b; ++i) {
+    const double dx = x[i] - (double)s.x, dy = y[i] - (double)s.y, dz = z[i] - (double)s.z;
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    r2 = d2 > r2 ? d2 : r2;
+  }
+  s.w = (float)(sqrt(r2) * 1.000001 + 1.0e-6);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1: pose transform.  grid = poses, block = 256.
+__global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
+  const int p = blockIdx.x;
+  if (p >= n_poses) return;
+  const double *pose = bb.poses + (size_t)p * cx.pose_len;
+  const double tx = pose[0], ty = pose[1], tz = pose[2];
+  const Quat q = {pose[3], pose[4], pose[5], pose[6]};
+  // inverse(): conjugate / norm2, src/qt.rs:24-34,48-50,187-198
+  const double n2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q.w, q.w), __dmul_rn(q.x, q.x)), __dmul_rn(q.y, q.y)),
+                              __dmul_rn(q.z, q.z));
+  const Quat qi = {__ddiv_rn(q.w, n2), __ddiv_rn(-q.x, n2), __ddiv_rn(-q.y, n2), __ddiv_rn(-q.z, n2)};
+  const double *rec_ext = pose + 7;
+  const double *lig_ext = pose + 7 + cx.n_rec_modes;
+
+  unsigned char *lb = bb.lig_blocks + (size_t)p * block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  double *ox = reinterpret_cast<double *>(lb), *oy = ox + cx.n_lig_pad, *oz = oy + cx.n_lig_pad;
+  float4 *osph = reinterpret_cast<float4 *>(oz + cx.n_lig_pad);
+  for (int i = threadIdx.x; i < cx.n_lig_pad; i += blockDim.x) {
+    double x = LIG_PAD, y = LIG_PAD, z = LIG_PAD;
+    if (i < cx.n_lig) {
+      // rotate(): self * (0, v) * self.inverse(), src/qt.rs:57-61
+      const Quat v = {0.0, cx.lig_x[i], cx.lig_y[i], cx.lig_z[i]};
+      const Quat r = qmul(qmul(q, v), qi);
+      x = __dadd_rn(r.x, tx);  // src/dfire.rs:286-288
+      y = __dadd_rn(r.y, ty);
+      z = __dadd_rn(r.z, tz);
+      for (int k = 0; k < cx.n_lig_modes; ++k) {  // src/dfire.rs:290-301
+        const double e = lig_ext[k];
+        const double *m = cx.lig_modes + (size_t)k * 3 * cx.n_lig_pad;
+        x = __dadd_rn(x, __dmul_rn(m[i], e));
+        y = __dadd_rn(y, __dmul_rn(m[cx.n_lig_pad + i], e));
+        z = __dadd_rn(z, __dmul_rn(m[2 * cx.n_lig_pad + i], e));
+      }
+    }
+    ox[i] = x; oy[i] = y; oz[i] = z;
+  }
+  double *rx = nullptr, *ry = nullptr, *rz = nullptr;
+  float4 *rsph = nullptr;
+  if (cx.n_rec_modes > 0) {  // src/dfire.rs:304-320
+    unsigned char *rb = bb.rec_blocks + (size_t)p * block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
+    rx = reinterpret_cast<double *>(rb); ry = rx + cx.n_rec_pad; rz = ry + cx.n_rec_pad;
+    rsph = reinterpret_cast<float4 *>(rz + cx.n_rec_pad);
+    for (int i = threadIdx.x; i < cx.n_rec_pad; i += blockDim.x) {
+      double x = cx.rec_x[i], y = cx.rec_y[i], z = cx.rec_z[i];
+      if (i < cx.n_rec) {
+        for (int k = 0; k < cx.n_rec_modes; ++k) {
+          const double e = rec_ext[k];
+          const double *m = cx.rec_modes + (size_t)k * 3 * cx.n_rec_pad;
+          x = __dadd_rn(x, __dmul_rn(m[i], e));
+          y = __dadd_rn(y, __dmul_rn(m[cx.n_rec_pad + i], e));
+          z = __dadd_rn(z, __dmul_rn(m[2 * cx.n_rec_pad + i], e));
+        }
+      }
+      rx[i] = x; ry[i] = y; rz[i] = z;
+    }
+  }
+  __syncthreads();  // block-scope visibility of the coordinates just written
+  for (int t = threadIdx.x; t < cx.n_lig_tiles; t += blockDim.x) {
+    const int a = t * LIG_TILE, b = min(a + LIG_TILE, cx.n_lig);
+    osph[t] = tile_sphere(ox, oy, oz, a, b);
+  }
+  if (cx.n_rec_modes > 0)
+    for (int t = threadIdx.x; t < cx.n_rec_tiles; t += blockDim.x) {
+      const int a = t * REC_TILE, b = min(a + REC_TILE, cx.n_rec);
+      rsph[t] = tile_sphere(rx, ry, rz, a, b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory carve-up of the pair kernels
+struct PairSmem {
+  uint64_t *bar;
+  int *next_tile;
+  unsigned long long *counters;  // detail: [0]=n_in_cutoff [1]=n_in_cutoff2 [2]=n_iface_pairs
+  unsigned *hist;                // detail: 21 bins (+pad)
+  double *lx, *ly, *lz;
+  float4 *lsph;
+  unsigned char *lig_static;  // DFIRE: u16 tb20[n_lig_pad]; DNA: f64 q,eps,rad [n_lig_pad] each
+  unsigned *iface_lig;        // [lig_words]
+  double *tile_sum;           // [tiles_per_split] (x2 for DNA)
+};
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t pair_smem_bytes(int method, int n_lig_pad, int n_lig_tiles, int lig_words,
+                                                  int tiles_per_split) {
+  size_t o = 16 + 32 + 96;  // barrier+counter, 3 u64 counters (+pad), 24 u32 histogram
+  o += block_bytes(n_lig_pad, n_lig_tiles);
+  o += align16(method == 0 ? (size_t)n_lig_pad * 2 : (size_t)n_lig_pad * 24);
+  o += align16((size_t)lig_words * 4);
+  o += align16((size_t)tiles_per_split * 8 * (method == 0 ? 1 : 2));
+  return o;
+}
+__device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceComplex &cx, const BatchBuffers &bb) {
+  PairSmem s;
+  s.bar = reinterpret_cast<uint64_t *>(base);
+  s.next_tile = reinterpret_cast<int *>(base + 8);
+  s.counters = reinterpret_cast<unsigned long long *>(base + 16);
+  s.hist = reinterpret_cast<unsigned *>(base + 48);
+  unsigned char *o = base + 144;
+  s.lx = reinterpret_cast<double *>(o);
+  s.ly = s.lx + cx.n_lig_pad;
+  s.lz = s.ly + cx.n_lig_pad;
+  s.lsph = reinterpret_cast<float4 *>(s.lz + cx.n_lig_pad);
+  o += block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  s.lig_static = o;
+  o += align16(cx.method == 0 ? (size_t)cx.n_lig_pad * 2 : (size_t)cx.n_lig_pad * 24);
+  s.iface_lig = reinterpret_cast<unsigned *>(o);
+  o += align16((size_t)bb.lig_words * 4);
+  s.tile_sum = reinterpret_cast<double *>(o);
+  return s;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// DIST_TO_BINS[idx] - 1 for idx 0..29 (src/dfire.rs:49-53,337), packed 5 bits per entry.
+// idx: 0 1 2 3 4 ... 15 | 16 17 18 19 20 21 22 23 24 25 26 27 28 29
+// bin: 0 0 0 1 2 ... 13 | 13 14 14 15 15 16 16 17 17 18 18 19 19 20
+__device__ __forceinline__ int dfire_bin_of(int idx) {
+  return idx <= 2 ? 0 : (idx <= 15 ? idx - 2 : 13 + ((idx - 15) >> 1));
+}
+
+// Common prologue: stage the ligand block (TMA) and the static ligand data, zero the bitmaps.
+template <int METHOD>
+__device__ __forceinline__ void pair_prologue(const DeviceComplex &cx, const BatchBuffers &bb, const PairSmem &s,
+                                              int pose, int n_tiles_here) {
+  const int tid = threadIdx.x;
+  const uint32_t lig_bytes = (uint32_t)block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  if (tid == 0) {
+    mbar_init(s.bar, 1);
+    fence_mbar_init();
+    *s.next_tile = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(s.bar, lig_bytes);
+    bulk_g2s(s.lx, bb.lig_blocks + (size_t)pose * lig_bytes, lig_bytes, s.bar);
+  }
+  if (METHOD == 0) {
+    unsigned short *tb = reinterpret_cast<unsigned short *>(s.lig_static);
+    for (int i = tid; i < cx.n_lig_pad; i += blockDim.x) tb[i] = cx.lig_tb20[i];
+  } else {
+    double *lq = reinterpret_cast<double *>(s.lig_static), *le = lq + cx.n_lig_pad, *lr = le + cx.n_lig_pad;
+    for (int i = tid; i < cx.n_lig_pad; i += blockDim.x) {
+      lq[i] = cx.lig_q[i]; le[i] = cx.lig_eps[i]; lr[i] = cx.lig_rad[i];
+    }
+  }
+  for (int i = tid; i < bb.lig_words; i += blockDim.x) s.iface_lig[i] = 0u;
+  for (int i = tid; i < n_tiles_here * (METHOD == 0 ? 1 : 2); i += blockDim.x) s.tile_sum[i] = 0.0;
+  if (tid < 3) s.counters[tid] = 0ull;
+  if (tid < 24) s.hist[tid] = 0u;
+  __syncthreads();
+  mbar_wait(s.bar, 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 2a: DFIRE pair loop, src/dfire.rs:325-345.
+template <bool DETAIL>
+__global__ void __launch_bounds__(PAIR_THREADS, 2)
+    dfire_pair_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int pose = blockIdx.x / bb.rec_splits, split = blockIdx.x % bb.rec_splits;
+  if (pose >= n_poses) return;
+  const int t0 = split * bb.tiles_per_split;
+  const int t1 = min(t0 + bb.tiles_per_split, cx.n_rec_tiles);
+  const PairSmem s = carve(smem_raw, cx, bb);
+  pair_prologue<0>(cx, bb, s, pose, t1 - t0);
+  const unsigned short *s_tb20 = reinterpret_cast<const unsigned short *>(s.lig_static);
+
+  const int lane = threadIdx.x & 31;
+  const double *gx = cx.rec_x, *gy = cx.rec_y, *gz = cx.rec_z;
+  const float4 *gsph = cx.rec_sphere;
+  if (cx.n_rec_modes > 0) {
+    const unsigned char *rb = bb.rec_blocks + (size_t)pose * block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
+    gx = reinterpret_cast<const double *>(rb); gy = gx + cx.n_rec_pad; gz = gy + cx.n_rec_pad;
+    gsph = reinterpret_cast<const float4 *>(gz + cx.n_rec_pad);
+  }
+  const double *__restrict__ pot = cx.pot;
+  unsigned *iface_rec_out = bb.iface_rec + (size_t)pose * cx.n_rec_tiles;
+
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(s.next_tile, 1);
+    t = __shfl_sync(0xffffffffu, t, 0) + t0;
+    if (t >= t1) break;
+    const int ia = t * REC_TILE + lane;
+    const double rx = gx[ia], ry = gy[ia], rz = gz[ia];
+    const int toff = cx.rec_toff[ia];
+    const float4 rs = gsph[t];
+    double acc = 0.0;
+    bool iface_r = false;
+    unsigned n_in = 0, n_if = 0;
+
+    for (int lt0 = 0; lt0 < cx.n_lig_tiles; lt0 += 32) {
+      const int lt = lt0 + lane;
+      bool pass = false;
+      if (lt < cx.n_lig_tiles) {
+        const float4 ls = s.lsph[lt];
+        const float dx = rs.x - ls.x, dy = rs.y - ls.y, dz = rs.z - ls.z;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        const float reach = 15.0f + rs.w + ls.w;  // sqrt(225): src/dfire.rs:334
+        pass = d2 <= reach * reach * 1.00001f;
+      }
+      unsigned m = __ballot_sync(0xffffffffu, pass);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const int j0 = (lt0 + b) * LIG_TILE;
+#pragma unroll
+        for (int jj = 0; jj < LIG_TILE; ++jj) {
+          const int j = j0 + jj;
+          const double dx = __dsub_rn(rx, s.lx[j]);
+          const double dy = __dsub_rn(ry, s.ly[j]);
+          const double dz = __dsub_rn(rz, s.lz[j]);
+          const double dist = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          if (dist <= 225.0) {
+            const double d = __dsub_rn(__dmul_rn(__dsqrt_rn(dist), 2.0), 1.0);  // src/dfire.rs:336
+            const int idx = (int)d;  // `d as usize`: truncation, d in (-1, 29]
+            const int bin = dfire_bin_of(idx);
+            acc = __dadd_rn(acc, __ldg(pot + toff + (int)s_tb20[j] + bin));
+            if (DETAIL) {
+              ++n_in;
+              atomicAdd(&s.hist[bin], 1u);
+            }
+            if (d <= 3.9) {  // INTERFACE_CUTOFF on the bin-space value, src/dfire.rs:339
+              iface_r = true;
+              atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
+              if (DETAIL) ++n_if;
+            }
+          }
+        }
+      }
+    }
+    const double tsum = warp_sum(acc);
+    const unsigned rbits = __ballot_sync(0xffffffffu, iface_r);
+    if (lane == 0) {
+      s.tile_sum[t - t0] = tsum;
+      iface_rec_out[t] = rbits;
+    }
+    if (DETAIL) {
+      n_in = warp_sum_u32(n_in);
+      n_if = warp_sum_u32(n_if);
+      if (lane == 0) {
+        atomicAdd(&s.counters[0], (unsigned long long)n_in);
+        atomicAdd(&s.counters[2], (unsigned long long)n_if);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    for (int i = 0; i < t1 - t0; ++i) sum = __dadd_rn(sum, s.tile_sum[i]);
+    double *part = bb.partials + ((size_t)pose * bb.rec_splits + split) * 2;
+    part[0] = sum;
+    part[1] = 0.0;
+  }
+  unsigned *ifl = bb.iface_lig + ((size_t)pose * bb.rec_splits + split) * bb.lig_words;
+  for (int i = threadIdx.x; i < bb.lig_words; i += blockDim.x) ifl[i] = s.iface_lig[i];
+  if (DETAIL) {
+    ld_pose_detail *dt = reinterpret_cast<ld_pose_detail *>(bb.detail) + pose;
+    if (threadIdx.x == 0) {
+      atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_in_cutoff), s.counters[0]);
+      atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_interface_pairs), s.counters[2]);
+    }
+    if (threadIdx.x < 21)
+      atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[threadIdx.x]),
+                (unsigned long long)s.hist[threadIdx.x]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 2b: DNA / pyDock pair loop, src/dna.rs:471-512 (= src/pydock.rs:486-527).
+// powi(6)/powi(3) follow LLVM's repeated-squaring expansion (x^2, x^4, x^2*x^4 ; x*x^2).
+template <bool DETAIL>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+    dna_pair_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int pose = blockIdx.x / bb.rec_splits, split = blockIdx.x % bb.rec_splits;
+  if (pose >= n_poses) return;
+  const int t0 = split * bb.tiles_per_split;
+  const int t1 = min(t0 + bb.tiles_per_split, cx.n_rec_tiles);
+  const PairSmem s = carve(smem_raw, cx, bb);
+  pair_prologue<1>(cx, bb, s, pose, t1 - t0);
+  const double *s_q = reinterpret_cast<const double *>(s.lig_static);
+  const double *s_eps = s_q + cx.n_lig_pad, *s_rad = s_eps + cx.n_lig_pad;
+
+  const int lane = threadIdx.x & 31;
+  const double *gx = cx.rec_x, *gy = cx.rec_y, *gz = cx.rec_z;
+  const float4 *gsph = cx.rec_sphere;
+  if (cx.n_rec_modes > 0) {
+    const unsigned char *rb = bb.rec_blocks + (size_t)pose * block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
+    gx = reinterpret_cast<const double *>(rb); gy = gx + cx.n_rec_pad; gz = gy + cx.n_rec_pad;
+    gsph = reinterpret_cast<const float4 *>(gz + cx.n_rec_pad);
+  }
+  unsigned *iface_rec_out = bb.iface_rec + (size_t)pose * cx.n_rec_tiles;
+  // src/dna.rs:15-25 — the constants are f64 products/quotients evaluated at compile time
+  const double ELEC_DIST_CUTOFF2 = 30.0 * 30.0, VDW_DIST_CUTOFF2 = 10.0 * 10.0;
+  const double ELEC_MAX_CUTOFF = 1.0 * 4.0 / 332.0, ELEC_MIN_CUTOFF = -1.0 * 4.0 / 332.0;
+  const double INTERFACE_CUTOFF2 = 3.9 * 3.9;  // src/constants.rs:15
+
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(s.next_tile, 1);
+    t = __shfl_sync(0xffffffffu, t, 0) + t0;
+    if (t >= t1) break;
+    const int ia = t * REC_TILE + lane;
+    const double rx = gx[ia], ry = gy[ia], rz = gz[ia];
+    const double rq = cx.rec_q[ia], reps = cx.rec_eps[ia], rrad = cx.rec_rad[ia];
+    const float4 rs = gsph[t];
+    double acc_e = 0.0, acc_v = 0.0;
+    bool iface_r = false;
+    unsigned n_e = 0, n_v = 0, n_if = 0;
+
+    for (int lt0 = 0; lt0 < cx.n_lig_tiles; lt0 += 32) {
+      const int lt = lt0 + lane;
+      bool pass = false;
+      if (lt < cx.n_lig_tiles) {
+        const float4 ls = s.lsph[lt];
+        const float dx = rs.x - ls.x, dy = rs.y - ls.y, dz = rs.z - ls.z;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        const float reach = 30.0f + rs.w + ls.w;  // ELEC_DIST_CUTOFF, the widest of the three
+        pass = d2 <= reach * reach * 1.00001f;
+      }
+      unsigned m = __ballot_sync(0xffffffffu, pass);
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const int j0 = (lt0 + b) * LIG_TILE;
+#pragma unroll
+        for (int jj = 0; jj < LIG_TILE; ++jj) {
+          const int j = j0 + jj;
+          const double dx = __dsub_rn(rx, s.lx[j]);
+          const double dy = __dsub_rn(ry, s.ly[j]);
+          const double dz = __dsub_rn(rz, s.lz[j]);
+          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+          if (d2 <= ELEC_DIST_CUTOFF2) {  // src/dna.rs:481-491
+            double e = __ddiv_rn(__dmul_rn(rq, s_q[j]), d2);
+            e = e > ELEC_MAX_CUTOFF ? ELEC_MAX_CUTOFF : e;
+            e = e < ELEC_MIN_CUTOFF ? ELEC_MIN_CUTOFF : e;
+            acc_e = __dadd_rn(acc_e, e);
+            if (DETAIL) ++n_e;
+            if (d2 <= VDW_DIST_CUTOFF2) {  // src/dna.rs:494-504
+              const double ve = __dsqrt_rn(__dmul_rn(reps, s_eps[j]));
+              const double vr = __dadd_rn(rrad, s_rad[j]);
+              const double vr2 = __dmul_rn(vr, vr), vr4 = __dmul_rn(vr2, vr2);
+              const double vr6 = __dmul_rn(vr2, vr4);
+              const double d6 = __dmul_rn(d2, __dmul_rn(d2, d2));
+              const double p6 = __ddiv_rn(vr6, d6);
+              double k = __dmul_rn(ve, __dsub_rn(__dmul_rn(p6, p6), __dmul_rn(2.0, p6)));
+              k = k > 1.0 ? 1.0 : k;
+              acc_v = __dadd_rn(acc_v, k);
+              if (DETAIL) ++n_v;
+              if (d2 <= INTERFACE_CUTOFF2) {  // src/dna.rs:507-510
+                iface_r = true;
+                atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
+                if (DETAIL) ++n_if;
+              }
+            }
+          }
+        }
+      }
+    }
+    const double esum = warp_sum(acc_e), vsum = warp_sum(acc_v);
+    const unsigned rbits = __ballot_sync(0xffffffffu, iface_r);
+    if (lane == 0) {
+      s.tile_sum[2 * (t - t0)] = esum;
+      s.tile_sum[2 * (t - t0) + 1] = vsum;
+      iface_rec_out[t] = rbits;
+    }
+    if (DETAIL) {
+      n_e = warp_sum_u32(n_e); n_v = warp_sum_u32(n_v); n_if = warp_sum_u32(n_if);
+      if (lane == 0) {
+        atomicAdd(&s.counters[0], (unsigned long long)n_e);
+        atomicAdd(&s.counters[1], (unsigned long long)n_v);
+        atomicAdd(&s.counters[2], (unsigned long long)n_if);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double se = 0.0, sv = 0.0;
+    for (int i = 0; i < t1 - t0; ++i) {
+      se = __dadd_rn(se, s.tile_sum[2 * i]);
+      sv = __dadd_rn(sv, s.tile_sum[2 * i + 1]);
+    }
+    double *part = bb.partials + ((size_t)pose * bb.rec_splits + split) * 2;
+    part[0] = se;
+    part[1] = sv;
+  }
+  unsigned *ifl = bb.iface_lig + ((size_t)pose * bb.rec_splits + split) * bb.lig_words;
+  for (int i = threadIdx.x; i < bb.lig_words; i += blockDim.x) ifl[i] = s.iface_lig[i];
+  if (DETAIL && threadIdx.x == 0) {
+    ld_pose_detail *dt = reinterpret_cast<ld_pose_detail *>(bb.detail) + pose;
+    atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_in_cutoff), s.counters[0]);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_in_cutoff2), s.counters[1]);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_interface_pairs), s.counters[2]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 3: epilogue.  One warp per pose.  src/dfire.rs:347-361, src/dna.rs:513-528, src/scoring.rs:21-47.
+__device__ __forceinline__ bool lig_bit(const unsigned *ifl, int splits, int words, int j) {
+  unsigned w = 0;
+  for (int c = 0; c < splits; ++c) w |= ifl[(size_t)c * words + (j >> 5)];
+  return (w >> (j & 31)) & 1u;
+}
+template <bool DETAIL>
+__global__ void __launch_bounds__(128) finalize_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
+  const int pose = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pose >= n_poses) return;
+  const unsigned *ifr = bb.iface_rec + (size_t)pose * cx.n_rec_tiles;
+  const unsigned *ifl = bb.iface_lig + (size_t)pose * bb.rec_splits * bb.lig_words;
+  unsigned hr = 0, hl = 0, hm = 0;
+  for (int r = lane; r < cx.n_rec_rst; r += 32) {
+    bool hit = false;
+    for (int k = cx.rec_rst_off[r]; k < cx.rec_rst_off[r + 1] && !hit; ++k) {
+      const int a = cx.rec_rst_idx[k];
+      hit = (ifr[a >> 5] >> (a & 31)) & 1u;
+    }
+    hr += hit;
+  }
+  for (int r = lane; r < cx.n_lig_rst; r += 32) {
+    bool hit = false;
+    for (int k = cx.lig_rst_off[r]; k < cx.lig_rst_off[r + 1] && !hit; ++k)
+      hit = lig_bit(ifl, bb.rec_splits, bb.lig_words, cx.lig_rst_idx[k]);
+    hl += hit;
+  }
+  for (int k = lane; k < cx.n_membrane; k += 32) {
+    const int a = cx.membrane_idx[k];
+    hm += (ifr[a >> 5] >> (a & 31)) & 1u;
+  }
+  hr = warp_sum_u32(hr); hl = warp_sum_u32(hl); hm = warp_sum_u32(hm);
+  if (lane != 0) return;
+  double s0 = 0.0, s1 = 0.0;
+  const double *part = bb.partials + (size_t)pose * bb.rec_splits * 2;
+  for (int c = 0; c < bb.rec_splits; ++c) {
+    s0 = __dadd_rn(s0, part[2 * c]);
+    s1 = __dadd_rn(s1, part[2 * c + 1]);
+  }
+  double score;
+  if (cx.method == 0) {
+    score = __dmul_rn(__dsub_rn(__dmul_rn(s0, 0.0157), 4.7), -1.0);  // src/dfire.rs:347
+  } else {
+    const double te = __ddiv_rn(__dmul_rn(s0, 332.0), 4.0);  // src/dna.rs:513
+    score = __dmul_rn(__dadd_rn(te, s1), -1.0);            // src/dna.rs:514
+  }
+  const double pr = cx.n_rec_rst ? __ddiv_rn((double)hr, (double)cx.n_rec_rst) : 0.0;
+  const double pl = cx.n_lig_rst ? __ddiv_rn((double)hl, (double)cx.n_lig_rst) : 0.0;
+  double pen = 0.0;
+  const double inter = cx.n_membrane ? __ddiv_rn((double)hm, (double)cx.n_membrane) : 0.0;
+  if (inter > 0.0) pen = __dmul_rn(999.0, inter);  // MEMBRANE_PENALTY_SCORE, src/constants.rs:21
+  bb.energies[pose] =
+      __dsub_rn(__dadd_rn(__dadd_rn(score, __dmul_rn(pr, score)), __dmul_rn(pl, score)), pen);  // src/dfire.rs:361
+  if (DETAIL) {
+    ld_pose_detail *dt = reinterpret_cast<ld_pose_detail *>(bb.detail) + pose;
+    dt->raw_sum = s0;
+    dt->raw_sum2 = s1;
+    dt->rec_rst_hit = (int)hr;
+    dt->lig_rst_hit = (int)hl;
+    dt->membrane_hit = (int)hm;
+  }
+}
+
+}  // namespace ldb200

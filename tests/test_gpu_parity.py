@@ -1,0 +1,118 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bar (BASELINE.json north_star): distance-bin indices, atom-type lookups and interface-contact counts
+bit-exact; per-pose energies within 1e-6 relative (ENERGY_RTOL in helpers.py).
+DFIRE runs on the seeded synthetic DCparams unless LIGHTDOCK_DATA points at a real one (the real
+table is absent from the build container: DFIRE parity against the reference's own numbers is unpinned).
+"""
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import ENERGY_RTOL, assert_parity, case, random_poses, scorer_from_oracle
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("1azp", O.DNA), ("1azp", O.PYDOCK), ("1czy", O.DFIRE), ("1ppe", O.DFIRE), ("2uuy", O.DFIRE),
+         ("1k4c", O.DFIRE), ("ab_icode", O.DFIRE)]
+
+
+@pytest.mark.parametrize("name,method", CASES)
+def test_transform_bit_exact(name, method):
+    cx, pos, _ = case(name, method)
+    sc = scorer_from_oracle(cx)
+    poses = pos[:16]
+    rec, lig = sc.transform(poses)
+    _, d = cx.energy(poses, detail=True)
+    assert np.array_equal(rec, d["coords_rec"]), "receptor coordinates differ from the oracle"
+    assert np.array_equal(lig, d["coords_lig"]), "ligand coordinates differ from the oracle"
+
+
+@pytest.mark.parametrize("name,method", CASES)
+def test_start_positions_parity(name, method):
+    cx, pos, _ = case(name, method)
+    sc = scorer_from_oracle(cx)
+    n = 200 if cx.rec.n * cx.lig.n < 2_000_000 else 24  # keep the oracle side to seconds
+    poses = pos[:n]
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    e_ref, d_ref = cx.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
+    # the plain (non-detail) kernel instantiation must give the same bits as the detail one
+    assert np.array_equal(sc.energy(poses), e_gpu)
+
+
+@pytest.mark.parametrize("name,method", [("1azp", O.DNA), ("2uuy", O.DFIRE), ("1k4c", O.DFIRE)])
+def test_random_close_poses_parity(name, method):
+    """Poses pushed into the receptor: many contacts, restraints and membrane beads hit."""
+    cx, pos, _ = case(name, method)
+    sc = scorer_from_oracle(cx)
+    rng = np.random.default_rng(7)
+    centre = cx.rec.coords.mean(axis=0)
+    n = 48 if cx.rec.n * cx.lig.n < 2_000_000 else 12
+    poses = random_poses(rng, n, cx.pose_len, centre=centre, spread=12.0)
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    e_ref, d_ref = cx.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
+    assert d_ref["n_interface_pairs"].max() > 0
+
+
+def test_dna_known_answer(golden_dir):
+    """src/dna.rs:538-572 / src/pydock.rs:553-587: identity pose on tests/1azp -> -364.88126358158974."""
+    g = golden_dir + "/unit/1azp/"
+    for method in (O.DNA, O.PYDOCK):
+        rec = O.Molecule(O.read_pdb(g + "1azp_receptor.pdb"), method)
+        lig = O.Molecule(O.read_pdb(g + "1azp_ligand.pdb"), method)
+        cx = O.Complex(rec, lig, method, False)
+        sc = scorer_from_oracle(cx)
+        e = sc.energy([[0, 0, 0, 1, 0, 0, 0]])[0]
+        assert abs(e - (-364.88126358158974)) <= ENERGY_RTOL * 364.88126358158974
+
+
+def test_1azp_gso1_golden(golden_dir):
+    """All 200 (pose -> energy) pairs of example/1azp/swarm_0/gso_1.out (DNA + ANM + restraints)."""
+    cx, pos, _ = case("1azp", O.DNA)
+    sc = scorer_from_oracle(cx)
+    _, _, _, _, score = O.parse_gso_out(golden_dir + "/1azp/swarm_0/gso_1.out")
+    e = sc.energy(pos)
+    assert np.abs(e - score).max() <= 5.1e-9 + ENERGY_RTOL * np.abs(score).max() * 0  # 8-decimal print precision
+    assert np.abs(np.round(e, 8) - score).max() <= 1e-8
+
+
+def test_rec_splits_same_result():
+    """Splitting the receptor over several CTAs per pose changes only the summation grouping."""
+    cx, pos, _ = case("1k4c", O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    poses = pos[:32]
+    sc.set_rec_splits(1)
+    e1, d1 = sc.energy_detail(poses)
+    for s in (2, 5, 27):
+        sc.set_rec_splits(s)
+        e2, d2 = sc.energy_detail(poses)
+        np.testing.assert_array_equal(d1["bin_hist"], d2["bin_hist"])
+        np.testing.assert_array_equal(d1["iface_lig"], d2["iface_lig"])
+        np.testing.assert_array_equal(d1["iface_rec"], d2["iface_rec"])
+        assert np.abs(e1 - e2).max() <= 1e-9 * np.abs(e1).max()
+
+
+def test_run_to_run_deterministic():
+    cx, pos, _ = case("1k4c", O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    e1 = sc.energy(pos)
+    e2 = sc.energy(pos)
+    assert np.array_equal(e1, e2)
+
+
+def test_edge_cases():
+    cx, pos, _ = case("1ppe", O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    assert sc.energy(np.zeros((0, 7))).shape == (0,)
+    # a pose far away: no pair in the cut-off -> (0*0.0157 - 4.7) * -1 = 4.7 exactly (src/dfire.rs:347)
+    far = np.array([[1e4, 0, 0, 1, 0, 0, 0]], dtype=np.float64)
+    e, d = sc.energy_detail(far)
+    assert d["n_in_cutoff"][0] == 0 and e[0] == 4.7
+    # un-normalised quaternion: rotate() divides by norm2 (src/qt.rs:48-50), must match the oracle
+    p = pos[:8].copy()
+    p[:, 3:7] *= 1.7
+    e_gpu, d_gpu = sc.energy_detail(p)
+    e_ref, d_ref = cx.energy(p, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
