@@ -345,7 +345,7 @@ static int ensure_chunk(ld_handle *h, int64_t chunk, int splits) {
   int rc;
   if ((rc = regrow(&h->d_lig_blocks, (size_t)chunk * h->lig_block)) != LD_OK) return rc;
   if ((rc = regrow(&h->d_rec_blocks, (size_t)chunk * h->rec_block)) != LD_OK) return rc;
-  if ((rc = regrow(&h->d_partials, (size_t)chunk * splits * 2)) != LD_OK) return rc;
+  if ((rc = regrow(&h->d_partials, (size_t)chunk * std::max(1, h->cx.n_rec_tiles) * 2)) != LD_OK) return rc;
   if ((rc = regrow(&h->d_iface_rec, (size_t)chunk * std::max(1, h->cx.n_rec_tiles))) != LD_OK) return rc;
   if ((rc = regrow(&h->d_iface_lig, (size_t)chunk * splits * std::max(1, lig_words))) != LD_OK) return rc;
   h->cap_chunk = chunk;
@@ -421,7 +421,7 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       }
       ++launches;
     } else {
-      CU(cudaMemsetAsync(h->d_partials, 0, (size_t)nc * splits * 2 * sizeof(double), st));
+      
       CU(cudaMemsetAsync(h->d_iface_lig, 0, (size_t)nc * splits * std::max(1, lig_words) * sizeof(unsigned), st));
     }
     const unsigned fgrid = (unsigned)((nc + 3) / 4);

@@ -57,7 +57,7 @@ struct BatchBuffers {
   const double *poses;      // [n][pose_len]
   unsigned char *lig_blocks;  // [n][lig_block_bytes]
   unsigned char *rec_blocks;  // [n][rec_block_bytes] (receptor ANM only)
-  double *partials;         // [n][rec_splits][2]
+  double *partials;         // per-tile sums: DFIRE [n][n_rec_tiles], DNA [n][n_rec_tiles][2]
   unsigned *iface_rec;      // [n][n_rec_tiles]
   unsigned *iface_lig;      // [n][rec_splits][lig_words]
   double *energies;         // [n]

@@ -360,13 +360,10 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double sum = 0.0;
-    for (int i = 0; i < t1 - t0; ++i) sum = __dadd_rn(sum, s.tile_sum[i]);
-    double *part = bb.partials + ((size_t)pose * bb.rec_splits + split) * 2;
-    part[0] = sum;
-    part[1] = 0.0;
-  }
+  // per-tile sums go out as they are: the finalize kernel adds them in tile order, so a pose's energy
+  // does not depend on how many CTAs shared its receptor nor on the batch it was scored in
+  for (int i = threadIdx.x; i < t1 - t0; i += blockDim.x)
+    bb.partials[(size_t)pose * cx.n_rec_tiles + t0 + i] = s.tile_sum[i];
   unsigned *ifl = bb.iface_lig + ((size_t)pose * bb.rec_splits + split) * bb.lig_words;
   for (int i = threadIdx.x; i < bb.lig_words; i += blockDim.x) ifl[i] = s.iface_lig[i];
   if (DETAIL) {
@@ -490,16 +487,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double se = 0.0, sv = 0.0;
-    for (int i = 0; i < t1 - t0; ++i) {
-      se = __dadd_rn(se, s.tile_sum[2 * i]);
-      sv = __dadd_rn(sv, s.tile_sum[2 * i + 1]);
-    }
-    double *part = bb.partials + ((size_t)pose * bb.rec_splits + split) * 2;
-    part[0] = se;
-    part[1] = sv;
-  }
+  for (int i = threadIdx.x; i < 2 * (t1 - t0); i += blockDim.x)
+    bb.partials[((size_t)pose * cx.n_rec_tiles + t0) * 2 + i] = s.tile_sum[i];
   unsigned *ifl = bb.iface_lig + ((size_t)pose * bb.rec_splits + split) * bb.lig_words;
   for (int i = threadIdx.x; i < bb.lig_words; i += blockDim.x) ifl[i] = s.iface_lig[i];
   if (DETAIL && threadIdx.x == 0) {
@@ -546,10 +535,15 @@ __global__ void __launch_bounds__(128) finalize_kernel(const DeviceComplex cx, c
   hr = warp_sum_u32(hr); hl = warp_sum_u32(hl); hm = warp_sum_u32(hm);
   if (lane != 0) return;
   double s0 = 0.0, s1 = 0.0;
-  const double *part = bb.partials + (size_t)pose * bb.rec_splits * 2;
-  for (int c = 0; c < bb.rec_splits; ++c) {
-    s0 = __dadd_rn(s0, part[2 * c]);
-    s1 = __dadd_rn(s1, part[2 * c + 1]);
+  if (cx.method == 0) {
+    const double *part = bb.partials + (size_t)pose * cx.n_rec_tiles;
+    for (int t = 0; t < cx.n_rec_tiles; ++t) s0 = __dadd_rn(s0, part[t]);
+  } else {
+    const double *part = bb.partials + (size_t)pose * cx.n_rec_tiles * 2;
+    for (int t = 0; t < cx.n_rec_tiles; ++t) {
+      s0 = __dadd_rn(s0, part[2 * t]);
+      s1 = __dadd_rn(s1, part[2 * t + 1]);
+    }
   }
   double score;
   if (cx.method == 0) {

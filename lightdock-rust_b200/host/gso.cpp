@@ -1,0 +1,280 @@
+#include "gso.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <stdexcept>
+#include <thread>
+
+namespace lightdock {
+
+Glowworm::Glowworm(uint32_t id_, std::vector<double> translation_, Quaternion rotation_,
+                   std::vector<double> rec_nmodes_, std::vector<double> lig_nmodes_, const Score *scoring_function_,
+                   bool use_anm_)
+    : id(id_), translation(std::move(translation_)), rotation(rotation_), rec_nmodes(std::move(rec_nmodes_)),
+      lig_nmodes(std::move(lig_nmodes_)), scoring_function(scoring_function_), use_anm(use_anm_) {}
+
+void Glowworm::write_pose(double *row) const {
+  row[0] = translation[0]; row[1] = translation[1]; row[2] = translation[2];
+  row[3] = rotation.w; row[4] = rotation.x; row[5] = rotation.y; row[6] = rotation.z;
+  size_t k = 7;
+  for (double v : rec_nmodes) row[k++] = v;
+  for (double v : lig_nmodes) row[k++] = v;
+}
+
+void Glowworm::compute_luciferin() {
+  const bool scored = needs_scoring();
+  double s = scoring;
+  if (scored) s = scoring_function->energy(translation, rotation, rec_nmodes, lig_nmodes);
+  apply_luciferin(s, scored);
+}
+
+void Glowworm::apply_luciferin(double new_scoring, bool scored) {
+  if (scored) scoring = new_scoring;
+  luciferin = (1.0 - rho) * luciferin + gamma * scoring;
+  step += 1;
+}
+
+void Glowworm::update_vision_range() {
+  vision_range = std::fmin(
+      max_vision_range,
+      std::fmax(0.0, vision_range + beta * static_cast<double>(static_cast<int32_t>(max_neighbors) -
+                                                               static_cast<int32_t>(neighbors.size()))));
+}
+
+void Glowworm::compute_probability_moving_toward_neighbor(const std::vector<double> &luciferins) {
+  probabilities.clear();
+  double total_sum = 0.0;
+  for (uint32_t neighbor_id : neighbors) {
+    const double difference = luciferins[neighbor_id] - luciferin;
+    probabilities.push_back(difference);
+    total_sum += difference;
+  }
+  for (double &p : probabilities) p /= total_sum;
+}
+
+uint32_t Glowworm::select_random_neighbor(double random_number) {
+  if (neighbors.empty()) return id;
+  double sum_probabilities = 0.0;
+  size_t i = 0;
+  while (sum_probabilities < random_number) {
+    // the reference indexes probabilities[i] unchecked-by-logic and panics on overrun
+    if (i >= probabilities.size()) throw std::runtime_error("index out of bounds in select_random_neighbor");
+    sum_probabilities += probabilities[i];
+    i += 1;
+  }
+  if (i == 0) throw std::runtime_error("index out of bounds in select_random_neighbor");
+  return neighbors[i - 1];
+}
+
+static void step_towards(std::vector<double> &mine, const std::vector<double> &other, double step_size) {
+  std::vector<double> delta;
+  delta.reserve(mine.size());
+  double cum_norm = 0.0;
+  for (size_t i = 0; i < mine.size(); ++i) {
+    const double diff = other[i] - mine[i];
+    delta.push_back(diff);
+    cum_norm += diff * diff;
+  }
+  const double coef = step_size / std::sqrt(cum_norm);
+  for (size_t i = 0; i < mine.size(); ++i) {
+    delta[i] *= coef;
+    mine[i] += delta[i];
+  }
+}
+
+void Glowworm::move_towards(uint32_t other_id, const std::vector<double> &other_position,
+                            const Quaternion &other_rotation, const std::vector<double> &other_anm_rec,
+                            const std::vector<double> &other_anm_lig) {
+  moved = id != other_id;
+  if (id == other_id) return;
+  double delta_x[3] = {other_position[0] - translation[0], other_position[1] - translation[1],
+                       other_position[2] - translation[2]};
+  const double norm = std::sqrt(delta_x[0] * delta_x[0] + delta_x[1] * delta_x[1] + delta_x[2] * delta_x[2]);
+  const double coef = DEFAULT_TRANSLATION_STEP / norm;
+  for (int d = 0; d < 3; ++d) {
+    delta_x[d] *= coef;
+    translation[d] += delta_x[d];
+  }
+  rotation = rotation.slerp(other_rotation, DEFAULT_ROTATION_STEP);
+  if (use_anm && !rec_nmodes.empty()) step_towards(rec_nmodes, other_anm_rec, DEFAULT_NMODES_STEP);
+  if (use_anm && !lig_nmodes.empty()) step_towards(lig_nmodes, other_anm_lig, DEFAULT_NMODES_STEP);
+}
+
+double distance(const Glowworm &one, const Glowworm &two) {
+  const double x1 = one.translation[0], x2 = two.translation[0];
+  const double y1 = one.translation[1], y2 = two.translation[1];
+  const double z1 = one.translation[2], z2 = two.translation[2];
+  return std::sqrt((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2));
+}
+
+void Swarm::add_glowworms(const std::vector<std::vector<double>> &positions, const Score *scoring, bool use_anm,
+                          size_t rec_num_anm, size_t lig_num_anm) {
+  for (size_t i = 0; i < positions.size(); ++i) {
+    const std::vector<double> &position = positions[i];
+    if (position.size() < 7) throw std::runtime_error("index out of bounds: start position has fewer than 7 values");
+    std::vector<double> translation{position[0], position[1], position[2]};
+    const Quaternion rotation(position[3], position[4], position[5], position[6]);
+    std::vector<double> rec_nmodes, lig_nmodes;
+    if (use_anm && rec_num_anm > 0) {
+      if (position.size() < 7 + rec_num_anm) throw std::runtime_error("index out of bounds: receptor ANM extents");
+      rec_nmodes.assign(position.begin() + 7, position.begin() + 7 + rec_num_anm);
+    }
+    if (use_anm && lig_num_anm > 0)
+      for (size_t j = 7 + rec_num_anm; j < position.size(); ++j) lig_nmodes.push_back(position[j]);
+    glowworms.emplace_back(static_cast<uint32_t>(i), std::move(translation), rotation, std::move(rec_nmodes),
+                           std::move(lig_nmodes), scoring, use_anm);
+  }
+}
+
+size_t Swarm::gather_poses(std::vector<double> &rows, std::vector<uint32_t> &who) const {
+  if (glowworms.empty()) return 0;
+  const size_t pl = glowworms[0].scoring_function->pose_len();
+  size_t n = 0;
+  for (const Glowworm &g : glowworms)
+    if (g.needs_scoring()) {
+      if (7 + g.rec_nmodes.size() + g.lig_nmodes.size() != pl)
+        throw std::runtime_error("start position width does not match the scoring function's pose length");
+      rows.resize(rows.size() + pl);
+      g.write_pose(rows.data() + rows.size() - pl);
+      who.push_back(g.id);
+      ++n;
+    }
+  return n;
+}
+
+void Swarm::scatter_scores(const std::vector<uint32_t> &who, const double *scores) {
+  size_t k = 0;
+  for (Glowworm &g : glowworms) {
+    const bool scored = k < who.size() && who[k] == g.id;
+    g.apply_luciferin(scored ? scores[k] : 0.0, scored);
+    if (scored) ++k;
+  }
+  energy_calls += who.size();
+}
+
+void Swarm::update_luciferin() {
+  if (glowworms.empty()) return;
+  std::vector<double> rows, scores;
+  std::vector<uint32_t> who;
+  const size_t n = gather_poses(rows, who);
+  scores.resize(n);
+  if (n) glowworms[0].scoring_function->energy_batch(n, rows.data(), scores.data());
+  scatter_scores(who, scores.data());
+}
+
+void Swarm::movement_phase(StdRng &rng) {
+  const size_t n = glowworms.size();
+  std::vector<std::vector<double>> positions, anm_recs, anm_ligs;
+  std::vector<Quaternion> rotations;
+  for (const Glowworm &g : glowworms) {
+    positions.push_back(g.translation);
+    rotations.push_back(g.rotation);
+    anm_recs.push_back(g.rec_nmodes);
+    anm_ligs.push_back(g.lig_nmodes);
+  }
+  std::vector<std::vector<uint32_t>> neighbors(n);
+  for (size_t i = 0; i < n; ++i) {
+    const Glowworm &g1 = glowworms[i];
+    for (size_t j = 0; j < n; ++j) {
+      if (i == j) continue;
+      const Glowworm &g2 = glowworms[j];
+      if (g1.luciferin < g2.luciferin && distance(g1, g2) < g1.vision_range) neighbors[i].push_back(g2.id);
+    }
+  }
+  std::vector<double> luciferins;
+  for (const Glowworm &g : glowworms) luciferins.push_back(g.luciferin);
+  for (size_t i = 0; i < n; ++i) {
+    glowworms[i].neighbors = neighbors[i];
+    glowworms[i].compute_probability_moving_toward_neighbor(luciferins);
+  }
+  for (size_t i = 0; i < n; ++i) {
+    Glowworm &g = glowworms[i];
+    const uint32_t nid = g.select_random_neighbor(rng.gen_f64());  // always one draw per glowworm (:118)
+    g.move_towards(nid, positions[nid], rotations[nid], anm_recs[nid], anm_ligs[nid]);
+    g.update_vision_range();
+  }
+}
+
+void Swarm::save(uint32_t step, const std::string &output_directory) const {
+  const std::string path = output_directory + "/gso_" + std::to_string(step) + ".out";
+  FILE *f = std::fopen(path.c_str(), "w");
+  if (!f) throw std::runtime_error("Error saving GSO output: cannot create " + path);
+  std::fprintf(f, "#Coordinates  RecID  LigID  Luciferin  Neighbor's number  Vision Range  Scoring\n");
+  for (const Glowworm &g : glowworms) {
+    std::fprintf(f, "(%.7f, %.7f, %.7f, %.7f, %.7f, %.7f, %.7f", g.translation[0], g.translation[1],
+                 g.translation[2], g.rotation.w, g.rotation.x, g.rotation.y, g.rotation.z);
+    if (g.use_anm && !g.rec_nmodes.empty())
+      for (double v : g.rec_nmodes) std::fprintf(f, ", %.7f", v);
+    if (g.use_anm && !g.lig_nmodes.empty())
+      for (double v : g.lig_nmodes) std::fprintf(f, ", %.7f", v);
+    std::fprintf(f, ")    0    0   %.8f  %zu %.3f %.8f\n", g.luciferin, g.neighbors.size(), g.vision_range, g.scoring);
+  }
+  std::fclose(f);
+}
+
+GSO::GSO(const std::vector<std::vector<double>> &positions, uint64_t seed, const Score *scoring, bool use_anm,
+         size_t rec_num_anm, size_t lig_num_anm, std::string output_directory_)
+    : rng(StdRng::seed_from_u64(seed)), output_directory(std::move(output_directory_)) {
+  swarm.add_glowworms(positions, scoring, use_anm, rec_num_anm, lig_num_anm);
+}
+
+void GSO::run(uint32_t steps) {
+  for (uint32_t step = 1; step <= steps; ++step) {
+    swarm.update_luciferin();
+    swarm.movement_phase(rng);
+    if ((step % 10 == 0 || step == 1) && !output_directory.empty()) swarm.save(step, output_directory);
+  }
+}
+
+void MultiGSO::add(const std::vector<std::vector<double>> &positions, uint64_t seed, bool use_anm,
+                   size_t rec_num_anm, size_t lig_num_anm, std::string output_directory) {
+  runs.emplace_back(positions, seed, scoring, use_anm, rec_num_anm, lig_num_anm, std::move(output_directory));
+}
+
+uint64_t MultiGSO::energy_calls() const {
+  uint64_t n = 0;
+  for (const GSO &g : runs) n += g.swarm.energy_calls;
+  return n;
+}
+
+void MultiGSO::run(uint32_t steps, int host_threads) {
+  const size_t ns = runs.size();
+  host_threads = std::max(1, std::min<int>(host_threads, (int)std::max<size_t>(ns, 1)));
+  std::vector<double> rows, scores;
+  std::vector<std::vector<uint32_t>> who(ns);
+  std::vector<size_t> first(ns + 1, 0);
+  auto parallel = [&](auto &&fn) {  // fn(swarm index), swarms striped over host threads
+    if (host_threads == 1) {
+      for (size_t s = 0; s < ns; ++s) fn(s);
+      return;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < host_threads; ++t)
+      pool.emplace_back([&, t] {
+        for (size_t s = t; s < ns; s += host_threads) fn(s);
+      });
+    for (auto &th : pool) th.join();
+  };
+  for (uint32_t step = 1; step <= steps; ++step) {
+    rows.clear();
+    for (size_t s = 0; s < ns; ++s) {
+      who[s].clear();
+      first[s] = rows.size();
+      runs[s].swarm.gather_poses(rows, who[s]);
+    }
+    first[ns] = rows.size();
+    const size_t pl = scoring->pose_len();
+    const size_t n = rows.size() / pl;
+    scores.resize(n);
+    if (n) scoring->energy_batch(n, rows.data(), scores.data());  // ONE batched launch for all swarms
+    parallel([&](size_t s) {
+      runs[s].swarm.scatter_scores(who[s], scores.data() + first[s] / pl);
+      runs[s].swarm.movement_phase(runs[s].rng);
+      if ((step % 10 == 0 || step == 1) && !runs[s].output_directory.empty())
+        runs[s].swarm.save(step, runs[s].output_directory);
+    });
+  }
+}
+
+}  // namespace lightdock

@@ -1,0 +1,92 @@
+// gso.hpp — host side of the Glowworm Swarm Optimisation loop, mirroring src/glowworm.rs,
+// src/swarm.rs and src/lib.rs.  Control flow, neighbour selection and the seeded RNG stream stay on
+// the host exactly as in the reference; the ONE body that changes is Swarm::update_luciferin, which
+// gathers every glowworm that must be rescored (`moved || step == 0`) and scores them with a single
+// batched Score::energy_batch call instead of one Score::energy call per glowworm.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "quaternion.hpp"
+#include "scoring.hpp"
+#include "stdrng.hpp"
+
+namespace lightdock {
+
+constexpr uint64_t DEFAULT_SEED = 324324;          // src/constants.rs:2
+constexpr double DEFAULT_TRANSLATION_STEP = 0.5;   // src/constants.rs:5
+constexpr double DEFAULT_ROTATION_STEP = 0.5;      // src/constants.rs:8
+constexpr double DEFAULT_NMODES_STEP = 0.5;        // src/constants.rs:24
+
+struct Glowworm {  // src/glowworm.rs:6-26
+  uint32_t id = 0;
+  std::vector<double> translation;
+  Quaternion rotation;
+  std::vector<double> rec_nmodes, lig_nmodes;
+  const Score *scoring_function = nullptr;
+  double rho = 0.5, gamma = 0.4, beta = 0.08;
+  double luciferin = 5.0, vision_range = 0.2, max_vision_range = 5.0;
+  uint32_t max_neighbors = 5;
+  std::vector<uint32_t> neighbors;
+  std::vector<double> probabilities;
+  double scoring = 0.0;
+  bool moved = false;
+  uint32_t step = 0;
+  bool use_anm = false;
+
+  Glowworm(uint32_t id, std::vector<double> translation, Quaternion rotation, std::vector<double> rec_nmodes,
+           std::vector<double> lig_nmodes, const Score *scoring_function, bool use_anm);
+
+  bool needs_scoring() const { return moved || step == 0; }  // src/glowworm.rs:62
+  void write_pose(double *row) const;
+  void compute_luciferin();                         // src/glowworm.rs:61-72 (single-pose form)
+  void apply_luciferin(double new_scoring, bool scored);  // the arithmetic of :70-71 after a batched score
+  void update_vision_range();                       // :91-96
+  void compute_probability_moving_toward_neighbor(const std::vector<double> &luciferins);  // :98-112
+  uint32_t select_random_neighbor(double random_number);  // :114-126
+  void move_towards(uint32_t other_id, const std::vector<double> &other_position, const Quaternion &other_rotation,
+                    const std::vector<double> &other_anm_rec, const std::vector<double> &other_anm_lig);  // :128-190
+};
+
+double distance(const Glowworm &one, const Glowworm &two);  // src/glowworm.rs:193-202
+
+struct Swarm {  // src/swarm.rs
+  std::vector<Glowworm> glowworms;
+  uint64_t energy_calls = 0;  // poses actually scored so far
+
+  void add_glowworms(const std::vector<std::vector<double>> &positions, const Score *scoring, bool use_anm,
+                     size_t rec_num_anm, size_t lig_num_anm);  // :26-64
+  void update_luciferin();                                    // :66-70, batched
+  // the two halves of update_luciferin, exposed so several swarms can share one launch
+  size_t gather_poses(std::vector<double> &rows, std::vector<uint32_t> &who) const;
+  void scatter_scores(const std::vector<uint32_t> &who, const double *scores);
+  void movement_phase(StdRng &rng);                           // :72-126
+  void save(uint32_t step, const std::string &output_directory) const;  // :128-167
+};
+
+struct GSO {  // src/lib.rs:20-59
+  Swarm swarm;
+  StdRng rng;
+  std::string output_directory;
+
+  GSO(const std::vector<std::vector<double>> &positions, uint64_t seed, const Score *scoring, bool use_anm,
+      size_t rec_num_anm, size_t lig_num_anm, std::string output_directory);
+  void run(uint32_t steps);
+};
+
+// Many independent swarms of the SAME complex advanced in lock-step: each step gathers the poses of
+// all swarms into one Score::energy_batch call (SURVEY.md §8 e/f: swarms are independent, so a GPU
+// owns a set of swarms and scores them together).  Each swarm keeps its own StdRng seeded exactly as
+// a stand-alone reference process would be, so every swarm's trajectory equals the single-swarm run.
+struct MultiGSO {
+  std::vector<GSO> runs;
+  const Score *scoring;
+  explicit MultiGSO(const Score *s) : scoring(s) {}
+  void add(const std::vector<std::vector<double>> &positions, uint64_t seed, bool use_anm, size_t rec_num_anm,
+           size_t lig_num_anm, std::string output_directory);
+  void run(uint32_t steps, int host_threads = 1);
+  uint64_t energy_calls() const;
+};
+
+}  // namespace lightdock

@@ -1,0 +1,83 @@
+// lightdock-rust (B200 build) — drop-in for the reference driver src/bin/lightdock-rust.rs:
+//   lightdock-rust <setup.json> <initial_positions_N.dat> <steps> <dfire|dna|pydock>
+// Same argv, same progress lines, same path-resolution quirks (PDBs relative to the setup.json
+// directory; rec_nm.npy / lig_nm.npy, data/DCparams and swarm_N/ relative to the CWD), same
+// swarm_N/gso_<step>.out files.  Scoring runs on CUDA device $LIGHTDOCK_B200_DEVICE (default 0).
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <exception>
+#include <stdexcept>
+#include <string>
+
+#include "gso.hpp"
+#include "simulate.hpp"
+
+using namespace lightdock;
+
+static int simulate(const std::string &simulation_path, const SetupFile &setup, const std::string &swarm_filename,
+                    uint32_t steps, Method method) {
+  std::printf("Reading starting positions from %s\n", rust_debug_str(swarm_filename).c_str());
+  const std::optional<int> swarm_id = parse_swarm_id(swarm_filename);
+  if (!swarm_id) throw std::runtime_error("Could not parse swarm from swarm filename");
+  std::printf("Swarm ID %d\n", *swarm_id);
+  const std::string swarm_directory = "swarm_" + std::to_string(*swarm_id);
+  struct stat st;
+  if (stat(swarm_directory.c_str(), &st) != 0 || !S_ISDIR(st.st_mode)) {
+    std::fprintf(stderr, "Output directory does not exist for swarm %d, creating it\n", *swarm_id);
+    if (mkdir(swarm_directory.c_str(), 0777) != 0) throw std::runtime_error("Error creating directory");
+  }
+  std::printf("Writing to swarm dir %s\n", rust_debug_str(swarm_directory).c_str());
+  const auto positions = parse_input_coordinates(swarm_filename);
+  const char *dev = std::getenv("LIGHTDOCK_B200_DEVICE");
+  LoadedCase lc = load_case(simulation_path, setup, method, "", dev ? std::atoi(dev) : 0, true);
+  std::printf("Creating GSO with %zu glowworms\n", positions.size());
+  GSO gso(positions, lc.seed, lc.scoring.get(), setup.use_anm, setup.anm_rec, setup.anm_lig, swarm_directory);
+  std::printf("Starting optimization (%u steps)\n", steps);
+  std::fflush(stdout);
+  gso.run(steps);
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc != 5) {
+    std::fprintf(stderr, "Wrong command line. Usage: %s setup_filename swarm_filename steps method\n", argv[0]);
+    return 0;  // the reference returns normally on CLI errors
+  }
+  const std::string setup_filename = argv[1], swarm_filename = argv[2], num_steps = argv[3];
+  char *end = nullptr;
+  const unsigned long long steps64 = std::strtoull(num_steps.c_str(), &end, 10);
+  if (num_steps.empty() || *end != '\0' || num_steps[0] == '-' || steps64 > 0xffffffffULL) {
+    std::fprintf(stderr, "Error: steps argument must be a number\n");
+    return 0;
+  }
+  std::string method_type = argv[4];
+  std::transform(method_type.begin(), method_type.end(), method_type.begin(), [](unsigned char c) { return std::tolower(c); });
+  Method method;
+  if (method_type == "dfire") method = Method::DFIRE;
+  else if (method_type == "dna") method = Method::DNA;
+  else if (method_type == "pydock") method = Method::PYDOCK;
+  else {
+    std::fprintf(stderr, "Error: method not supported\n");
+    return 0;
+  }
+  SetupFile setup;
+  try {
+    setup = read_setup_from_file(setup_filename);
+  } catch (const std::exception &e) {
+    std::fprintf(stderr, "Error reading setup file [%s]: %s\n", rust_debug_str(setup_filename).c_str(),
+                 rust_debug_str(e.what()).c_str());
+    return 0;
+  }
+  const size_t slash = setup_filename.find_last_of('/');
+  const std::string simulation_path = slash == std::string::npos ? "" : setup_filename.substr(0, slash);
+  try {
+    return simulate(simulation_path, setup, swarm_filename, (uint32_t)steps64, method);
+  } catch (const std::exception &e) {
+    // the reference panics here; mirror the message and the panic exit status
+    std::fprintf(stderr, "thread '<unnamed>' panicked: %s\n", e.what());
+    return 101;
+  }
+}

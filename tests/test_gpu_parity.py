@@ -79,7 +79,8 @@ def test_1azp_gso1_golden(golden_dir):
 
 
 def test_rec_splits_same_result():
-    """Splitting the receptor over several CTAs per pose changes only the summation grouping."""
+    """Splitting the receptor over several CTAs per pose must not change a single bit: per-tile sums
+    are combined in tile order whatever the split (batch-invariant energies)."""
     cx, pos, _ = case("1k4c", O.DFIRE)
     sc = scorer_from_oracle(cx)
     poses = pos[:32]
@@ -91,7 +92,7 @@ def test_rec_splits_same_result():
         np.testing.assert_array_equal(d1["bin_hist"], d2["bin_hist"])
         np.testing.assert_array_equal(d1["iface_lig"], d2["iface_lig"])
         np.testing.assert_array_equal(d1["iface_rec"], d2["iface_rec"])
-        assert np.abs(e1 - e2).max() <= 1e-9 * np.abs(e1).max()
+        assert np.array_equal(e1, e2)
 
 
 def test_run_to_run_deterministic():

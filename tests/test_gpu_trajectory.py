@@ -1,0 +1,87 @@
+"""GPU end-to-end: the drop-in CLI / C++ host GSO driving the CUDA scorer reproduces the reference's
+100-step trajectories (final poses and scores) within the north-star tolerance (1e-6 relative), and
+every discrete field (neighbour counts) exactly."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import ENERGY_RTOL, GOLDEN, case
+
+pytestmark = pytest.mark.gpu
+
+STEPS = [1, 10, 20, 30, 40, 50, 60, 70, 80, 90, 100]
+
+
+def compare_gso_files(got, want, rtol=ENERGY_RTOL):
+    pg, lg, ng, vg, sg = O.parse_gso_out(got)
+    pw, lw, nw, vw, sw = O.parse_gso_out(want)
+    assert pg.shape == pw.shape
+    np.testing.assert_array_equal(ng, nw, err_msg=f"neighbour counts differ in {got}")
+    np.testing.assert_array_equal(vg, vw, err_msg="vision range")
+    assert np.abs(pg - pw).max() <= 1.5e-7 + rtol * np.abs(pw).max(), "poses"
+    # printed with 8 decimals: allow one unit of print precision on top of the relative tolerance
+    assert (np.abs(sg - sw) <= 1.1e-8 + rtol * np.abs(sw)).all(), "scoring"
+    assert (np.abs(lg - lw) <= 1.1e-8 + rtol * np.abs(lw)).all(), "luciferin"
+
+
+def test_cli_reproduces_1azp_golden_trajectory(tmp_path):
+    """example/1azp: DNA scoring + ANM (10/10 modes) + active restraints, seed 324324, 100 steps."""
+    from ldb200 import host
+    g = os.path.join(GOLDEN, "1azp")
+    for f in ("rec_nm.npy", "lig_nm.npy"):  # the reference reads the ANM files from the CWD
+        shutil.copy(os.path.join(g, f), tmp_path / f)
+    r = subprocess.run([host.CLI_PATH, os.path.join(g, "setup.json"), os.path.join(g, "initial_positions_0.dat"),
+                        "100", "dna"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.splitlines()
+    assert out[0].startswith('Reading starting positions from "') and out[1] == "Swarm ID 0"
+    assert out[2] == 'Writing to swarm dir "swarm_0"'
+    assert out[-3:] == ["Loading DNA scoring function", "Creating GSO with 200 glowworms",
+                        "Starting optimization (100 steps)"]
+    produced = sorted(os.listdir(tmp_path / "swarm_0"))
+    assert produced == sorted(f"gso_{s}.out" for s in STEPS)
+    for s in STEPS:
+        compare_gso_files(str(tmp_path / "swarm_0" / f"gso_{s}.out"), os.path.join(g, "swarm_0", f"gso_{s}.out"))
+
+
+def test_host_gso_matches_oracle_gso_dfire_anm():
+    """2uuy (DFIRE + ANM) for 30 steps: product host+GPU vs oracle GSO, discrete fields exact."""
+    from ldb200 import host
+    cx, pos, seed = case("2uuy", O.DFIRE)
+    g = os.path.join(GOLDEN, "2uuy")
+    tmp = os.environ.get("TMPDIR", "/tmp") + "/ld_dcparams_2uuy"
+    os.makedirs(tmp, exist_ok=True)
+    O.write_dcparams(os.path.join(tmp, "DCparams"), cx.potential)
+    os.environ["LIGHTDOCK_DATA"] = tmp
+    try:
+        c = host.Case(os.path.join(g, "setup.json"), "dfire", anm_dir=g)
+        state, calls = c.gso(os.path.join(g, "initial_positions_0.dat"), 30)
+    finally:
+        del os.environ["LIGHTDOCK_DATA"]
+    final, tr, ocalls = cx.gso_run(pos, seed, 30, trace=True)
+    last = tr[-1]
+    assert calls == ocalls
+    np.testing.assert_array_equal(state[:, 2], last[:, 2])            # neighbour counts
+    np.testing.assert_array_equal(state[:, 3], last[:, 3])            # vision range
+    assert np.abs(state[:, 4:] - last[:, 5:]).max() <= 1e-9            # poses
+    assert (np.abs(state[:, 1] - last[:, 1]) <= ENERGY_RTOL * np.abs(last[:, 1])).all()  # scoring
+
+
+def test_multi_gso_equals_single_swarm_runs():
+    """Lock-step multi-swarm driver: every swarm's trajectory equals its stand-alone run."""
+    from ldb200 import host
+    g = os.path.join(GOLDEN, "1azp")
+    c = host.Case(os.path.join(g, "setup.json"), "dna", anm_dir=g)
+    pos = np.array([[float(x) for x in l.split(" ")] for l in open(os.path.join(g, "initial_positions_0.dat")).read().splitlines()])
+    single, calls1 = c.gso(os.path.join(g, "initial_positions_0.dat"), 12)
+    rng = np.random.default_rng(5)
+    pos2 = pos.copy()
+    pos2[:, :3] += rng.normal(0, 0.3, size=(pos.shape[0], 3))
+    multi, calls = c.multi_gso(np.stack([pos, pos2, pos]), [c.seed, c.seed, 99], 12, host_threads=3)
+    assert np.array_equal(multi[0], single)
+    assert not np.array_equal(multi[1], single) and not np.array_equal(multi[2], single)
+    assert calls > calls1

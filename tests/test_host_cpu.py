@@ -1,0 +1,115 @@
+"""CPU-side tests of the product's C++ host layer (no GPU): the host restatements that must match
+the reference bit for bit — StdRng stream, slerp, rotate, PDB iteration order, atom typing,
+restraint / membrane indexing — checked against the oracle and the reference's known answers."""
+import ctypes
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import GOLDEN, ROOT
+
+host = pytest.importorskip("ldb200.host")
+
+
+def test_stdrng_known_answers():
+    # first five draws for DEFAULT_SEED and the oracle stream
+    d = host.rng_draws(324324, 5)
+    assert list(d) == [0.916682432764016, 0.982482828413927, 0.1690497920582783, 0.8221525196944237,
+                       0.5337791401145179]
+    r = O.Rng(987654321)
+    assert list(host.rng_draws(987654321, 1000)) == [r.f64() for _ in range(1000)]
+
+
+def test_stdrng_random_quaternion_known_answer():
+    """src/qt.rs:451-462: Quaternion::random with seed 324324324."""
+    u1, u2, u3 = host.rng_draws(324324324, 3)
+    q = (math.sqrt(1 - u1) * math.sin(2 * math.pi * u2), math.sqrt(1 - u1) * math.cos(2 * math.pi * u2),
+         math.sqrt(u1) * math.sin(2 * math.pi * u3), math.sqrt(u1) * math.cos(2 * math.pi * u3))
+    exp = (0.31924330894562036, -0.5980633213833059, 0.5444724265858514, 0.49391674399349367)
+    assert all(abs(a - b) < 2.220446049250313e-16 * 4 for a, b in zip(q, exp))
+
+
+def test_rotate_known_answer():
+    """src/qt.rs:360-369 (exact)."""
+    assert list(host.rotate([0.707106781, 0.0, 0.707106781, 0.0], [1.0, 0.0, 0.0])) == [0.0, 0.0, -1.0]
+
+
+def test_slerp_matches_oracle_and_reference_cases():
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        a, b = rng.normal(size=4), rng.normal(size=4)
+        t = rng.uniform()
+        assert list(host.slerp(a, b, t)) == O.slerp(a, b, t)
+    # src/qt.rs:440-448: half-way between two quaternions
+    s = host.slerp([0.7071067811865475, 0, 0, 0.7071067811865475], [0, 0.7071067811865475, 0.7071067811865475, 0], 0.5)
+    assert np.allclose(s, [0.5, 0.5, 0.5, 0.5], atol=2.3e-16)
+    # nearly parallel -> linear branch (LINEAR_THRESHOLD)
+    a = np.array([1.0, 0.0, 0.0, 0.0]); b = np.array([0.99999, 0.004, 0.0, 0.0])
+    assert list(host.slerp(a, b, 0.5)) == O.slerp(a, b, 0.5)
+
+
+CASES = [("1azp", "lightdock_protein.pdb", "dna", ["A.TRP.24", "A.VAL.26", "A.ARG.42"]),
+         ("1azp", "lightdock_dna.pdb", "dna", ["B.DT.13"]),
+         ("1azp", "lightdock_dna.pdb", "pydock", ["B.DT.13", "B.XX.99"]),
+         ("1k4c", "lightdock_receptor_membrane.pdb", "dfire", []),
+         ("1k4c", "lightdock_ligand.pdb", "dfire", []),
+         ("1czy", "lightdock_1czy_protein.pdb", "dfire", ["A.SER.467"]),
+         ("1ppe", "lightdock_1ppe_e.pdb", "dfire", ["E.ILE.16"]),
+         ("2uuy", "lightdock_2UUY_lig.pdb", "dfire", []),
+         ("ab_icode", "lightdock_receptor.pdb", "dfire", ["H.ASP.52A", "H.LEU.82C"])]
+
+
+@pytest.mark.parametrize("case,pdb,method,active", CASES)
+def test_model_building_matches_oracle(case, pdb, method, active):
+    """Atom order, DFIRE types / AMBER parameters, restraint groups, membrane beads: bit-exact."""
+    path = os.path.join(GOLDEN, case, pdb)
+    m = host.build_model(path, method, active)
+    om = O.Molecule(O.read_pdb(path), {"dfire": O.DFIRE, "dna": O.DNA, "pydock": O.PYDOCK}[method], active)
+    assert m["n"] == om.n
+    assert np.array_equal(m["coords"], om.coords)
+    if method == "dfire":
+        assert np.array_equal(m["dfire_type"], om.dfire_type)
+    else:
+        assert np.array_equal(m["ele"], om.ele) and np.array_equal(m["vdw_e"], om.vdw_e)
+        assert np.array_equal(m["vdw_r"], om.vdw_r)
+    assert np.array_equal(m["membrane"], om.membrane)
+    # group order may differ (HashMap in the reference: only counts matter) -> compare as sets of tuples
+    def groups(off, idx):
+        return sorted(tuple(idx[off[i]:off[i + 1]]) for i in range(len(off) - 1))
+    assert groups(m["rst_offsets"], m["rst_atoms"]) == groups(om.rst_offsets, om.rst_atoms)
+
+
+def test_membrane_and_icode_cases_are_exercised():
+    m = host.build_model(os.path.join(GOLDEN, "1k4c", "lightdock_receptor_membrane.pdb"), "dfire")
+    assert m["n"] == 3413 and m["membrane"].size == 453 and (m["dfire_type"][m["membrane"]] == 167).all()
+    m = host.build_model(os.path.join(GOLDEN, "ab_icode", "lightdock_receptor.pdb"), "dfire", ["H.ASP.52A", "H.LEU.82C"])
+    assert len(m["rst_offsets"]) - 1 == 2 and m["rst_atoms"].size > 0
+
+
+def test_unsupported_atoms_raise_like_the_reference_panics():
+    with pytest.raises(Exception, match="not supported"):
+        host.build_model(os.path.join(GOLDEN, "1azp", "lightdock_dna.pdb"), "dfire")  # DG is not a DFIRE residue
+    with pytest.raises(Exception, match="not supported"):
+        host.build_model(os.path.join(GOLDEN, "1k4c", "lightdock_receptor_membrane.pdb"), "dna")  # MMB-BJ
+
+
+def test_cli_argument_errors_match_reference(tmp_path):
+    """src/bin/lightdock-rust.rs:91-147: messages on stderr, exit status 0."""
+    cli = host.CLI_PATH
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 0 and "Wrong command line. Usage:" in r.stderr and "setup_filename swarm_filename steps method" in r.stderr
+    r = subprocess.run([cli, "s.json", "initial_positions_0.dat", "ten", "dfire"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stderr.strip() == "Error: steps argument must be a number"
+    r = subprocess.run([cli, "s.json", "initial_positions_0.dat", "10", "zrank"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stderr.strip() == "Error: method not supported"
+    r = subprocess.run([cli, "missing.json", "initial_positions_0.dat", "10", "DFIRE"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stderr.startswith('Error reading setup file ["missing.json"]:')
+    bad = tmp_path / "setup.json"
+    bad.write_text('{"anm_seed": 1}')
+    r = subprocess.run([cli, str(bad), "initial_positions_0.dat", "10", "dna"], capture_output=True, text=True)
+    assert r.returncode == 0 and "missing field" in r.stderr
