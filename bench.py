@@ -1,0 +1,349 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the LightDock scoring hot path on B200.
+
+Metric (BASELINE.json): glowworm poses scored / s (and atom-pair evals / s) on the synthetic
+1k4c-shaped workload: the real 1k4c membrane receptor (3413 atoms incl. 453 MMB beads) and ligand
+(3268 atoms), DFIRE scoring, 400 swarms x 200 glowworms, swarms sharded `s mod G` over the GPUs.
+A "step" is one GSO-step scoring pass: every pose of every swarm owned by the rank is scored by one
+ld_score_batch call.  DFIRE uses the seeded synthetic DCparams unless $LIGHTDOCK_DATA holds a real one.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+`value`   : poses/s with the pose rows already resident in HBM (CUDA events on torch's current stream,
+            the stream the kernels are launched on), whole job = sum over ranks / max time over ranks.
+`e2e`     : the same through the reference-facing C ABI with HOST buffers (ld_score_batch: pinned staging,
+            H2D of the pose rows, kernels, D2H of the energies inside the timed region).
+`roofline`: the dominant kernel (dfire_pair_kernel) against the measured non-fused FP64 rate (SURVEY.md
+            §8d: this path is FP64-pipe bound, not HBM / tensor bound); `achieved` counts the reference's
+            brute-force 8 flops per atom pair, so it exceeds what the GPU executes (tile culling) — the
+            executed fraction is reported beside it.
+`cpu_baseline`: the oracle port (oracle/ld_oracle.c, same scalar f64 loop) on all host cores, bounded sample.
+`--impl reference`: only that CPU arm (the Rust reference cannot be built here: no cargo).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "lightdock-rust_b200"))
+
+N_REC, N_LIG = 3413, 3268
+METRIC, UNIT = "glowworm_poses_scored_per_s", "poses/s"
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def workload_config(args, world):
+    return {"workload": "synthetic 1k4c-sized: real 1k4c receptor (3413 atoms, 453 MMB beads) + ligand (3268 atoms), "
+                        f"DFIRE, {args.swarms} swarms x {args.glowworms} glowworms, every pose rescored each step",
+            "swarms": args.swarms, "glowworms": args.glowworms, "poses_per_step": args.swarms * args.glowworms,
+            "pairs_per_pose": N_REC * N_LIG, "sharding": f"swarm s -> GPU s mod {world}, no collective on the data path",
+            "l2": "flushed between steps (256 MiB memset inside the timed region)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_complex():
+    """CPU baseline leg only: the oracle's model of the same complex."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    from ldb200 import workload
+    pot = workload.synthetic_dcparams()
+    d = os.environ.get("LIGHTDOCK_DATA")
+    if d and os.path.exists(os.path.join(d, "DCparams")):
+        pot = O.load_dcparams(os.path.join(d, "DCparams"))
+    cx, _, _, _ = O.load_case(os.path.join(ROOT, "tests", "golden", "1k4c"), O.DFIRE, potential=pot)
+    return cx
+
+
+def cpu_rate(cx, poses, cores, target_s):
+    """poses/s of the oracle on `cores` threads over a bounded sample of ~target_s seconds."""
+    n0 = min(len(poses), cores * 4)
+    t = time.perf_counter()
+    cx.energy_mt(poses[:n0], cores)
+    dt = time.perf_counter() - t
+    n = int(min(len(poses), max(cores * 4, (n0 / dt) * target_s)))
+    n -= n % cores
+    t = time.perf_counter()
+    cx.energy_mt(poses[:n], cores)
+    dt = time.perf_counter() - t
+    return n / dt, n, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm's CPU implementation (oracle port) on all host cores."""
+    if rank != 0:
+        return
+    from ldb200 import workload
+    cores = host_cores()
+    cx = oracle_complex()
+    poses = workload.synthetic_1k4c_swarms(args.swarms, args.glowworms).reshape(-1, 7)
+    rng = np.random.default_rng(1)
+    poses = poses[rng.permutation(len(poses))]
+    per_step = cores * 24  # bounded sample of the workload per step (~0.3 s of work per core)
+    for w in range(args.warmup):
+        cx.energy_mt(poses[w * per_step:(w + 1) * per_step], cores)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        o = ((args.warmup + k) * per_step) % (len(poses) - per_step)
+        cx.energy_mt(poses[o:o + per_step], cores)
+    dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = f"{per_step} poses/step ({cores} threads x 24) drawn from the same {len(poses)}-pose workload"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "pair_evals_per_s": value * N_REC * N_LIG,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle/ld_oracle.c port of the reference's scalar f64 loop, one thread per host core; the Rust "
+                "reference itself cannot be built in this image (no cargo/rustc)"}))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def summary(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 <= ts <= t1 + 0.2):
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import ldb200
+    from ldb200 import host, workload
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = ldb200.load_library()
+
+    dc_dir, table_kind = workload.ensure_dcparams_dir(tempfile.gettempdir())
+    os.environ["LIGHTDOCK_DATA"] = dc_dir
+    case = host.Case(os.path.join(workload.GOLDEN_1K4C, "setup.json"), "dfire", device=local_rank)
+    assert (case.n_rec, case.n_lig, case.pose_len) == (N_REC, N_LIG, 7)
+    h = case.ld_handle()
+
+    mine = workload.shard_swarms(args.swarms, rank, world)
+    all_poses = workload.synthetic_1k4c_swarms(args.swarms, args.glowworms)
+    poses = np.ascontiguousarray(all_poses[mine].reshape(-1, 7))
+    n_local = poses.shape[0]
+    n_total = args.swarms * args.glowworms
+    dev = torch.device("cuda", local_rank)
+    d_poses = torch.from_numpy(poses).to(dev)
+    d_energy = torch.zeros(n_local, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # a real (non-NULL) stream: the C ABI reads a NULL stream as "use the handle's own stream", and the
+    # CUDA events below must sit on the stream the kernels are launched on
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    stream = work_stream.cuda_stream
+    assert stream != 0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_device():
+        flush.zero_()
+        ldb200._check(lib, lib.ld_score_batch_device(h, n_local, d_poses.data_ptr(), d_energy.data_ptr(), stream))
+
+    # ---- device-resident throughput (`value`) --------------------------------------------------
+    for _ in range(args.warmup):
+        step_device()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.3)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    clk = clocks.summary(t_wall0, t_wall1) if clocks else None
+    launches_per_step = ldb200.handle_stats(lib, h)["kernel_launches"]
+    value = n_total * args.steps / (ms_total * 1e-3)
+    e_dev = d_energy.cpu().numpy()
+
+    # ---- per-kernel time of the same step (events inside the library, same stream) -------------
+    lib.ld_set_profiling(h, 1)
+    pair_ms = tr_ms = fin_ms = 0.0
+    for _ in range(args.steps):
+        step_device()
+        st = ldb200.handle_stats(lib, h)
+        pair_ms += st["pair_ms"]; tr_ms += st["transform_ms"]; fin_ms += st["finalize_ms"]
+    lib.ld_set_profiling(h, 0)
+    pair_launches = (launches_per_step // 3) * args.steps
+    pair_ms_step = max_over_ranks(pair_ms / args.steps)
+
+    # ---- end to end through the C ABI with host buffers (`e2e`) --------------------------------
+    e_host = np.empty(n_local)
+    for _ in range(min(args.warmup, 3)):
+        ldb200._check(lib, lib.ld_score_batch(h, n_local, poses.ctypes.data, e_host.ctypes.data))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        ldb200._check(lib, lib.ld_score_batch(h, n_local, poses.ctypes.data, e_host.ctypes.data))
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = n_total * args.steps / e2e_s
+    if not np.array_equal(e_host, e_dev):
+        raise SystemExit("bench.py: host-buffer and device-buffer paths disagree")
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- executed work (culling) on a sample, outside the timed region -------------------------
+    sample = poses[:: max(1, n_local // 256)][:256]
+    det = (ldb200.PoseDetail * len(sample))()
+    es = np.empty(len(sample))
+    ldb200._check(lib, lib.ld_score_batch_detail(h, len(sample), np.ascontiguousarray(sample).ctypes.data,
+                                                 es.ctypes.data, det, None, None))
+    tested = np.mean([d.n_pairs_tested for d in det]) / (N_REC * N_LIG)
+    in_cut = np.mean([d.n_in_cutoff for d in det]) / (N_REC * N_LIG)
+
+    # ---- roofline denominators measured on this box ---------------------------------------------
+    fp64_tf, fp32_tf, gather_g = ldb200.probe_peaks(local_rank)
+    pairs_per_rank_step = n_local * N_REC * N_LIG
+    achieved_tf = 8.0 * pairs_per_rank_step / (pair_ms_step * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    # algorithmic HBM bytes per pose: ligand block written once + read once, pose row in, energy out
+    lig_block = (3272 * 40 + 409 * 16 + 16)
+    hbm_bytes = n_local * (2 * lig_block + 56 + 8)
+    roofline = {
+        "bound": "fp64", "kernel": "dfire_pair_kernel", "achieved": achieved_tf, "peak": fp64_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / fp64_tf, "traffic": None,
+        "peak_source": "ld_probe_peaks: non-fused DADD+DMUL rate measured on this GPU (MEASURED_PEAKS.json has no "
+                       "FP64 figure; SURVEY.md 8d)",
+        "algorithmic_flops_per_pair": 8, "pair_kernel_ms_per_step": pair_ms_step,
+        "pair_kernel_launches_timed": pair_launches,
+        "executed_pair_test_fraction": tested, "in_cutoff_fraction": in_cut,
+        "executed_frac_of_fp64_peak": achieved_tf * tested / fp64_tf,
+        "note": "achieved counts the reference's brute-force loop (8 FP64 flops x N_rec x N_lig per pose); the kernel "
+                "culls tile pairs with an FP32 sphere test and executes only `executed_pair_test_fraction` of them, "
+                "so frac > 1 is pruning, not missing work",
+        "gather": {"gloads_per_s": in_cut * pairs_per_rank_step / (pair_ms_step * 1e-3) / 1e9,
+                   "peak_gloads_per_s": gather_g},
+        "hbm": {"achieved_gbs": hbm_bytes / ((ms_total / args.steps) * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+        "fp32_nonfma_tflops_measured": fp32_tf,
+        "share_of_step": {"transform": tr_ms / (tr_ms + pair_ms + fin_ms), "pair": pair_ms / (tr_ms + pair_ms + fin_ms),
+                          "finalize": fin_ms / (tr_ms + pair_ms + fin_ms)}}
+
+    # ---- CPU baseline (oracle port on this box's host cores, bounded sample) -------------------
+    cores = host_cores()
+    cpu = None
+    if not args.no_cpu_baseline:
+        cx = oracle_complex()
+        rate, n_cpu, dt = cpu_rate(cx, np.ascontiguousarray(all_poses.reshape(-1, 7)[:: max(1, n_total // 8192)]),
+                                   cores, args.cpu_seconds)
+        e_cpu = cx.energy(poses[:8])
+        rel = np.max(np.abs(e_cpu - e_dev[:8]) / np.abs(e_cpu))
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_cpu} poses of the same workload in {dt:.1f} s on {cores} threads (oracle/ld_oracle.c)",
+               "pair_evals_per_s": rate * N_REC * N_LIG, "gpu_vs_oracle_max_rel_err_8_poses": float(rel)}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": f"synthetic swarms on the real 1k4c structures; DCparams {table_kind}",
+           "config": workload_config(args, world), "pair_evals_per_s": value * N_REC * N_LIG,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * 7 * 8,
+                   "d2h_bytes_per_step": n_local * 8, "ms_per_step": e2e_s / args.steps * 1e3,
+                   "api": "ld_score_batch (C ABI, host buffers)"},
+           "gpu_launches": launches_per_step * args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--swarms", type=int, default=400)
+    ap.add_argument("--glowworms", type=int, default=200)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,9 @@ typedef struct ld_pose_detail {
   int32_t lig_rst_hit;
   int32_t membrane_hit;        /* beads at the interface (src/scoring.rs:38-47)                   */
   int32_t reserved;
+  int64_t n_pairs_tested;      /* atom-pair distance tests the GPU executed (after tile culling)   */
+  int64_t n_exact_fallback;    /* DFIRE: pairs too close to a decision threshold for the FP32
+                                  classification, re-evaluated in exact FP64                       */
 } ld_pose_detail;
 
 /* Work counters of the last ld_score_batch* call (what the GPU actually executed). */
@@ -93,6 +96,9 @@ typedef struct ld_batch_stats {
   int32_t kernel_launches;       /* CUDA kernels launched by the call                             */
   int32_t rec_splits;            /* receptor tile ranges per pose (CTAs per pose)                 */
   double device_ms;              /* device time of the call (CUDA events); host-buffer calls only */
+  /* per-kernel device time of the last call, filled only while profiling is on (ld_set_profiling)
+   * and read back by ld_get_stats, which synchronises the stream the call used */
+  double transform_ms, pair_ms, finalize_ms;
 } ld_batch_stats;
 
 typedef struct ld_handle ld_handle;
@@ -126,10 +132,20 @@ int ld_score_batch_detail(ld_handle *h, int64_t n_poses, const double *poses, do
 int ld_transform_batch(ld_handle *h, int64_t n_poses, const double *poses, double *rec_coords,
                        double *lig_coords);
 
-int ld_get_stats(const ld_handle *h, ld_batch_stats *out);
+int ld_get_stats(ld_handle *h, ld_batch_stats *out);
 
 /* Tuning knob for benchmarks/tests: force the number of receptor splits (0 = automatic). */
 int ld_set_rec_splits(ld_handle *h, int32_t splits);
+
+/* Brackets every kernel launch with CUDA events on the launching stream (bench.py's roofline leg). */
+int ld_set_profiling(ld_handle *h, int32_t on);
+
+/* On-box micro-benchmarks for the roofline denominators SURVEY.md §8(d) asks for (MEASURED_PEAKS.json
+ * has no FP64 / L2-gather figure): sustained non-fused FP64 add+mul rate in TFLOP/s, FP32 FMA-free
+ * rate in TFLOP/s, and random 8-byte gather rate from a DFIRE-table-sized (4.57 MB) L2-resident
+ * window in G loads/s. */
+int ld_probe_peaks(int32_t device, double *fp64_nonfma_tflops, double *fp32_nonfma_tflops,
+                   double *l2_gather_gloads);
 
 const char *ld_last_error(void);
 const char *ld_version(void);

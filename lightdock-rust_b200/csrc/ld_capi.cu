@@ -58,6 +58,11 @@ struct ld_handle {
   int max_smem_optin = 0;
   int sm_count = 0;
   ld_batch_stats stats{};
+  // profiling: events bracketing every kernel of the last call (4 per chunk)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  size_t prof_used = 0;
+  cudaStream_t last_stream = nullptr;
 };
 
 template <typename T>
@@ -190,6 +195,7 @@ extern "C" int ld_destroy(ld_handle *h) {
   cudaFree(h->d_lig_blocks); cudaFree(h->d_rec_blocks); cudaFree(h->d_partials);
   cudaFree(h->d_iface_rec); cudaFree(h->d_iface_lig);
   cudaFreeHost(h->h_poses); cudaFreeHost(h->h_energies);
+  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -251,13 +257,18 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
   for (int t = 0; t < R.n_tiles; ++t)
     sph[t] = tile_sphere(R.x.data(), R.y.data(), R.z.data(), t * REC_TILE, std::min((t + 1) * REC_TILE, R.n));
   UP(sph, rec_sphere);
+  {
+    double mx = 0.0;
+    for (int i = 0; i < R.n; ++i) mx = std::max(mx, std::max(std::fabs(R.x[i]), std::max(std::fabs(R.y[i]), std::fabs(R.z[i]))));
+    cx.rec_maxabs = (float)(mx * 1.0001 + 1.0);
+  }
   if (method == 0) {
     std::vector<double> pot(desc->dfire_potential, desc->dfire_potential + LD_DFIRE_TABLE_LEN);
     UP(pot, pot);
   }
 #undef UP
-  h->lig_block = block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
-  h->rec_block = nrm > 0 ? block_bytes(cx.n_rec_pad, cx.n_rec_tiles) : 0;
+  h->lig_block = lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  h->rec_block = nrm > 0 ? rec_block_bytes(cx.n_rec_pad, cx.n_rec_tiles) : 0;
   if (h->lig_block >= (1u << 20)) return fail(LD_ELIMIT, "ligand too large for one bulk copy");
 
   // the pair kernels need opt-in dynamic shared memory; check the worst case (one split) fits
@@ -304,9 +315,40 @@ extern "C" int ld_set_rec_splits(ld_handle *h, int32_t splits) {
   return LD_OK;
 }
 
-extern "C" int ld_get_stats(const ld_handle *h, ld_batch_stats *out) {
+extern "C" int ld_set_profiling(ld_handle *h, int32_t on) {
+  if (!h) return fail(LD_EINVAL, "ld_set_profiling: NULL handle");
+  h->profiling = on != 0;
+  return LD_OK;
+}
+
+extern "C" int ld_get_stats(ld_handle *h, ld_batch_stats *out) {
   if (!h || !out) return fail(LD_EINVAL, "ld_get_stats: NULL argument");
+  if (h->profiling && h->prof_used >= 4) {
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->last_stream));
+    double t[3] = {0, 0, 0};
+    for (size_t c = 0; c + 4 <= h->prof_used; c += 4)
+      for (int k = 0; k < 3; ++k) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, h->prof_events[c + k], h->prof_events[c + k + 1]));
+        t[k] += ms;
+      }
+    h->stats.transform_ms = t[0];
+    h->stats.pair_ms = t[1];
+    h->stats.finalize_ms = t[2];
+  }
   *out = h->stats;
+  return LD_OK;
+}
+
+static int prof_mark(ld_handle *h, cudaStream_t st) {
+  if (!h->profiling) return LD_OK;
+  if (h->prof_used == h->prof_events.size()) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    h->prof_events.push_back(e);
+  }
+  CU(cudaEventRecord(h->prof_events[h->prof_used++], st));
   return LD_OK;
 }
 
@@ -384,6 +426,8 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
   h->stats = ld_batch_stats{};
   h->stats.n_poses = n;
   h->stats.pair_evals_bruteforce = n * (int64_t)cx.n_rec * (int64_t)cx.n_lig;
+  h->prof_used = 0;
+  h->last_stream = st;
   if (n == 0) return LD_OK;
   const int64_t climit = chunk_limit(h);
   const int lig_words = (cx.n_lig_pad + 31) / 32;
@@ -407,8 +451,10 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
     bb.tiles_per_split = (std::max(1, cx.n_rec_tiles) + splits - 1) / splits;
     bb.lig_words = lig_words;
     h->stats.rec_splits = splits;
+    if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     transform_kernel<<<(unsigned)nc, 256, 0, st>>>(cx, bb, (int)nc);
     ++launches;
+    if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     if (cx.n_rec_tiles > 0) {
       const size_t smem = pair_smem_bytes(cx.method, cx.n_lig_pad, cx.n_lig_tiles, lig_words, bb.tiles_per_split);
       const unsigned grid = (unsigned)(nc * splits);
@@ -424,10 +470,12 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       
       CU(cudaMemsetAsync(h->d_iface_lig, 0, (size_t)nc * splits * std::max(1, lig_words) * sizeof(unsigned), st));
     }
+    if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     const unsigned fgrid = (unsigned)((nc + 3) / 4);
     if (detail) finalize_kernel<true><<<fgrid, 128, 0, st>>>(cx, bb, (int)nc);
     else finalize_kernel<false><<<fgrid, 128, 0, st>>>(cx, bb, (int)nc);
     ++launches;
+    if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     CU(cudaGetLastError());
     if (host_ifr) {
       // detail mode: fetch this chunk's bitmaps (OR over splits for the ligand) before they are overwritten

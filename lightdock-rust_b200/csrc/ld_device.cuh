@@ -8,9 +8,15 @@
 //     DFIRE column offset (type*20, u16) or DNA parameters.
 //   ANM modes re-ordered to [mode][xyz][sorted atom] so a warp reads them coalesced.
 //   DFIRE potential: 571,220 f64 (4.57 MB) — stays resident in the 126 MB L2.
-// Per batch: one "ligand block" per pose (transformed SoA f64 coordinates + tile spheres, contiguous,
-//   16-byte aligned) written by the transform kernel and pulled into shared memory by the pair kernel
-//   with ONE cp.async.bulk (TMA) copy; a "receptor block" per pose only when receptor ANM is active.
+// Per batch: one "ligand block" per pose written by the transform kernel (16-byte aligned, contiguous):
+//     [x f64][y f64][z f64]  exact transformed coordinates (n_lig_pad each)
+//     [float4 xyzt]          the same coordinates rounded to f32 + the DFIRE column offset (type*20) as int bits
+//     [float4 sphere]        one conservative bounding sphere per ligand tile
+//     [float4 meta]          meta.x = max |coordinate| of the pose's ligand (sets the rigorous f32 margins)
+//   The pair kernels pull the part they need into shared memory with cp.async.bulk (TMA) copies:
+//   DFIRE takes [xyzt|sphere|meta] (its f64 coordinates are touched only by the rare exact fallback, from
+//   L2), DNA takes [x|y|z] and [sphere|meta].  A "receptor block" ([x][y][z][sphere][meta]) exists per
+//   pose only when receptor ANM is active.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,6 +42,7 @@ struct DeviceComplex {
   const int *rec_toff;                      // DFIRE: type * 3380
   const double *rec_q, *rec_eps, *rec_rad;  // DNA
   const float4 *rec_sphere;                 // static tile spheres (used when n_rec_modes == 0)
+  float rec_maxabs;                         // max |coordinate| of the static receptor
   const double *rec_modes;                  // [k][3][n_rec_pad]
   // ligand (sorted order, local frame)
   const double *lig_x, *lig_y, *lig_z;
@@ -48,9 +55,14 @@ struct DeviceComplex {
   const int *rec_rst_off, *rec_rst_idx, *lig_rst_off, *lig_rst_idx, *membrane_idx;
 };
 
-// bytes of one transformed-coordinate block: x,y,z f64 [n_pad] followed by float4 spheres [n_tiles]
-__host__ __device__ inline size_t block_bytes(int n_pad, int n_tiles) {
-  return (size_t)n_pad * 24 + (size_t)n_tiles * 16;
+// byte offsets inside one ligand block
+__host__ __device__ inline size_t lig_off_f4(int n_pad) { return (size_t)n_pad * 24; }
+__host__ __device__ inline size_t lig_off_sph(int n_pad) { return (size_t)n_pad * 40; }
+__host__ __device__ inline size_t lig_off_meta(int n_pad, int n_tiles) { return (size_t)n_pad * 40 + (size_t)n_tiles * 16; }
+__host__ __device__ inline size_t lig_block_bytes(int n_pad, int n_tiles) { return lig_off_meta(n_pad, n_tiles) + 16; }
+// receptor block (ANM only): x,y,z f64 [n_pad], float4 spheres [n_tiles], float4 meta
+__host__ __device__ inline size_t rec_block_bytes(int n_pad, int n_tiles) {
+  return (size_t)n_pad * 24 + (size_t)n_tiles * 16 + 16;
 }
 
 struct BatchBuffers {

@@ -104,8 +104,15 @@ __host__ __device__ inline float4 tile_sphere(const double *x, const double *y, 
 }
 
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
 // Kernel 1: pose transform.  grid = poses, block = 256.
 __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
+  __shared__ float s_max[2][8];
   const int p = blockIdx.x;
   if (p >= n_poses) return;
   const double *pose = bb.poses + (size_t)p * cx.pose_len;
@@ -118,11 +125,15 @@ __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, 
   const double *rec_ext = pose + 7;
   const double *lig_ext = pose + 7 + cx.n_rec_modes;
 
-  unsigned char *lb = bb.lig_blocks + (size_t)p * block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  unsigned char *lb = bb.lig_blocks + (size_t)p * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
   double *ox = reinterpret_cast<double *>(lb), *oy = ox + cx.n_lig_pad, *oz = oy + cx.n_lig_pad;
-  float4 *osph = reinterpret_cast<float4 *>(oz + cx.n_lig_pad);
+  float4 *of4 = reinterpret_cast<float4 *>(lb + lig_off_f4(cx.n_lig_pad));
+  float4 *osph = reinterpret_cast<float4 *>(lb + lig_off_sph(cx.n_lig_pad));
+  float4 *ometa = reinterpret_cast<float4 *>(lb + lig_off_meta(cx.n_lig_pad, cx.n_lig_tiles));
+  float lmax = 0.f, rmax = 0.f;
   for (int i = threadIdx.x; i < cx.n_lig_pad; i += blockDim.x) {
     double x = LIG_PAD, y = LIG_PAD, z = LIG_PAD;
+    int tb = 0;
     if (i < cx.n_lig) {
       // rotate(): self * (0, v) * self.inverse(), src/qt.rs:57-61
       const Quat v = {0.0, cx.lig_x[i], cx.lig_y[i], cx.lig_z[i]};
@@ -137,15 +148,19 @@ __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, 
         y = __dadd_rn(y, __dmul_rn(m[cx.n_lig_pad + i], e));
         z = __dadd_rn(z, __dmul_rn(m[2 * cx.n_lig_pad + i], e));
       }
+      lmax = fmaxf(lmax, fmaxf(fabsf((float)x), fmaxf(fabsf((float)y), fabsf((float)z))));
+      if (cx.method == 0) tb = cx.lig_tb20[i];
     }
     ox[i] = x; oy[i] = y; oz[i] = z;
+    of4[i] = make_float4((float)x, (float)y, (float)z, __int_as_float(tb));
   }
   double *rx = nullptr, *ry = nullptr, *rz = nullptr;
-  float4 *rsph = nullptr;
+  float4 *rsph = nullptr, *rmeta = nullptr;
   if (cx.n_rec_modes > 0) {  // src/dfire.rs:304-320
-    unsigned char *rb = bb.rec_blocks + (size_t)p * block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
+    unsigned char *rb = bb.rec_blocks + (size_t)p * rec_block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
     rx = reinterpret_cast<double *>(rb); ry = rx + cx.n_rec_pad; rz = ry + cx.n_rec_pad;
     rsph = reinterpret_cast<float4 *>(rz + cx.n_rec_pad);
+    rmeta = rsph + cx.n_rec_tiles;
     for (int i = threadIdx.x; i < cx.n_rec_pad; i += blockDim.x) {
       double x = cx.rec_x[i], y = cx.rec_y[i], z = cx.rec_z[i];
       if (i < cx.n_rec) {
@@ -156,11 +171,22 @@ __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, 
           y = __dadd_rn(y, __dmul_rn(m[cx.n_rec_pad + i], e));
           z = __dadd_rn(z, __dmul_rn(m[2 * cx.n_rec_pad + i], e));
         }
+        rmax = fmaxf(rmax, fmaxf(fabsf((float)x), fmaxf(fabsf((float)y), fabsf((float)z))));
       }
       rx[i] = x; ry[i] = y; rz[i] = z;
     }
   }
-  __syncthreads();  // block-scope visibility of the coordinates just written
+  lmax = warp_max_f(lmax);
+  rmax = warp_max_f(rmax);
+  if ((threadIdx.x & 31) == 0) { s_max[0][threadIdx.x >> 5] = lmax; s_max[1][threadIdx.x >> 5] = rmax; }
+  __syncthreads();  // block-scope visibility of the coordinates just written + the per-warp maxima
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a = fmaxf(a, s_max[0][w]); b = fmaxf(b, s_max[1][w]); }
+    // inflate: the f32 conversions above round to nearest
+    *ometa = make_float4(a * 1.0001f + 1.0f, 0.f, 0.f, 0.f);
+    if (rmeta) *rmeta = make_float4(b * 1.0001f + 1.0f, 0.f, 0.f, 0.f);
+  }
   for (int t = threadIdx.x; t < cx.n_lig_tiles; t += blockDim.x) {
     const int a = t * LIG_TILE, b = min(a + LIG_TILE, cx.n_lig);
     osph[t] = tile_sphere(ox, oy, oz, a, b);
@@ -174,25 +200,39 @@ __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, 
 
 // ---------------------------------------------------------------------------------------------
 // shared-memory carve-up of the pair kernels
+//   [0,8) mbarrier | [8,12) next-tile counter | [16,48) 4 u64 detail counters | [48,144) 24 u32 histogram
+//   [144, ...)   TMA destination(s): DFIRE float4 xyzt[n_lig_pad] + spheres + meta ; DNA x,y,z f64 + spheres + meta
+//   DNA only:    ligand charge / eps / radius (f64 each)
+//   iface_lig bitmap | per-tile sums | DFIRE: per-warp work-item rings (64 u32 each)
 struct PairSmem {
   uint64_t *bar;
   int *next_tile;
-  unsigned long long *counters;  // detail: [0]=n_in_cutoff [1]=n_in_cutoff2 [2]=n_iface_pairs
+  unsigned long long *counters;  // detail: [0]=n_in_cutoff [1]=n_in_cutoff2 / ambiguous [2]=n_iface_pairs [3]=pairs tested
   unsigned *hist;                // detail: 21 bins (+pad)
-  double *lx, *ly, *lz;
-  float4 *lsph;
-  unsigned char *lig_static;  // DFIRE: u16 tb20[n_lig_pad]; DNA: f64 q,eps,rad [n_lig_pad] each
-  unsigned *iface_lig;        // [lig_words]
-  double *tile_sum;           // [tiles_per_split] (x2 for DNA)
+  unsigned char *tma;            // start of the TMA-filled region
+  const float4 *l4;              // DFIRE: f32 coordinates + type*20 bits
+  const double *lx, *ly, *lz;    // DNA: exact coordinates
+  const float4 *lsph;
+  const float4 *lmeta;
+  double *lig_static;            // DNA: q, eps, rad
+  unsigned *iface_lig;           // [lig_words]
+  double *tile_sum;              // [tiles_per_split] (x2 for DNA)
+  unsigned *rings;               // DFIRE: [warps][64]
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+constexpr int RING = 64;
 __host__ __device__ inline size_t pair_smem_bytes(int method, int n_lig_pad, int n_lig_tiles, int lig_words,
                                                   int tiles_per_split) {
-  size_t o = 16 + 32 + 96;  // barrier+counter, 3 u64 counters (+pad), 24 u32 histogram
-  o += block_bytes(n_lig_pad, n_lig_tiles);
-  o += align16(method == 0 ? (size_t)n_lig_pad * 2 : (size_t)n_lig_pad * 24);
+  size_t o = 144;
+  if (method == 0) {
+    o += (size_t)n_lig_pad * 16 + (size_t)n_lig_tiles * 16 + 16;
+  } else {
+    o += (size_t)n_lig_pad * 24 + (size_t)n_lig_tiles * 16 + 16;
+    o += (size_t)n_lig_pad * 24;
+  }
   o += align16((size_t)lig_words * 4);
   o += align16((size_t)tiles_per_split * 8 * (method == 0 ? 1 : 2));
+  if (method == 0) o += (size_t)(PAIR_THREADS / 32) * RING * 4;
   return o;
 }
 __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceComplex &cx, const BatchBuffers &bb) {
@@ -202,16 +242,30 @@ __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceCompl
   s.counters = reinterpret_cast<unsigned long long *>(base + 16);
   s.hist = reinterpret_cast<unsigned *>(base + 48);
   unsigned char *o = base + 144;
-  s.lx = reinterpret_cast<double *>(o);
-  s.ly = s.lx + cx.n_lig_pad;
-  s.lz = s.ly + cx.n_lig_pad;
-  s.lsph = reinterpret_cast<float4 *>(s.lz + cx.n_lig_pad);
-  o += block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
-  s.lig_static = o;
-  o += align16(cx.method == 0 ? (size_t)cx.n_lig_pad * 2 : (size_t)cx.n_lig_pad * 24);
+  s.tma = o;
+  s.l4 = nullptr; s.lx = s.ly = s.lz = nullptr; s.lig_static = nullptr; s.rings = nullptr;
+  if (cx.method == 0) {
+    s.l4 = reinterpret_cast<const float4 *>(o);
+    o += (size_t)cx.n_lig_pad * 16;
+  } else {
+    s.lx = reinterpret_cast<const double *>(o);
+    s.ly = s.lx + cx.n_lig_pad;
+    s.lz = s.ly + cx.n_lig_pad;
+    o += (size_t)cx.n_lig_pad * 24;
+  }
+  s.lsph = reinterpret_cast<const float4 *>(o);
+  o += (size_t)cx.n_lig_tiles * 16;
+  s.lmeta = reinterpret_cast<const float4 *>(o);
+  o += 16;
+  if (cx.method != 0) {
+    s.lig_static = reinterpret_cast<double *>(o);
+    o += (size_t)cx.n_lig_pad * 24;
+  }
   s.iface_lig = reinterpret_cast<unsigned *>(o);
   o += align16((size_t)bb.lig_words * 4);
   s.tile_sum = reinterpret_cast<double *>(o);
+  o += align16((size_t)bb.tiles_per_split * 8 * (cx.method == 0 ? 1 : 2));
+  if (cx.method == 0) s.rings = reinterpret_cast<unsigned *>(o);
   return s;
 }
 
@@ -226,19 +280,18 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
   return v;
 }
 
-// DIST_TO_BINS[idx] - 1 for idx 0..29 (src/dfire.rs:49-53,337), packed 5 bits per entry.
+// DIST_TO_BINS[idx] - 1 for idx 0..29 (src/dfire.rs:49-53,337).
 // idx: 0 1 2 3 4 ... 15 | 16 17 18 19 20 21 22 23 24 25 26 27 28 29
 // bin: 0 0 0 1 2 ... 13 | 13 14 14 15 15 16 16 17 17 18 18 19 19 20
 __device__ __forceinline__ int dfire_bin_of(int idx) {
   return idx <= 2 ? 0 : (idx <= 15 ? idx - 2 : 13 + ((idx - 15) >> 1));
 }
 
-// Common prologue: stage the ligand block (TMA) and the static ligand data, zero the bitmaps.
+// Common prologue: stage the pose's ligand data (TMA) and the static ligand data, zero the bitmaps.
 template <int METHOD>
 __device__ __forceinline__ void pair_prologue(const DeviceComplex &cx, const BatchBuffers &bb, const PairSmem &s,
                                               int pose, int n_tiles_here) {
   const int tid = threadIdx.x;
-  const uint32_t lig_bytes = (uint32_t)block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
   if (tid == 0) {
     mbar_init(s.bar, 1);
     fence_mbar_init();
@@ -246,28 +299,136 @@ __device__ __forceinline__ void pair_prologue(const DeviceComplex &cx, const Bat
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(s.bar, lig_bytes);
-    bulk_g2s(s.lx, bb.lig_blocks + (size_t)pose * lig_bytes, lig_bytes, s.bar);
+    const unsigned char *lb = bb.lig_blocks + (size_t)pose * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+    const uint32_t tail = (uint32_t)(cx.n_lig_tiles * 16 + 16);  // spheres + meta
+    if (METHOD == 0) {
+      const uint32_t bytes = (uint32_t)cx.n_lig_pad * 16 + tail;
+      mbar_expect_tx(s.bar, bytes);
+      bulk_g2s(s.tma, lb + lig_off_f4(cx.n_lig_pad), bytes, s.bar);  // xyzt | spheres | meta are contiguous
+    } else {
+      const uint32_t xyz = (uint32_t)cx.n_lig_pad * 24;
+      mbar_expect_tx(s.bar, xyz + tail);
+      bulk_g2s(s.tma, lb, xyz, s.bar);
+      bulk_g2s(s.tma + xyz, lb + lig_off_sph(cx.n_lig_pad), tail, s.bar);
+    }
   }
-  if (METHOD == 0) {
-    unsigned short *tb = reinterpret_cast<unsigned short *>(s.lig_static);
-    for (int i = tid; i < cx.n_lig_pad; i += blockDim.x) tb[i] = cx.lig_tb20[i];
-  } else {
-    double *lq = reinterpret_cast<double *>(s.lig_static), *le = lq + cx.n_lig_pad, *lr = le + cx.n_lig_pad;
+  if (METHOD != 0) {
+    double *lq = s.lig_static, *le = lq + cx.n_lig_pad, *lr = le + cx.n_lig_pad;
     for (int i = tid; i < cx.n_lig_pad; i += blockDim.x) {
       lq[i] = cx.lig_q[i]; le[i] = cx.lig_eps[i]; lr[i] = cx.lig_rad[i];
     }
   }
   for (int i = tid; i < bb.lig_words; i += blockDim.x) s.iface_lig[i] = 0u;
   for (int i = tid; i < n_tiles_here * (METHOD == 0 ? 1 : 2); i += blockDim.x) s.tile_sum[i] = 0.0;
-  if (tid < 3) s.counters[tid] = 0ull;
+  if (tid < 4) s.counters[tid] = 0ull;
   if (tid < 24) s.hist[tid] = 0u;
   __syncthreads();
   mbar_wait(s.bar, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Kernel 2a: DFIRE pair loop, src/dfire.rs:325-345.
+// Kernel 2a: DFIRE pair loop, src/dfire.rs:325-345 — three culling levels, then an FP32 classification
+// that is PROVABLY equal to the reference's FP64 decisions, with an exact FP64 fallback for the rest:
+//   A. warp tile (32 receptor atoms) x 32 ligand tiles at a time: sphere-sphere test, one ligand tile per lane;
+//   B. every lane tests ITS atom against each surviving ligand-tile sphere; (atom, tile) hits are compacted
+//      (ballot + popc) into a warp-private ring of work items in shared memory;
+//   C. whenever 32 items are queued each lane takes one: the atom's f32 coordinates come from the owning
+//      lane by shuffle, the tile's 8 ligand atoms from shared memory (rotated start so lanes hit different
+//      banks), distance^2 in FP32.  |d2f - dist_f64| <= delta (bound below), so if d2f is further than
+//      delta from every decision threshold (the 29 bin edges ((k+1)/2)^2, the 225 cut-off, the 6.0025
+//      interface edge) the bin / cut-off / interface decisions taken on d2f are exactly the reference's.
+//      Otherwise (~0.1 % of in-range pairs) the pair is re-evaluated in exact never-fused FP64 from the
+//      coordinates in global memory.  The table value is gathered as f64 and accumulated in f64.
+// Error bound: coordinates are rounded to f32 (<= 2^-24*M each, M = max |coordinate|), the difference and
+// the 3-term sum add <= 4 ulp_f32 of d2f:  |d2f - dist| <= 2*sqrt(3*240)*2^-23*M + 5*2^-24*240 + fp64 noise
+// < 6.4e-6*M + 8e-5.  delta = 2e-5*M + 5e-4 leaves a 3x margin.
+// Exact fallback for one pair: the reference's arithmetic, src/dfire.rs:331-342, from the f64 coordinates in
+// global memory.  Returns -1 if the pair is outside the cut-off, else bin | (interface ? 32 : 0).
+// Deliberately not inlined: it runs for ~0.1 % of the in-range pairs and must not bloat the hot loop.
+__device__ __noinline__ int dfire_exact_pair(const double *gx, const double *gy, const double *gz, const double *glx,
+                                             const double *gly, const double *glz, int ia, int j) {
+  const double ex = __dsub_rn(gx[ia], glx[j]), ey = __dsub_rn(gy[ia], gly[j]), ez = __dsub_rn(gz[ia], glz[j]);
+  const double dist = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+  if (!(dist <= 225.0)) return -1;
+  const double d = __dsub_rn(__dmul_rn(__dsqrt_rn(dist), 2.0), 1.0);
+  const int bin = dfire_bin_of((int)d);  // `d as usize`: truncation, d in (-1, 29]
+  return bin | (d <= 3.9 ? 32 : 0);      // INTERFACE_CUTOFF on the bin-space value, src/dfire.rs:339
+}
+
+template <bool DETAIL>
+__device__ __forceinline__ void dfire_items(const PairSmem &s, const unsigned *ring, int head, int n_active,
+                                            float rxf, float ryf, float rzf, int toff, int tile_base,
+                                            const double *gx, const double *gy, const double *gz,
+                                            const double *glx, const double *gly, const double *glz,
+                                            const double *__restrict__ pot, float delta, int n_lig, double &acc0,
+                                            double &acc1, unsigned &ifr_mask, unsigned &n_in, unsigned &n_if,
+                                            unsigned &n_tested, unsigned &n_amb) {
+  const int lane = threadIdx.x & 31;
+  const bool active = lane < n_active;
+  unsigned item = active ? ring[(head + lane) & (RING - 1)] : (unsigned)(lane << 16);
+  const int i = item >> 16, lt = item & 0xffffu;
+  const float ax = __shfl_sync(0xffffffffu, rxf, i), ay = __shfl_sync(0xffffffffu, ryf, i),
+              az = __shfl_sync(0xffffffffu, rzf, i);
+  const int at = __shfl_sync(0xffffffffu, toff, i);
+  if (!active) return;
+  const float thr_out = 225.0f + delta;
+  if (DETAIL) n_tested += min(LIG_TILE, n_lig - lt * LIG_TILE);
+  // pass 1: classify the 8 pairs (no table access yet); pass 2: issue the 8 gathers back to back so they
+  // are all in flight together; pass 3: accumulate.  Pairs that are out contribute +0.0 (exact no-op).
+  int addr[LIG_TILE];
+#pragma unroll
+  for (int k = 0; k < LIG_TILE; ++k) {
+    const int j = lt * LIG_TILE + ((k + lane) & (LIG_TILE - 1));
+    const float4 a = s.l4[j];
+    const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
+    const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    addr[k] = -1;
+    if (d2f <= thr_out) {
+      const int tb = __float_as_int(a.w);
+      int idx = (int)fmaf(2.0f, sqrtf(d2f), -1.0f);
+      idx = max(0, min(idx, 29));
+      const float kf = (float)(idx + 1);
+      const float lo = 0.25f * kf * kf, hi = 0.25f * (kf + 1.0f) * (kf + 1.0f);
+      // idx == 29 means d2f >= 225: never decided in f32 (dist == 225.0 exactly is still inside)
+      const bool sure = (idx < 29) && (hi - d2f > delta) && (idx == 0 || d2f - lo > delta) &&
+                        (fabsf(d2f - 6.0025f) > delta);
+      bool in = false, ifc = false;
+      int bin = 0;
+      if (sure) {
+        in = true;
+        bin = dfire_bin_of(idx);
+        ifc = d2f < 6.0025f;
+      } else {
+        if (DETAIL) ++n_amb;
+        const int r = dfire_exact_pair(gx, gy, gz, glx, gly, glz, tile_base + i, j);
+        in = r >= 0;
+        bin = r & 31;
+        ifc = (r & 32) != 0;
+      }
+      if (in) {
+        addr[k] = at + tb + bin;
+        if (DETAIL) {
+          ++n_in;
+          atomicAdd(&s.hist[bin], 1u);
+        }
+        if (ifc) {
+          ifr_mask |= 1u << i;
+          atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
+          if (DETAIL) ++n_if;
+        }
+      }
+    }
+  }
+  double val[LIG_TILE];
+#pragma unroll
+  for (int k = 0; k < LIG_TILE; ++k) val[k] = addr[k] >= 0 ? __ldg(pot + addr[k]) : 0.0;
+#pragma unroll
+  for (int k = 0; k < LIG_TILE; k += 2) {
+    acc0 = __dadd_rn(acc0, val[k]);
+    acc1 = __dadd_rn(acc1, val[k + 1]);
+  }
+}
+
 template <bool DETAIL>
 __global__ void __launch_bounds__(PAIR_THREADS, 2)
     dfire_pair_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
@@ -278,18 +439,25 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
   const int t1 = min(t0 + bb.tiles_per_split, cx.n_rec_tiles);
   const PairSmem s = carve(smem_raw, cx, bb);
   pair_prologue<0>(cx, bb, s, pose, t1 - t0);
-  const unsigned short *s_tb20 = reinterpret_cast<const unsigned short *>(s.lig_static);
 
   const int lane = threadIdx.x & 31;
+  unsigned *ring = s.rings + (threadIdx.x >> 5) * RING;
+  const unsigned char *lb = bb.lig_blocks + (size_t)pose * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  const double *glx = reinterpret_cast<const double *>(lb), *gly = glx + cx.n_lig_pad, *glz = gly + cx.n_lig_pad;
   const double *gx = cx.rec_x, *gy = cx.rec_y, *gz = cx.rec_z;
   const float4 *gsph = cx.rec_sphere;
+  float maxabs = fmaxf(cx.rec_maxabs, s.lmeta->x);
   if (cx.n_rec_modes > 0) {
-    const unsigned char *rb = bb.rec_blocks + (size_t)pose * block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
+    const unsigned char *rb = bb.rec_blocks + (size_t)pose * rec_block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
     gx = reinterpret_cast<const double *>(rb); gy = gx + cx.n_rec_pad; gz = gy + cx.n_rec_pad;
     gsph = reinterpret_cast<const float4 *>(gz + cx.n_rec_pad);
+    maxabs = fmaxf(gsph[cx.n_rec_tiles].x, s.lmeta->x);
   }
+  const float delta = 5.0e-4f + 2.0e-5f * maxabs;  // |d2f - dist| bound (see above)
+  const float lin = 1.0e-4f + 2.4e-7f * maxabs;    // error of an f32 atom-to-sphere-centre distance
   const double *__restrict__ pot = cx.pot;
   unsigned *iface_rec_out = bb.iface_rec + (size_t)pose * cx.n_rec_tiles;
+  const unsigned lt_mask = (1u << lane) - 1u;
 
   for (;;) {
     int t = 0;
@@ -297,65 +465,67 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
     t = __shfl_sync(0xffffffffu, t, 0) + t0;
     if (t >= t1) break;
     const int ia = t * REC_TILE + lane;
-    const double rx = gx[ia], ry = gy[ia], rz = gz[ia];
+    const float rxf = (float)gx[ia], ryf = (float)gy[ia], rzf = (float)gz[ia];
     const int toff = cx.rec_toff[ia];
     const float4 rs = gsph[t];
-    double acc = 0.0;
-    bool iface_r = false;
-    unsigned n_in = 0, n_if = 0;
+    double acc0 = 0.0, acc1 = 0.0;
+    unsigned ifr_mask = 0u, n_in = 0, n_if = 0, n_tested = 0, n_amb = 0;
+    int q_head = 0, q_count = 0;  // warp-uniform
 
     for (int lt0 = 0; lt0 < cx.n_lig_tiles; lt0 += 32) {
-      const int lt = lt0 + lane;
-      bool pass = false;
-      if (lt < cx.n_lig_tiles) {
-        const float4 ls = s.lsph[lt];
+      // A: this warp's tile sphere against 32 ligand-tile spheres, one per lane
+      const int ltl = lt0 + lane;
+      bool hit = false;
+      if (ltl < cx.n_lig_tiles) {
+        const float4 ls = s.lsph[ltl];
         const float dx = rs.x - ls.x, dy = rs.y - ls.y, dz = rs.z - ls.z;
         const float d2 = dx * dx + dy * dy + dz * dz;
         const float reach = 15.0f + rs.w + ls.w;  // sqrt(225): src/dfire.rs:334
-        pass = d2 <= reach * reach * 1.00001f;
+        hit = d2 <= reach * reach * 1.00001f;
       }
-      unsigned m = __ballot_sync(0xffffffffu, pass);
+      unsigned m = __ballot_sync(0xffffffffu, hit);
       while (m) {
-        const int b = __ffs(m) - 1;
+        const int lt = lt0 + __ffs(m) - 1;
         m &= m - 1;
-        const int j0 = (lt0 + b) * LIG_TILE;
-#pragma unroll
-        for (int jj = 0; jj < LIG_TILE; ++jj) {
-          const int j = j0 + jj;
-          const double dx = __dsub_rn(rx, s.lx[j]);
-          const double dy = __dsub_rn(ry, s.ly[j]);
-          const double dz = __dsub_rn(rz, s.lz[j]);
-          const double dist = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-          if (dist <= 225.0) {
-            const double d = __dsub_rn(__dmul_rn(__dsqrt_rn(dist), 2.0), 1.0);  // src/dfire.rs:336
-            const int idx = (int)d;  // `d as usize`: truncation, d in (-1, 29]
-            const int bin = dfire_bin_of(idx);
-            acc = __dadd_rn(acc, __ldg(pot + toff + (int)s_tb20[j] + bin));
-            if (DETAIL) {
-              ++n_in;
-              atomicAdd(&s.hist[bin], 1u);
-            }
-            if (d <= 3.9) {  // INTERFACE_CUTOFF on the bin-space value, src/dfire.rs:339
-              iface_r = true;
-              atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
-              if (DETAIL) ++n_if;
-            }
+        // B: my atom against this ligand tile's sphere
+        const float4 ls = s.lsph[lt];
+        const float dx = rxf - ls.x, dy = ryf - ls.y, dz = rzf - ls.z;
+        const float d2 = dx * dx + dy * dy + dz * dz;
+        const float reach = 15.0f + ls.w + lin;
+        const bool mine = d2 <= reach * reach * 1.00001f;
+        const unsigned pm = __ballot_sync(0xffffffffu, mine);
+        if (pm) {
+          if (mine) ring[(q_head + q_count + __popc(pm & lt_mask)) & (RING - 1)] = ((unsigned)lane << 16) | (unsigned)lt;
+          q_count += __popc(pm);
+          __syncwarp();
+          if (q_count >= 32) {  // C: a full row of work items
+            dfire_items<DETAIL>(s, ring, q_head, 32, rxf, ryf, rzf, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz, pot,
+                                delta, cx.n_lig, acc0, acc1, ifr_mask, n_in, n_if, n_tested, n_amb);
+            q_head = (q_head + 32) & (RING - 1);
+            q_count -= 32;
+            __syncwarp();
           }
         }
       }
     }
-    const double tsum = warp_sum(acc);
-    const unsigned rbits = __ballot_sync(0xffffffffu, iface_r);
+    if (q_count > 0)
+      dfire_items<DETAIL>(s, ring, q_head, q_count, rxf, ryf, rzf, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz, pot,
+                          delta, cx.n_lig, acc0, acc1, ifr_mask, n_in, n_if, n_tested, n_amb);
+    __syncwarp();
+    const double tsum = warp_sum(__dadd_rn(acc0, acc1));
+    const unsigned rbits = __reduce_or_sync(0xffffffffu, ifr_mask);
     if (lane == 0) {
       s.tile_sum[t - t0] = tsum;
       iface_rec_out[t] = rbits;
     }
     if (DETAIL) {
-      n_in = warp_sum_u32(n_in);
-      n_if = warp_sum_u32(n_if);
+      n_in = warp_sum_u32(n_in); n_if = warp_sum_u32(n_if);
+      n_tested = warp_sum_u32(n_tested); n_amb = warp_sum_u32(n_amb);
       if (lane == 0) {
         atomicAdd(&s.counters[0], (unsigned long long)n_in);
+        atomicAdd(&s.counters[1], (unsigned long long)n_amb);
         atomicAdd(&s.counters[2], (unsigned long long)n_if);
+        atomicAdd(&s.counters[3], (unsigned long long)n_tested);
       }
     }
   }
@@ -370,7 +540,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
     ld_pose_detail *dt = reinterpret_cast<ld_pose_detail *>(bb.detail) + pose;
     if (threadIdx.x == 0) {
       atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_in_cutoff), s.counters[0]);
+      atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_exact_fallback), s.counters[1]);
       atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_interface_pairs), s.counters[2]);
+      atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_pairs_tested), s.counters[3]);
     }
     if (threadIdx.x < 21)
       atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[threadIdx.x]),
@@ -391,14 +563,14 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
   const int t1 = min(t0 + bb.tiles_per_split, cx.n_rec_tiles);
   const PairSmem s = carve(smem_raw, cx, bb);
   pair_prologue<1>(cx, bb, s, pose, t1 - t0);
-  const double *s_q = reinterpret_cast<const double *>(s.lig_static);
+  const double *s_q = s.lig_static;
   const double *s_eps = s_q + cx.n_lig_pad, *s_rad = s_eps + cx.n_lig_pad;
 
   const int lane = threadIdx.x & 31;
   const double *gx = cx.rec_x, *gy = cx.rec_y, *gz = cx.rec_z;
   const float4 *gsph = cx.rec_sphere;
   if (cx.n_rec_modes > 0) {
-    const unsigned char *rb = bb.rec_blocks + (size_t)pose * block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
+    const unsigned char *rb = bb.rec_blocks + (size_t)pose * rec_block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
     gx = reinterpret_cast<const double *>(rb); gy = gx + cx.n_rec_pad; gz = gy + cx.n_rec_pad;
     gsph = reinterpret_cast<const float4 *>(gz + cx.n_rec_pad);
   }
@@ -419,7 +591,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
     const float4 rs = gsph[t];
     double acc_e = 0.0, acc_v = 0.0;
     bool iface_r = false;
-    unsigned n_e = 0, n_v = 0, n_if = 0;
+    unsigned n_e = 0, n_v = 0, n_if = 0, n_tested = 0;
 
     for (int lt0 = 0; lt0 < cx.n_lig_tiles; lt0 += 32) {
       const int lt = lt0 + lane;
@@ -436,6 +608,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
         const int b = __ffs(m) - 1;
         m &= m - 1;
         const int j0 = (lt0 + b) * LIG_TILE;
+        if (DETAIL && ia < cx.n_rec) n_tested += min(LIG_TILE, cx.n_lig - j0);
 #pragma unroll
         for (int jj = 0; jj < LIG_TILE; ++jj) {
           const int j = j0 + jj;
@@ -479,10 +652,12 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
     }
     if (DETAIL) {
       n_e = warp_sum_u32(n_e); n_v = warp_sum_u32(n_v); n_if = warp_sum_u32(n_if);
+      n_tested = warp_sum_u32(n_tested);
       if (lane == 0) {
         atomicAdd(&s.counters[0], (unsigned long long)n_e);
         atomicAdd(&s.counters[1], (unsigned long long)n_v);
         atomicAdd(&s.counters[2], (unsigned long long)n_if);
+        atomicAdd(&s.counters[3], (unsigned long long)n_tested);
       }
     }
   }
@@ -496,6 +671,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
     atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_in_cutoff), s.counters[0]);
     atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_in_cutoff2), s.counters[1]);
     atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_interface_pairs), s.counters[2]);
+    atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_pairs_tested), s.counters[3]);
   }
 }
 

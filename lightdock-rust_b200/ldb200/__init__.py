@@ -17,7 +17,7 @@ DFIRE_TABLE_LEN = 169 * 169 * 20
 
 EXPORTS = ["ld_create", "ld_destroy", "ld_pose_len", "ld_score_batch", "ld_score_batch_device",
            "ld_score_batch_detail", "ld_transform_batch", "ld_get_stats", "ld_set_rec_splits",
-           "ld_last_error", "ld_version"]
+           "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version"]
 
 
 class MoleculeDesc(C.Structure):
@@ -38,12 +38,13 @@ class PoseDetail(C.Structure):
     _fields_ = [("raw_sum", C.c_double), ("raw_sum2", C.c_double), ("n_in_cutoff", C.c_int64),
                 ("n_in_cutoff2", C.c_int64), ("n_interface_pairs", C.c_int64), ("bin_hist", C.c_int64 * 21),
                 ("rec_rst_hit", C.c_int32), ("lig_rst_hit", C.c_int32), ("membrane_hit", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("n_pairs_tested", C.c_int64), ("n_exact_fallback", C.c_int64)]
 
 
 class BatchStats(C.Structure):
     _fields_ = [("n_poses", C.c_int64), ("pair_evals_bruteforce", C.c_int64), ("kernel_launches", C.c_int32),
-                ("rec_splits", C.c_int32), ("device_ms", C.c_double)]
+                ("rec_splits", C.c_int32), ("device_ms", C.c_double), ("transform_ms", C.c_double),
+                ("pair_ms", C.c_double), ("finalize_ms", C.c_double)]
 
 
 class LdError(RuntimeError):
@@ -72,6 +73,8 @@ def load_library():
         lib.ld_transform_batch.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ld_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
         lib.ld_set_rec_splits.argtypes = [C.c_void_p, C.c_int32]
+        lib.ld_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        lib.ld_probe_peaks.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
 
@@ -178,6 +181,8 @@ class Scorer:
             rec_rst_hit=np.array([d.rec_rst_hit for d in det], dtype=np.int32),
             lig_rst_hit=np.array([d.lig_rst_hit for d in det], dtype=np.int32),
             membrane_hit=np.array([d.membrane_hit for d in det], dtype=np.int32),
+            n_pairs_tested=np.array([d.n_pairs_tested for d in det], dtype=np.int64),
+            n_exact_fallback=np.array([d.n_exact_fallback for d in det], dtype=np.int64),
             iface_rec=irec, iface_lig=ilig)
 
     def transform(self, poses):
@@ -196,8 +201,24 @@ class Scorer:
     def set_rec_splits(self, splits):
         _check(self.lib, self.lib.ld_set_rec_splits(self.h, int(splits)))
 
+    def set_profiling(self, on):
+        _check(self.lib, self.lib.ld_set_profiling(self.h, int(bool(on))))
+
     def stats(self):
-        s = BatchStats()
-        _check(self.lib, self.lib.ld_get_stats(self.h, C.byref(s)))
-        return dict(n_poses=s.n_poses, pair_evals_bruteforce=s.pair_evals_bruteforce,
-                    kernel_launches=s.kernel_launches, rec_splits=s.rec_splits, device_ms=s.device_ms)
+        return handle_stats(self.lib, self.h)
+
+
+def handle_stats(lib, h):
+    s = BatchStats()
+    _check(lib, lib.ld_get_stats(h, C.byref(s)))
+    return dict(n_poses=s.n_poses, pair_evals_bruteforce=s.pair_evals_bruteforce,
+                kernel_launches=s.kernel_launches, rec_splits=s.rec_splits, device_ms=s.device_ms,
+                transform_ms=s.transform_ms, pair_ms=s.pair_ms, finalize_ms=s.finalize_ms)
+
+
+def probe_peaks(device=0):
+    """On-box roofline denominators: (fp64 non-FMA TFLOP/s, fp32 non-FMA TFLOP/s, L2 gather Gloads/s)."""
+    lib = load_library()
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    _check(lib, lib.ld_probe_peaks(int(device), C.addressof(a), C.addressof(b), C.addressof(c)))
+    return a.value, b.value, c.value

@@ -117,3 +117,71 @@ def test_edge_cases():
     e_gpu, d_gpu = sc.energy_detail(p)
     e_ref, d_ref = cx.energy(p, detail=True)
     assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
+
+
+def _threshold_complex():
+    """One receptor atom at the origin, ligand atoms on the x axis at the decision thresholds of the DFIRE
+    loop and a few ulps / small offsets either side: every bin edge (k+1)/2, the 15 A cut-off (dist == 225
+    gives DIST_TO_BINS[29]-1 = 20, i.e. the next ligand type's bin 0) and the 2.45 A interface edge."""
+    edges = [(k + 1) / 2.0 for k in range(0, 30)] + [2.45, 15.0]
+    xs = []
+    for e in edges:
+        v = np.float64(e)
+        xs += [v, np.nextafter(v, 0), np.nextafter(v, 100), np.nextafter(np.nextafter(v, 0), 0),
+               np.nextafter(np.nextafter(v, 100), 100), v - 1e-7, v + 1e-7, v - 3e-5, v + 3e-5, v - 1e-3, v + 1e-3]
+    xs = np.array(xs, dtype=np.float64)
+    lig = np.zeros((xs.size, 3)); lig[:, 0] = xs
+    rec = np.zeros((3, 3)); rec[1] = [0, 400, 0]; rec[2] = [0, 0, -400]
+
+    class M:  # duck-typed oracle Molecule
+        pass
+    def mol(c, types):
+        m = M()
+        m.n = len(c); m.coords = np.ascontiguousarray(c); m.dfire_type = np.asarray(types, np.int32)
+        m.ele = m.vdw_e = m.vdw_r = None
+        m.membrane = np.zeros(0, np.int32); m.rst_offsets = np.array([0, 1], np.int32); m.rst_atoms = np.array([0], np.int32)
+        m.n_modes = 0; m.modes = np.zeros(0)
+        return m
+    rng = np.random.default_rng(11)
+    return mol(rec, [5, 17, 167]), mol(lig, rng.integers(0, 168, size=xs.size))
+
+
+def test_dfire_decision_thresholds_exact():
+    """Pairs sitting on / next to every decision threshold must fall on the reference's side of it."""
+    rec, lig = _threshold_complex()
+    pot, _ = O.real_or_synthetic_dcparams()
+    cx = O.Complex(rec, lig, O.DFIRE, False, pot)
+    sc = scorer_from_oracle(cx)
+    poses = np.array([[0, 0, 0, 1, 0, 0, 0],            # identity: coordinates exact
+                      [0, 0, 0, 0, 1, 0, 0],            # 180 deg about x: x unchanged
+                      [1e-9, 0, 0, 1, 0, 0, 0], [-1e-9, 0, 0, 1, 0, 0, 0],
+                      [3e-6, 0, 0, 1, 0, 0, 0], [0, 2e-4, 0, 1, 0, 0, 0],
+                      [0.25, 0, 0, 1, 0, 0, 0], [-0.25, 0, 0, 1, 0, 0, 0]], dtype=np.float64)
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    e_ref, d_ref = cx.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, O.DFIRE)
+    assert d_ref["bin_hist"][0][20] >= 1, "dist == 225 exactly must land in bin 20 (src/dfire.rs:337)"
+    assert d_gpu["n_exact_fallback"][0] > 0, "threshold pairs must take the exact FP64 path"
+
+
+def test_dfire_exact_fallback_is_rare():
+    cx, pos, _ = case("1k4c", O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    _, d = sc.energy_detail(pos[:64])
+    frac = d["n_exact_fallback"].sum() / d["n_in_cutoff"].sum()
+    assert frac < 0.01, frac
+
+
+def test_large_coordinates_stay_exact():
+    """f32 margins scale with the coordinate magnitude: shift the whole system 5000 A away from the origin."""
+    cx, pos, _ = case("1ppe", O.DFIRE)
+    shift = np.array([5000.0, -3000.0, 2000.0])
+    rec = cx.rec; lig = cx.lig
+    import copy
+    rec2 = copy.copy(rec); rec2.coords = rec.coords + shift
+    cx2 = O.Complex(rec2, lig, O.DFIRE, False, cx.potential)
+    sc = scorer_from_oracle(cx2)
+    p = pos[:24].copy(); p[:, :3] += shift
+    e_gpu, d_gpu = sc.energy_detail(p)
+    e_ref, d_ref = cx2.energy(p, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, O.DFIRE)
