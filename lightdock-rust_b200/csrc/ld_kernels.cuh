@@ -232,7 +232,7 @@ __host__ __device__ inline size_t pair_smem_bytes(int method, int n_lig_pad, int
   }
   o += align16((size_t)lig_words * 4);
   o += align16((size_t)tiles_per_split * 8 * (method == 0 ? 1 : 2));
-  if (method == 0) o += (size_t)(PAIR_THREADS / 32) * RING * 4;
+  if (method == 0) o += (size_t)(PAIR_THREADS / 32) * RING * 4 + 32 * 16;  // work-item rings + BinEntry table
   return o;
 }
 __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceComplex &cx, const BatchBuffers &bb) {
@@ -355,9 +355,24 @@ __device__ __noinline__ int dfire_exact_pair(const double *gx, const double *gy,
   return bin | (d <= 3.9 ? 32 : 0);      // INTERFACE_CUTOFF on the bin-space value, src/dfire.rs:339
 }
 
+// Decision table of the FP32 classification, one entry per truncated bin-space index idx = (int)(2*sqrt(d2)-1):
+// a pair whose d2f lies strictly inside (lo, hi) — the index's interval ((idx+1)/2)^2 .. ((idx+2)/2)^2 shrunk by
+// delta on both sides — provably has that index in the reference's FP64 arithmetic.  idx 0 has no lower edge
+// (d < 1 saturates to 0) and idx 29 (d2 >= 225) is never decided in FP32.
+struct __align__(16) BinEntry {
+  float lo, hi;
+  int bin;  // DIST_TO_BINS[idx] - 1
+  int pad;
+};
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 template <bool DETAIL>
-__device__ __forceinline__ void dfire_items(const PairSmem &s, const unsigned *ring, int head, int n_active,
-                                            float rxf, float ryf, float rzf, int toff, int tile_base,
+__device__ __forceinline__ void dfire_items(const PairSmem &s, const BinEntry *tab, const unsigned *ring, int head,
+                                            int n_active, float rxf, float ryf, float rzf, int toff, int tile_base,
                                             const double *gx, const double *gy, const double *gz,
                                             const double *glx, const double *gly, const double *glz,
                                             const double *__restrict__ pot, float delta, int n_lig, double &acc0,
@@ -376,29 +391,23 @@ __device__ __forceinline__ void dfire_items(const PairSmem &s, const unsigned *r
   // pass 1: classify the 8 pairs (no table access yet); pass 2: issue the 8 gathers back to back so they
   // are all in flight together; pass 3: accumulate.  Pairs that are out contribute +0.0 (exact no-op).
   int addr[LIG_TILE];
+  unsigned ifc_bits = 0u;
+  const int jbase = lt * LIG_TILE;
 #pragma unroll
   for (int k = 0; k < LIG_TILE; ++k) {
-    const int j = lt * LIG_TILE + ((k + lane) & (LIG_TILE - 1));
+    const int j = jbase + ((k + lane) & (LIG_TILE - 1));
     const float4 a = s.l4[j];
     const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
     const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     addr[k] = -1;
     if (d2f <= thr_out) {
-      const int tb = __float_as_int(a.w);
-      int idx = (int)fmaf(2.0f, sqrtf(d2f), -1.0f);
+      // any estimate of idx will do: the interval test below is what proves it (d2f == 0 gives NaN -> 0)
+      int idx = __float2int_rz(fmaf(d2f + d2f, rsqrt_approx(d2f), -1.0f));
       idx = max(0, min(idx, 29));
-      const float kf = (float)(idx + 1);
-      const float lo = 0.25f * kf * kf, hi = 0.25f * (kf + 1.0f) * (kf + 1.0f);
-      // idx == 29 means d2f >= 225: never decided in f32 (dist == 225.0 exactly is still inside)
-      const bool sure = (idx < 29) && (hi - d2f > delta) && (idx == 0 || d2f - lo > delta) &&
-                        (fabsf(d2f - 6.0025f) > delta);
-      bool in = false, ifc = false;
-      int bin = 0;
-      if (sure) {
-        in = true;
-        bin = dfire_bin_of(idx);
-        ifc = d2f < 6.0025f;
-      } else {
+      const BinEntry e = tab[idx];
+      int bin = e.bin;
+      bool in = true, ifc = d2f < 6.0025f;
+      if (!(d2f > e.lo && d2f < e.hi && fabsf(d2f - 6.0025f) > delta)) {
         if (DETAIL) ++n_amb;
         const int r = dfire_exact_pair(gx, gy, gz, glx, gly, glz, tile_base + i, j);
         in = r >= 0;
@@ -406,15 +415,11 @@ __device__ __forceinline__ void dfire_items(const PairSmem &s, const unsigned *r
         ifc = (r & 32) != 0;
       }
       if (in) {
-        addr[k] = at + tb + bin;
+        addr[k] = at + __float_as_int(a.w) + bin;
+        ifc_bits |= (ifc ? 1u : 0u) << k;
         if (DETAIL) {
           ++n_in;
           atomicAdd(&s.hist[bin], 1u);
-        }
-        if (ifc) {
-          ifr_mask |= 1u << i;
-          atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
-          if (DETAIL) ++n_if;
         }
       }
     }
@@ -422,6 +427,14 @@ __device__ __forceinline__ void dfire_items(const PairSmem &s, const unsigned *r
   double val[LIG_TILE];
 #pragma unroll
   for (int k = 0; k < LIG_TILE; ++k) val[k] = addr[k] >= 0 ? __ldg(pot + addr[k]) : 0.0;
+  if (ifc_bits) {  // rare: a contact closer than 2.45 A (src/dfire.rs:339-342)
+    ifr_mask |= 1u << i;
+    for (unsigned b = ifc_bits; b; b &= b - 1) {
+      const int j = jbase + ((__ffs(b) - 1 + lane) & (LIG_TILE - 1));
+      atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
+      if (DETAIL) ++n_if;
+    }
+  }
 #pragma unroll
   for (int k = 0; k < LIG_TILE; k += 2) {
     acc0 = __dadd_rn(acc0, val[k]);
@@ -455,6 +468,18 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
   }
   const float delta = 5.0e-4f + 2.0e-5f * maxabs;  // |d2f - dist| bound (see above)
   const float lin = 1.0e-4f + 2.4e-7f * maxabs;    // error of an f32 atom-to-sphere-centre distance
+  BinEntry *tab = reinterpret_cast<BinEntry *>(s.rings + (PAIR_THREADS / 32) * RING);
+  if (threadIdx.x < 30) {
+    const int idx = threadIdx.x;
+    const float kf = (float)(idx + 1);
+    BinEntry e;
+    e.lo = idx == 0 ? -INFINITY : 0.25f * kf * kf + delta;
+    e.hi = idx == 29 ? -INFINITY : 0.25f * (kf + 1.0f) * (kf + 1.0f) - delta;
+    e.bin = dfire_bin_of(idx);
+    e.pad = 0;
+    tab[idx] = e;
+  }
+  __syncthreads();
   const double *__restrict__ pot = cx.pot;
   unsigned *iface_rec_out = bb.iface_rec + (size_t)pose * cx.n_rec_tiles;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -499,7 +524,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
           q_count += __popc(pm);
           __syncwarp();
           if (q_count >= 32) {  // C: a full row of work items
-            dfire_items<DETAIL>(s, ring, q_head, 32, rxf, ryf, rzf, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz, pot,
+            dfire_items<DETAIL>(s, tab, ring, q_head, 32, rxf, ryf, rzf, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz, pot,
                                 delta, cx.n_lig, acc0, acc1, ifr_mask, n_in, n_if, n_tested, n_amb);
             q_head = (q_head + 32) & (RING - 1);
             q_count -= 32;
@@ -509,7 +534,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
       }
     }
     if (q_count > 0)
-      dfire_items<DETAIL>(s, ring, q_head, q_count, rxf, ryf, rzf, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz, pot,
+      dfire_items<DETAIL>(s, tab, ring, q_head, q_count, rxf, ryf, rzf, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz, pot,
                           delta, cx.n_lig, acc0, acc1, ifr_mask, n_in, n_if, n_tested, n_amb);
     __syncwarp();
     const double tsum = warp_sum(__dadd_rn(acc0, acc1));
