@@ -232,7 +232,7 @@ __host__ __device__ inline size_t pair_smem_bytes(int method, int n_lig_pad, int
   }
   o += align16((size_t)lig_words * 4);
   o += align16((size_t)tiles_per_split * 8 * (method == 0 ? 1 : 2));
-  if (method == 0) o += (size_t)(PAIR_THREADS / 32) * RING * 4 + 32 * 16;  // work-item rings + BinEntry table
+  if (method == 0) o += (size_t)(PAIR_THREADS / 32) * RING * 4 + 32 * 8;  // work-item rings + decision table
   return o;
 }
 __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceComplex &cx, const BatchBuffers &bb) {
@@ -355,23 +355,20 @@ __device__ __noinline__ int dfire_exact_pair(const double *gx, const double *gy,
   return bin | (d <= 3.9 ? 32 : 0);      // INTERFACE_CUTOFF on the bin-space value, src/dfire.rs:339
 }
 
-// Decision table of the FP32 classification, one entry per truncated bin-space index idx = (int)(2*sqrt(d2)-1):
+// Decision table of the FP32 classification, one float2 per truncated bin-space index idx = (int)(2*sqrt(d2)-1):
 // a pair whose d2f lies strictly inside (lo, hi) — the index's interval ((idx+1)/2)^2 .. ((idx+2)/2)^2 shrunk by
 // delta on both sides — provably has that index in the reference's FP64 arithmetic.  idx 0 has no lower edge
 // (d < 1 saturates to 0) and idx 29 (d2 >= 225) is never decided in FP32.
-struct __align__(16) BinEntry {
-  float lo, hi;
-  int bin;  // DIST_TO_BINS[idx] - 1
-  int pad;
-};
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+// DIST_TO_BINS[idx]-1 without branches: idx-2 below the knee at 15, (idx+11)/2 above it, clamped at 0.
+__device__ __forceinline__ int dfire_bin_fast(int idx) { return min(max(idx - 2, 0), (idx + 11) >> 1); }
 
 template <bool DETAIL>
-__device__ __forceinline__ void dfire_items(const PairSmem &s, const BinEntry *tab, const unsigned *ring, int head,
+__device__ __forceinline__ void dfire_items(const PairSmem &s, const float2 *tab, const unsigned *ring, int head,
                                             int n_active, float rxf, float ryf, float rzf, int toff, int tile_base,
                                             const double *gx, const double *gy, const double *gz,
                                             const double *glx, const double *gly, const double *glz,
@@ -388,10 +385,10 @@ __device__ __forceinline__ void dfire_items(const PairSmem &s, const BinEntry *t
   if (!active) return;
   const float thr_out = 225.0f + delta;
   if (DETAIL) n_tested += min(LIG_TILE, n_lig - lt * LIG_TILE);
-  // pass 1: classify the 8 pairs (no table access yet); pass 2: issue the 8 gathers back to back so they
-  // are all in flight together; pass 3: accumulate.  Pairs that are out contribute +0.0 (exact no-op).
+  // pass 1 is branch-free so the 8 independent chains interleave: classify each pair in FP32;
+  // pass 2 issues the 8 table gathers back to back; pass 3 accumulates (+0.0 for pairs that are out).
   int addr[LIG_TILE];
-  unsigned ifc_bits = 0u;
+  unsigned ifc_bits = 0u, amb_bits = 0u;
   const int jbase = lt * LIG_TILE;
 #pragma unroll
   for (int k = 0; k < LIG_TILE; ++k) {
@@ -399,34 +396,36 @@ __device__ __forceinline__ void dfire_items(const PairSmem &s, const BinEntry *t
     const float4 a = s.l4[j];
     const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
     const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    addr[k] = -1;
-    if (d2f <= thr_out) {
-      // any estimate of idx will do: the interval test below is what proves it (d2f == 0 gives NaN -> 0)
-      int idx = __float2int_rz(fmaf(d2f + d2f, rsqrt_approx(d2f), -1.0f));
-      idx = max(0, min(idx, 29));
-      const BinEntry e = tab[idx];
-      int bin = e.bin;
-      bool in = true, ifc = d2f < 6.0025f;
-      if (!(d2f > e.lo && d2f < e.hi && fabsf(d2f - 6.0025f) > delta)) {
-        if (DETAIL) ++n_amb;
-        const int r = dfire_exact_pair(gx, gy, gz, glx, gly, glz, tile_base + i, j);
-        in = r >= 0;
-        bin = r & 31;
-        ifc = (r & 32) != 0;
-      }
-      if (in) {
-        addr[k] = at + __float_as_int(a.w) + bin;
-        ifc_bits |= (ifc ? 1u : 0u) << k;
-        if (DETAIL) {
-          ++n_in;
-          atomicAdd(&s.hist[bin], 1u);
-        }
-      }
-    }
+    // any estimate of idx will do: the interval test is what proves it (d2f == 0 gives NaN -> 0)
+    int idx = __float2int_rz(fmaf(d2f + d2f, rsqrt_approx(d2f), -1.0f));
+    idx = max(0, min(idx, 29));
+    const float2 e = tab[idx];
+    const bool inr = d2f <= thr_out;
+    const bool sure = d2f > e.x && d2f < e.y && fabsf(d2f - 6.0025f) > delta;
+    addr[k] = (inr && sure) ? at + __float_as_int(a.w) + dfire_bin_fast(idx) : -1;
+    ifc_bits |= ((inr && sure && d2f < 6.0025f) ? 1u : 0u) << k;
+    amb_bits |= ((inr && !sure) ? 1u : 0u) << k;
   }
   double val[LIG_TILE];
 #pragma unroll
   for (int k = 0; k < LIG_TILE; ++k) val[k] = addr[k] >= 0 ? __ldg(pot + addr[k]) : 0.0;
+  double extra = 0.0;
+  if (amb_bits) {  // rare: too close to a decision threshold -> exact FP64 re-evaluation
+    for (unsigned b = amb_bits; b; b &= b - 1) {
+      const int k = __ffs(b) - 1;
+      const int j = jbase + ((k + lane) & (LIG_TILE - 1));
+      if (DETAIL) ++n_amb;
+      const int r = dfire_exact_pair(gx, gy, gz, glx, gly, glz, tile_base + i, j);
+      if (r >= 0) {
+        extra = __dadd_rn(extra, __ldg(pot + at + __float_as_int(s.l4[j].w) + (r & 31)));
+        if (r & 32) ifc_bits |= 1u << k;
+        if (DETAIL) {
+          ++n_in;
+          atomicAdd(&s.hist[r & 31], 1u);
+        }
+      }
+    }
+  }
   if (ifc_bits) {  // rare: a contact closer than 2.45 A (src/dfire.rs:339-342)
     ifr_mask |= 1u << i;
     for (unsigned b = ifc_bits; b; b &= b - 1) {
@@ -435,11 +434,20 @@ __device__ __forceinline__ void dfire_items(const PairSmem &s, const BinEntry *t
       if (DETAIL) ++n_if;
     }
   }
+  if (DETAIL) {
+#pragma unroll
+    for (int k = 0; k < LIG_TILE; ++k)
+      if (addr[k] >= 0) {
+        ++n_in;
+        atomicAdd(&s.hist[(addr[k] - at) % 20], 1u);  // at and tb are multiples of 20; bin 20 aliases to 0 of tb+1
+      }
+  }
 #pragma unroll
   for (int k = 0; k < LIG_TILE; k += 2) {
     acc0 = __dadd_rn(acc0, val[k]);
     acc1 = __dadd_rn(acc1, val[k + 1]);
   }
+  acc0 = __dadd_rn(acc0, extra);
 }
 
 template <bool DETAIL>
@@ -468,16 +476,12 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
   }
   const float delta = 5.0e-4f + 2.0e-5f * maxabs;  // |d2f - dist| bound (see above)
   const float lin = 1.0e-4f + 2.4e-7f * maxabs;    // error of an f32 atom-to-sphere-centre distance
-  BinEntry *tab = reinterpret_cast<BinEntry *>(s.rings + (PAIR_THREADS / 32) * RING);
+  float2 *tab = reinterpret_cast<float2 *>(s.rings + (PAIR_THREADS / 32) * RING);
   if (threadIdx.x < 30) {
     const int idx = threadIdx.x;
     const float kf = (float)(idx + 1);
-    BinEntry e;
-    e.lo = idx == 0 ? -INFINITY : 0.25f * kf * kf + delta;
-    e.hi = idx == 29 ? -INFINITY : 0.25f * (kf + 1.0f) * (kf + 1.0f) - delta;
-    e.bin = dfire_bin_of(idx);
-    e.pad = 0;
-    tab[idx] = e;
+    tab[idx] = make_float2(idx == 0 ? -INFINITY : 0.25f * kf * kf + delta,
+                           idx == 29 ? -INFINITY : 0.25f * (kf + 1.0f) * (kf + 1.0f) - delta);
   }
   __syncthreads();
   const double *__restrict__ pot = cx.pot;
