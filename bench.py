@@ -163,6 +163,8 @@ def run_b200(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("WARN", "VERSION"):
+            os.environ.pop("NCCL_DEBUG")  # those levels printf "NCCL version ..." on stdout, next to the JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = ldb200.load_library()
 
@@ -320,7 +322,7 @@ def run_b200(args, rank, world, local_rank):
                    "d2h_bytes_per_step": n_local * 8, "ms_per_step": e2e_s / args.steps * 1e3,
                    "api": "ld_score_batch (C ABI, host buffers)"},
            "gpu_launches": launches_per_step * args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
