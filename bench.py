@@ -254,6 +254,23 @@ def run_b200(args, rank, world, local_rank):
     if not np.array_equal(e_host, e_dev):
         raise SystemExit("bench.py: host-buffer and device-buffer paths disagree")
 
+    # ---- whole GSO run through the host driver (MultiGSO: real control flow, RNG stream, moved-only rescoring) ----
+    gso = None
+    if args.gso_steps > 0:
+        threads = max(1, min(32, host_cores() // world))
+        seeds = np.full(len(mine), 324324, dtype=np.uint64)  # every swarm is seeded like a stand-alone reference process
+        barrier()
+        t0 = time.perf_counter()
+        _, calls = case.multi_gso(all_poses[mine], seeds, args.gso_steps, host_threads=threads)
+        gso_s = max_over_ranks(time.perf_counter() - t0)
+        calls_t = torch.tensor([calls], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(calls_t, op=dist.ReduceOp.SUM)
+        gso = {"steps": args.gso_steps, "swarms": args.swarms, "energy_calls": int(calls_t.item()),
+               "wall_s": gso_s, "poses_per_s": calls_t.item() / gso_s, "host_threads_per_rank": threads,
+               "moved_fraction": calls_t.item() / (n_total * args.gso_steps),
+               "what": "lightdock host GSO (C++ MultiGSO) + one ld_score_batch per step, wall clock incl. host movement phase"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -321,7 +338,8 @@ def run_b200(args, rank, world, local_rank):
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_local * 7 * 8,
                    "d2h_bytes_per_step": n_local * 8, "ms_per_step": e2e_s / args.steps * 1e3,
                    "api": "ld_score_batch (C ABI, host buffers)"},
-           "gpu_launches": launches_per_step * args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu}
+           "gpu_launches": launches_per_step * args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+           "gso_run": gso}
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -337,6 +355,7 @@ def main():
     ap.add_argument("--glowworms", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gso-steps", type=int, default=10, help="steps of the real GSO loop for the gso_run figure (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
