@@ -235,7 +235,10 @@ def run_b200(args, rank, world, local_rank):
         st = ldb200.handle_stats(lib, h)
         pair_ms += st["pair_ms"]; tr_ms += st["transform_ms"]; fin_ms += st["finalize_ms"]
     lib.ld_set_profiling(h, 0)
-    pair_launches = (launches_per_step // 3) * args.steps
+    st_last = ldb200.handle_stats(lib, h)
+    pair_launches = st_last["pair_launches"] * args.steps
+    path = {ldb200.PATH_GENERIC: "generic", ldb200.PATH_RIGID: "rigid"}[st_last["path"]]
+    pair_kernel = "dfire_rigid_kernel" if path == "rigid" else "dfire_pair_kernel"
     pair_ms_step = max_over_ranks(pair_ms / args.steps)
 
     # ---- end to end through the C ABI with host buffers (`e2e`) --------------------------------
@@ -295,11 +298,18 @@ def run_b200(args, rank, world, local_rank):
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    # algorithmic HBM bytes per pose: ligand block written once + read once, pose row in, energy out
-    lig_block = (3272 * 40 + 409 * 16 + 16)
-    hbm_bytes = n_local * (2 * lig_block + 56 + 8)
+    if path == "rigid":
+        # algorithmic HBM bytes per pose: pose row in, energy out, per-pose rotation data (128 B written + read),
+        # per-group partial sums and receptor interface words (written + read), ligand interface bitmap
+        # (cleared + read); the complex itself (cell lists, table rows, ligand) is L2/shared-memory resident
+        n_groups = int(case.path_info().split(" receptor groups")[0].split()[-1])
+        hbm_bytes = n_local * (56 + 8 + 2 * 128 + 2 * n_groups * (8 + 4) + 2 * 4 * ((N_LIG + 7) // 8 * 8 + 31) // 32)
+    else:
+        # algorithmic HBM bytes per pose: ligand block written once + read once, pose row in, energy out
+        lig_block = (3272 * 40 + 409 * 16 + 16)
+        hbm_bytes = n_local * (2 * lig_block + 56 + 8)
     roofline = {
-        "bound": "fp64", "kernel": "dfire_pair_kernel", "achieved": achieved_tf, "peak": fp64_tf, "unit": "TFLOP/s",
+        "bound": "fp64", "kernel": pair_kernel, "path": path, "path_info": case.path_info(), "achieved": achieved_tf, "peak": fp64_tf, "unit": "TFLOP/s",
         "frac": achieved_tf / fp64_tf, "traffic": None,
         "peak_source": "ld_probe_peaks: non-fused DADD+DMUL rate measured on this GPU (MEASURED_PEAKS.json has no "
                        "FP64 figure; SURVEY.md 8d)",
@@ -308,8 +318,10 @@ def run_b200(args, rank, world, local_rank):
         "executed_pair_test_fraction": tested, "in_cutoff_fraction": in_cut,
         "executed_frac_of_fp64_peak": achieved_tf * tested / fp64_tf,
         "note": "achieved counts the reference's brute-force loop (8 FP64 flops x N_rec x N_lig per pose); the kernel "
-                "culls tile pairs with an FP32 sphere test and executes only `executed_pair_test_fraction` of them, "
-                "so frac > 1 is pruning, not missing work",
+                "prunes with ligand-frame cell lists (rigid path) or FP32 sphere tests (generic path), classifies the "
+                "surviving pairs in FP32 with proven margins and executes only `executed_pair_test_fraction` of the "
+                "pairs, so frac > 1 is pruning + reformulation, not missing work; the kernel's own limiter is "
+                "instruction issue (profiles/)",
         "gather": {"gloads_per_s": in_cut * pairs_per_rank_step / (pair_ms_step * 1e-3) / 1e9,
                    "peak_gloads_per_s": gather_g},
         "hbm": {"achieved_gbs": hbm_bytes / ((ms_total / args.steps) * 1e-3) / 1e9, "peak_gbs": hbm_peak,

@@ -99,6 +99,8 @@ typedef struct ld_batch_stats {
   /* per-kernel device time of the last call, filled only while profiling is on (ld_set_profiling)
    * and read back by ld_get_stats, which synchronises the stream the call used */
   double transform_ms, pair_ms, finalize_ms;
+  int32_t path;                  /* LD_PATH_GENERIC or LD_PATH_RIGID: the pair kernel the call used */
+  int32_t pair_launches;         /* launches of that pair kernel                                  */
 } ld_batch_stats;
 
 typedef struct ld_handle ld_handle;
@@ -136,6 +138,18 @@ int ld_get_stats(ld_handle *h, ld_batch_stats *out);
 
 /* Tuning knob for benchmarks/tests: force the number of receptor splits (0 = automatic). */
 int ld_set_rec_splits(ld_handle *h, int32_t splits);
+
+/* Pair-kernel selection.  AUTO = RIGID whenever it applies (DFIRE, no ligand ANM modes, ligand and
+ * table rows fit in shared memory), else GENERIC.  RIGID moves each receptor atom into the ligand's
+ * frame and looks candidates up in ligand-frame cell lists built once by ld_create; GENERIC moves the
+ * ligand per pose and culls with bounding spheres.  Both give the same discrete outputs; energies may
+ * differ in the last bits (summation order).  Forcing RIGID on a complex it cannot take is LD_EINVAL. */
+#define LD_PATH_AUTO 0
+#define LD_PATH_GENERIC 1
+#define LD_PATH_RIGID 2
+int ld_set_path(ld_handle *h, int32_t path);
+/* One-line description of the rigid-path structures (groups, cells, list sizes) or why it is off. */
+const char *ld_path_info(const ld_handle *h);
 
 /* Brackets every kernel launch with CUDA events on the launching stream (bench.py's roofline leg). */
 int ld_set_profiling(ld_handle *h, int32_t on);

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "ld_kernels.cuh"
+#include "ld_rigid.cuh"
 
 using namespace ldb200;
 
@@ -45,8 +46,20 @@ struct ld_handle {
   int forced_splits = 0;
   size_t lig_block = 0, rec_block = 0;
   // work buffers
+  // rigid-ligand DFIRE path (ld_rigid.cuh): type-grouped receptor + ligand-frame cell lists
+  bool rigid_ok = false;
+  int path_mode = LD_PATH_AUTO;
+  RigidComplex rc{};
+  DeviceComplex cxr{};                  // what finalize_kernel sees on the rigid path (groups as tiles)
+  std::vector<int> rec_perm_r;          // grouped position -> original atom index, -1 = pad lane
+  unsigned *d_unit_counter = nullptr;
+  RigidComplex *d_rc = nullptr;         // device copy of rc for the rare exact path
+  double *d_prep = nullptr;             // [cap_chunk][RG_PREP] per-pose rotation data (rigid path)
+  int64_t cap_prep = 0;
+  std::string rigid_info;
   int64_t cap_poses = 0;   // capacity of poses/energies/detail buffers
-  int64_t cap_chunk = 0;   // capacity (poses) of block/partial/bitmap buffers
+  int64_t cap_chunk = 0;   // capacity (poses) of partial/bitmap buffers
+  int64_t cap_blocks = 0;  // capacity (poses) of the per-pose coordinate blocks (generic path only)
   int cap_splits = 0;
   double *d_poses = nullptr, *d_energies = nullptr;
   ld_pose_detail *d_detail = nullptr;
@@ -193,13 +206,230 @@ extern "C" int ld_destroy(ld_handle *h) {
   for (void *p : h->owned) cudaFree(p);
   cudaFree(h->d_poses); cudaFree(h->d_energies); cudaFree(h->d_detail);
   cudaFree(h->d_lig_blocks); cudaFree(h->d_rec_blocks); cudaFree(h->d_partials);
-  cudaFree(h->d_iface_rec); cudaFree(h->d_iface_lig);
+  cudaFree(h->d_iface_rec); cudaFree(h->d_iface_lig); cudaFree(h->d_unit_counter); cudaFree(h->d_rc); cudaFree(h->d_prep);
   cudaFreeHost(h->h_poses); cudaFreeHost(h->h_energies);
   for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
+  return LD_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Rigid-ligand DFIRE path (ld_rigid.cuh): everything below is built once per complex.
+//
+// Receptor atoms are packed into groups of <= 32 atoms spanning <= rows_max DFIRE types: types with
+// >= 32 atoms fill whole groups on their own, the remainders are packed first-fit-decreasing.
+struct RigidGroup {
+  std::vector<int> atoms, types;
+};
+static std::vector<RigidGroup> pack_groups(const ld_molecule_desc &m, int rows_max) {
+  std::vector<std::vector<int>> by_type(169);
+  for (int i = 0; i < m.n_atoms; ++i) by_type[m.dfire_type[i]].push_back(i);
+  std::vector<RigidGroup> groups;
+  std::vector<std::pair<int, std::vector<int>>> pieces;  // (type, atoms) with < 32 atoms
+  for (int t = 0; t < 169; ++t) {
+    const std::vector<int> &a = by_type[t];
+    size_t pos = 0;
+    for (; a.size() - pos >= 32; pos += 32) {
+      RigidGroup g;
+      g.atoms.assign(a.begin() + pos, a.begin() + pos + 32);
+      g.types.push_back(t);
+      groups.push_back(std::move(g));
+    }
+    if (pos < a.size()) pieces.emplace_back(t, std::vector<int>(a.begin() + pos, a.end()));
+  }
+  std::stable_sort(pieces.begin(), pieces.end(),
+                   [](const auto &x, const auto &y) { return x.second.size() > y.second.size(); });
+  const size_t first_open = groups.size();
+  for (auto &pc : pieces) {
+    size_t k = first_open;
+    for (; k < groups.size(); ++k)
+      if (groups[k].atoms.size() + pc.second.size() <= 32 && (int)groups[k].types.size() < rows_max) break;
+    if (k == groups.size()) groups.emplace_back();
+    groups[k].atoms.insert(groups[k].atoms.end(), pc.second.begin(), pc.second.end());
+    groups[k].types.push_back(pc.first);
+  }
+  return groups;
+}
+
+static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMol &L) {
+  const DeviceComplex &cx = h->cx;
+  const ld_molecule_desc &R = desc->receptor;
+  h->rigid_ok = false;
+  if (cx.method != 0) { h->rigid_info = "rigid path off: not DFIRE"; return LD_OK; }
+  if (cx.n_lig_modes > 0) { h->rigid_info = "rigid path off: the ligand has ANM modes"; return LD_OK; }
+  if (cx.n_rec == 0 || cx.n_lig == 0) { h->rigid_info = "rigid path off: empty partner"; return LD_OK; }
+  if (cx.n_lig_tiles > 65535) { h->rigid_info = "rigid path off: ligand tile ids exceed 16 bits"; return LD_OK; }
+  const long avail = (long)h->max_smem_optin - (long)rigid_smem_bytes(cx.n_lig_pad, 0);
+  const int rows_max = (int)std::min<long>(RG_MAX_ROWS, avail / RG_ROW_BYTES);
+  if (rows_max < 1) { h->rigid_info = "rigid path off: ligand + one table row exceed shared memory"; return LD_OK; }
+
+  RigidComplex &rc = h->rc;
+  rc = RigidComplex{};
+  std::vector<RigidGroup> groups = pack_groups(R, rows_max);
+  // most expensive first: protein atoms meet the ligand, membrane beads (type 167) rarely do
+  std::vector<int> order(groups.size());
+  std::iota(order.begin(), order.end(), 0);
+  auto weight = [&](int g) {
+    int w = 0;
+    for (int a : groups[g].atoms) w += R.dfire_type[a] == 167 ? 1 : 8;
+    return w;
+  };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight(a) > weight(b); });
+
+  const int ng = (int)groups.size(), npos = ng * 32;
+  const int nrm = cx.n_rec_modes;
+  std::vector<double> x(npos, REC_PAD), y(npos, REC_PAD), z(npos, REC_PAD);
+  std::vector<int> slot(npos, -1), toff(npos, 0), gtypes((size_t)ng * RG_MAX_ROWS, -1), inv(R.n_atoms, -1);
+  std::vector<double> modes((size_t)nrm * 3 * npos, 0.0);
+  h->rec_perm_r.assign(npos, -1);
+  for (int g = 0; g < ng; ++g) {
+    for (size_t r = 0; r < groups[g].types.size(); ++r) gtypes[(size_t)g * RG_MAX_ROWS + r] = groups[g].types[r];
+    for (size_t k = 0; k < groups[g].atoms.size(); ++k) {
+      const int a = groups[g].atoms[k], pos = g * 32 + (int)k;
+      x[pos] = R.coords[3 * a]; y[pos] = R.coords[3 * a + 1]; z[pos] = R.coords[3 * a + 2];
+      const int ty = R.dfire_type[a];
+      slot[pos] = (int)(std::find(groups[g].types.begin(), groups[g].types.end(), ty) - groups[g].types.begin());
+      toff[pos] = ty * DFIRE_ROW;
+      inv[a] = pos;
+      h->rec_perm_r[pos] = a;
+      for (int m = 0; m < nrm; ++m)
+        for (int d = 0; d < 3; ++d)
+          modes[((size_t)m * 3 + d) * npos + pos] = R.modes[((size_t)m * R.n_atoms + a) * 3 + d];
+    }
+  }
+  std::vector<int> rst_idx, mem_idx;
+  for (int r = 0; r < R.n_restraints; ++r)
+    for (int k = R.rst_offsets[r]; k < R.rst_offsets[r + 1]; ++k) rst_idx.push_back(inv[R.rst_atoms[k]]);
+  for (int k = 0; k < R.n_membrane; ++k) mem_idx.push_back(inv[R.membrane[k]]);
+
+  // table rows re-indexed by the truncated bin-space value (indices 4..28 -> DIST_TO_BINS, src/dfire.rs:49-53,337)
+  const size_t row8 = RG_ROW_BYTES / 8;
+  std::vector<double> potx(169 * row8, 0.0);
+  for (int ta = 0; ta < 169; ++ta)
+    for (int tb = 0; tb < 169; ++tb)
+      for (int sidx = 0; sidx < RG_SLOTS; ++sidx) {
+        const int idx = sidx + RG_SLOT0;
+        const int bin = idx <= 2 ? 0 : (idx <= 15 ? idx - 2 : 13 + ((idx - 15) >> 1));  // idx -1 -> 0
+        potx[ta * row8 + (size_t)tb * RG_SLOTS + sidx] = desc->dfire_potential[(size_t)ta * DFIRE_ROW + tb * 20 + bin];
+      }
+
+  // ligand, local frame, f32 + column offset
+  std::vector<float4> l4(cx.n_lig_pad);
+  for (int j = 0; j < cx.n_lig_pad; ++j) {
+    if (j < cx.n_lig) {
+      l4[j] = make_float4((float)L.x[j], (float)L.y[j], (float)L.z[j], (float)((L.tb20[j] / 20) * RG_SLOTS));
+    } else {
+      l4[j] = make_float4(1.0e6f, 1.0e6f, 1.0e6f, 0.f);
+    }
+  }
+
+  // cell grid over the ligand's bounding box grown by the cut-off; a cell lists every tile with an atom
+  // within 15 A + slack of the cell's box (slack: f32 cell assignment + the classification margin delta)
+  double cell = 3.0;
+  if (const char *e = getenv("LDB200_CELL")) cell = std::max(1.0, std::min(8.0, atof(e)));
+  const double reach = 15.0 + 0.01;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  const std::vector<double> *LC[3] = {&L.x, &L.y, &L.z};
+  for (int j = 0; j < cx.n_lig; ++j)
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::min(lo[d], (*LC[d])[j]);
+      hi[d] = std::max(hi[d], (*LC[d])[j]);
+    }
+  float g0[3];
+  int nc[3];
+  const float inv_h = (float)(1.0 / cell);
+  const double hh = 1.0 / (double)inv_h;  // the cell size the device's (f - g0) * inv_h implies
+  double maxabs = 0.0;
+  for (int d = 0; d < 3; ++d) {
+    g0[d] = (float)(lo[d] - reach - 0.05);
+    nc[d] = (int)std::floor((hi[d] + reach + 0.05 - (double)g0[d]) / hh) + 1;
+    maxabs = std::max(maxabs, std::max(std::fabs((double)g0[d]), std::fabs((double)g0[d] + nc[d] * hh)));
+  }
+  const size_t ncell = (size_t)nc[0] * nc[1] * nc[2];
+  if (ncell > ((size_t)1 << 26)) { h->rigid_info = "rigid path off: cell grid too large"; return LD_OK; }
+  std::vector<std::vector<unsigned short>> lists(ncell);
+  std::vector<int> stamp(ncell, -1);
+  const double reach2 = reach * reach;
+  for (int t = 0; t < cx.n_lig_tiles; ++t)
+    for (int j = t * LIG_TILE; j < std::min((t + 1) * LIG_TILE, cx.n_lig); ++j) {
+      // the f32 value the kernel uses and the f64 one differ by < 1e-5: inside the slack
+      const double a[3] = {L.x[j], L.y[j], L.z[j]};
+      int c0[3], c1[3];
+      for (int d = 0; d < 3; ++d) {
+        c0[d] = std::max(0, (int)std::floor((a[d] - reach - (double)g0[d]) / hh));
+        c1[d] = std::min(nc[d] - 1, (int)std::floor((a[d] + reach - (double)g0[d]) / hh));
+      }
+      for (int cz = c0[2]; cz <= c1[2]; ++cz) {
+        const double bz0 = (double)g0[2] + cz * hh, ez = std::max(0.0, std::max(bz0 - a[2], a[2] - (bz0 + hh)));
+        for (int cy = c0[1]; cy <= c1[1]; ++cy) {
+          const double by0 = (double)g0[1] + cy * hh, ey = std::max(0.0, std::max(by0 - a[1], a[1] - (by0 + hh)));
+          if (ez * ez + ey * ey > reach2) continue;
+          for (int cxx = c0[0]; cxx <= c1[0]; ++cxx) {
+            const double bx0 = (double)g0[0] + cxx * hh, ex = std::max(0.0, std::max(bx0 - a[0], a[0] - (bx0 + hh)));
+            if (ex * ex + ey * ey + ez * ez > reach2) continue;
+            const size_t c = ((size_t)cz * nc[1] + cy) * nc[0] + cxx;
+            if (stamp[c] != t) {
+              stamp[c] = t;
+              lists[c].push_back((unsigned short)t);
+            }
+          }
+        }
+      }
+    }
+  std::vector<uint2> cells(ncell);
+  size_t total = 0, longest = 0, nonempty = 0;
+  for (size_t c = 0; c < ncell; ++c) {
+    cells[c] = make_uint2((unsigned)total, (unsigned)lists[c].size());
+    total += (lists[c].size() + 1) & ~(size_t)1;  // lists start on even offsets (the kernel reads entry pairs)
+    longest = std::max(longest, lists[c].size());
+    nonempty += !lists[c].empty();
+  }
+  if (total >= ((size_t)1 << 31)) { h->rigid_info = "rigid path off: cell lists too large"; return LD_OK; }
+  std::vector<unsigned short> flat(std::max<size_t>(total, 2), 0);
+  for (size_t c = 0; c < ncell; ++c) std::copy(lists[c].begin(), lists[c].end(), flat.begin() + cells[c].x);
+
+  int rcode;
+#define UPR(vec, field) \
+  if ((rcode = upload(h, vec, &rc.field)) != LD_OK) return rcode
+  UPR(x, rec_x); UPR(y, rec_y); UPR(z, rec_z); UPR(slot, rec_slot); UPR(toff, rec_toff);
+  UPR(gtypes, group_types); UPR(order, group_order); UPR(modes, rec_modes);
+  UPR(l4, lig4); UPR(potx, potx); UPR(cells, cells); UPR(flat, cell_tiles);
+#undef UPR
+  rc.n_groups = ng; rc.n_rec_pos = npos;
+  rc.n_lig = cx.n_lig; rc.n_lig_pad = cx.n_lig_pad; rc.n_lig_tiles = cx.n_lig_tiles;
+  rc.n_rec_modes = nrm; rc.pose_len = cx.pose_len; rc.rows_max = rows_max;
+  rc.lig_x = cx.lig_x; rc.lig_y = cx.lig_y; rc.lig_z = cx.lig_z; rc.lig_tb20 = cx.lig_tb20; rc.pot = cx.pot;
+  rc.gx0 = g0[0]; rc.gy0 = g0[1]; rc.gz0 = g0[2]; rc.inv_h = inv_h;
+  rc.nx = nc[0]; rc.ny = nc[1]; rc.nz = nc[2];
+  const double delta = 2.0e-4 + 1.3e-5 * maxabs;  // 2x the |d2f - dist_ref| bound derived at rigid_row()
+  rc.thr_out = (float)(225.0 + delta);
+  rc.half_minus_eps = (float)(0.5 - 2.5e-5);
+  rc.delta = (float)(1.02 * delta);
+  if (!(delta < 0.01)) { h->rigid_info = "rigid path off: ligand extent makes the FP32 margin too wide"; return LD_OK; }
+
+  // what finalize_kernel sees: groups play the role of receptor tiles
+  h->cxr = cx;
+  h->cxr.n_rec_tiles = ng;
+  h->cxr.n_rec_pad = npos;
+  if ((rcode = upload(h, rst_idx, &h->cxr.rec_rst_idx)) != LD_OK) return rcode;
+  if ((rcode = upload(h, mem_idx, &h->cxr.membrane_idx)) != LD_OK) return rcode;
+  CU(cudaMalloc(reinterpret_cast<void **>(&h->d_unit_counter), sizeof(unsigned)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&h->d_rc), sizeof(RigidComplex)));
+  CU(cudaMemcpy(h->d_rc, &rc, sizeof(RigidComplex), cudaMemcpyHostToDevice));
+  CU(cudaFuncSetAttribute(dfire_rigid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CU(cudaFuncSetAttribute(dfire_rigid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  char buf[512];
+  snprintf(buf, sizeof buf,
+           "rigid path on: %d receptor groups (%.1f atoms/group, <=%d table rows each), cell %.2f A, grid %dx%dx%d, "
+           "%zu non-empty cells, %zu list entries (longest %zu), delta %.2e, smem %zu B",
+           ng, (double)cx.n_rec / ng, rows_max, hh, nc[0], nc[1], nc[2], nonempty, total, longest, delta,
+           rigid_smem_bytes(cx.n_lig_pad, rows_max));
+  h->rigid_info = buf;
+  h->rigid_ok = true;
   return LD_OK;
 }
 
@@ -281,7 +511,10 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
   CU(cudaFuncSetAttribute(dfire_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CU(cudaFuncSetAttribute(dna_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CU(cudaFuncSetAttribute(dna_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  return LD_OK;
+  if (const char *e = getenv("LDB200_PATH")) {  // benchmarking aid; ld_set_path() is the API
+    if (!strcmp(e, "generic")) h->path_mode = LD_PATH_GENERIC;
+  }
+  return build_rigid(desc, h, L);
 }
 
 extern "C" int ld_create(const ld_complex_desc *desc, ld_handle **out) {
@@ -314,6 +547,15 @@ extern "C" int ld_set_rec_splits(ld_handle *h, int32_t splits) {
   h->forced_splits = splits;
   return LD_OK;
 }
+
+extern "C" int ld_set_path(ld_handle *h, int32_t path) {
+  if (!h || path < LD_PATH_AUTO || path > LD_PATH_RIGID) return fail(LD_EINVAL, "ld_set_path: bad argument");
+  if (path == LD_PATH_RIGID && !h->rigid_ok) return fail(LD_EINVAL, "ld_set_path: " + h->rigid_info);
+  h->path_mode = path;
+  return LD_OK;
+}
+
+extern "C" const char *ld_path_info(const ld_handle *h) { return h ? h->rigid_info.c_str() : ""; }
 
 extern "C" int ld_set_profiling(ld_handle *h, int32_t on) {
   if (!h) return fail(LD_EINVAL, "ld_set_profiling: NULL handle");
@@ -373,22 +615,29 @@ static int choose_splits(const ld_handle *h, int64_t n) {
   return (int)std::max<int64_t>(1, s);
 }
 
-static int64_t chunk_limit(const ld_handle *h) {
+static bool use_rigid(const ld_handle *h) { return h->rigid_ok && h->path_mode != LD_PATH_GENERIC; }
+
+static int64_t chunk_limit(const ld_handle *h, bool rigid) {
+  if (rigid) return (int64_t)1 << 20;  // no per-pose coordinate blocks on this path (~2 KB per pose)
   const size_t per_pose = h->lig_block + h->rec_block + 64;
   int64_t c = (int64_t)((size_t)1 << 30) / (int64_t)per_pose;  // <= 1 GiB of coordinate blocks in flight
   return std::max<int64_t>(1, std::min<int64_t>(c, 16384));
 }
 
-static int ensure_chunk(ld_handle *h, int64_t chunk, int splits) {
+static int ensure_chunk(ld_handle *h, int64_t chunk, int splits, bool need_blocks) {
+  int rc;
+  if (need_blocks && chunk > h->cap_blocks) {
+    if ((rc = regrow(&h->d_lig_blocks, (size_t)chunk * h->lig_block)) != LD_OK) return rc;
+    if ((rc = regrow(&h->d_rec_blocks, (size_t)chunk * h->rec_block)) != LD_OK) return rc;
+    h->cap_blocks = chunk;
+  }
   if (chunk <= h->cap_chunk && splits <= h->cap_splits) return LD_OK;
   chunk = std::max(chunk, h->cap_chunk);
   splits = std::max(splits, h->cap_splits);
   const int lig_words = (h->cx.n_lig_pad + 31) / 32;
-  int rc;
-  if ((rc = regrow(&h->d_lig_blocks, (size_t)chunk * h->lig_block)) != LD_OK) return rc;
-  if ((rc = regrow(&h->d_rec_blocks, (size_t)chunk * h->rec_block)) != LD_OK) return rc;
-  if ((rc = regrow(&h->d_partials, (size_t)chunk * std::max(1, h->cx.n_rec_tiles) * 2)) != LD_OK) return rc;
-  if ((rc = regrow(&h->d_iface_rec, (size_t)chunk * std::max(1, h->cx.n_rec_tiles))) != LD_OK) return rc;
+  const int tiles = std::max(1, std::max(h->cx.n_rec_tiles, h->rigid_ok ? h->rc.n_groups : 0));
+  if ((rc = regrow(&h->d_partials, (size_t)chunk * tiles * 2)) != LD_OK) return rc;
+  if ((rc = regrow(&h->d_iface_rec, (size_t)chunk * tiles)) != LD_OK) return rc;
   if ((rc = regrow(&h->d_iface_lig, (size_t)chunk * splits * std::max(1, lig_words))) != LD_OK) return rc;
   h->cap_chunk = chunk;
   h->cap_splits = splits;
@@ -429,15 +678,73 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
   h->prof_used = 0;
   h->last_stream = st;
   if (n == 0) return LD_OK;
-  const int64_t climit = chunk_limit(h);
+  const int64_t climit = chunk_limit(h, use_rigid(h));
   const int lig_words = (cx.n_lig_pad + 31) / 32;
   const bool detail = d_detail != nullptr;
-  int launches = 0;
+  int launches = 0, pair_launches = 0;
   for (int64_t p0 = 0; p0 < n; p0 += climit) {
     const int64_t nc = std::min(climit, n - p0);
     const int splits = choose_splits(h, nc);
     int rc;
-    if ((rc = ensure_chunk(h, nc, splits)) != LD_OK) return rc;
+    const bool rigid = use_rigid(h);
+    if ((rc = ensure_chunk(h, nc, rigid ? 1 : splits, !rigid)) != LD_OK) return rc;
+    if (rigid) {
+      const RigidComplex &rg = h->rc;
+      BatchBuffers bb{};
+      bb.poses = d_poses + (size_t)p0 * cx.pose_len;
+      bb.partials = h->d_partials;
+      bb.iface_rec = h->d_iface_rec;
+      bb.iface_lig = h->d_iface_lig;
+      bb.energies = d_energies + p0;
+      bb.detail = detail ? (void *)(d_detail + p0) : nullptr;
+      bb.rec_splits = 1;
+      bb.tiles_per_split = rg.n_groups;
+      bb.lig_words = lig_words;
+      h->stats.rec_splits = 1;
+      h->stats.path = LD_PATH_RIGID;
+      if (nc > h->cap_prep) {
+        if ((rc = regrow(&h->d_prep, (size_t)nc * RG_PREP)) != LD_OK) return rc;
+        h->cap_prep = nc;
+      }
+      if ((rc = prof_mark(h, st)) != LD_OK) return rc;
+      // per-pose rotation data (the only "transform" on this path: nothing is moved per atom)
+      rigid_prep_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(bb.poses, (int)nc, cx.pose_len, h->d_prep);
+      ++launches;
+      if ((rc = prof_mark(h, st)) != LD_OK) return rc;
+      CU(cudaMemsetAsync(h->d_iface_lig, 0, (size_t)nc * lig_words * sizeof(unsigned), st));
+      CU(cudaMemsetAsync(h->d_unit_counter, 0, sizeof(unsigned), st));
+      // work units: (group, range of poses); ~16 units per SM and group changes kept rare
+      int64_t ppu = (nc * rg.n_groups + (int64_t)h->sm_count * 16 - 1) / ((int64_t)h->sm_count * 16);
+      ppu = std::max<int64_t>(RG_WARPS, std::min<int64_t>(ppu, 1024));
+      const int n_chunks = (int)((nc + ppu - 1) / ppu);
+      const int64_t n_units = (int64_t)n_chunks * rg.n_groups;
+      const unsigned grid = (unsigned)std::min<int64_t>(h->sm_count, n_units);
+      const size_t smem = rigid_smem_bytes(rg.n_lig_pad, rg.rows_max);
+      if (detail)
+        dfire_rigid_kernel<true><<<grid, RG_THREADS, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->d_unit_counter,
+                                                             h->d_rc, h->d_prep);
+      else
+        dfire_rigid_kernel<false><<<grid, RG_THREADS, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->d_unit_counter,
+                                                             h->d_rc, h->d_prep);
+      ++launches;
+      ++pair_launches;
+      if ((rc = prof_mark(h, st)) != LD_OK) return rc;
+      const unsigned fgrid = (unsigned)((nc + 3) / 4);
+      if (detail) finalize_kernel<true><<<fgrid, 128, 0, st>>>(h->cxr, bb, (int)nc);
+      else finalize_kernel<false><<<fgrid, 128, 0, st>>>(h->cxr, bb, (int)nc);
+      ++launches;
+      if ((rc = prof_mark(h, st)) != LD_OK) return rc;
+      CU(cudaGetLastError());
+      if (host_ifr) {
+        CU(cudaMemcpyAsync(host_ifr->data() + (size_t)p0 * rg.n_groups, h->d_iface_rec,
+                           (size_t)nc * rg.n_groups * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(host_ifl->data() + (size_t)p0 * lig_words, h->d_iface_lig,
+                           (size_t)nc * lig_words * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+      }
+      continue;
+    }
+    h->stats.path = LD_PATH_GENERIC;
     BatchBuffers bb{};
     bb.poses = d_poses + (size_t)p0 * cx.pose_len;
     bb.lig_blocks = h->d_lig_blocks;
@@ -466,6 +773,7 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
         else dna_pair_kernel<false><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
       }
       ++launches;
+      ++pair_launches;
     } else {
       
       CU(cudaMemsetAsync(h->d_iface_lig, 0, (size_t)nc * splits * std::max(1, lig_words) * sizeof(unsigned), st));
@@ -492,6 +800,7 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
     }
   }
   h->stats.kernel_launches = launches;
+  h->stats.pair_launches = pair_launches;
   return LD_OK;
 }
 
@@ -524,8 +833,10 @@ static int score_host(ld_handle *h, int64_t n, const double *poses, double *ener
   const int lig_words = (cx.n_lig_pad + 31) / 32;
   std::vector<unsigned> ifr, ifl;
   const bool want_iface = want_detail && (iface_rec || iface_lig);
+  const bool rigid = use_rigid(h);
+  const int rec_tiles = rigid ? h->rc.n_groups : cx.n_rec_tiles;
   if (want_iface) {
-    ifr.assign((size_t)n * std::max(1, cx.n_rec_tiles), 0u);
+    ifr.assign((size_t)n * std::max(1, rec_tiles), 0u);
     ifl.assign((size_t)n * std::max(1, lig_words), 0u);
   }
   rc = run_device(h, n, h->d_poses, h->d_energies, h->stream, want_detail ? h->d_detail : nullptr,
@@ -542,10 +853,13 @@ static int score_host(ld_handle *h, int64_t n, const double *poses, double *ener
   std::memcpy(energies, h->h_energies, (size_t)n * sizeof(double));
   if (want_iface) {
     for (int64_t p = 0; p < n; ++p) {
-      if (iface_rec)
-        for (int i = 0; i < cx.n_rec; ++i)
-          iface_rec[(size_t)p * cx.n_rec + h->rec_perm[i]] =
-              (ifr[(size_t)p * cx.n_rec_tiles + (i >> 5)] >> (i & 31)) & 1u;
+      if (iface_rec) {
+        const std::vector<int> &perm = rigid ? h->rec_perm_r : h->rec_perm;
+        const int npos = rigid ? h->rc.n_rec_pos : cx.n_rec;
+        for (int i = 0; i < npos; ++i)
+          if (perm[i] >= 0)
+            iface_rec[(size_t)p * cx.n_rec + perm[i]] = (ifr[(size_t)p * rec_tiles + (i >> 5)] >> (i & 31)) & 1u;
+      }
       if (iface_lig)
         for (int j = 0; j < cx.n_lig; ++j)
           iface_lig[(size_t)p * cx.n_lig + h->lig_perm[j]] = (ifl[(size_t)p * lig_words + (j >> 5)] >> (j & 31)) & 1u;
@@ -573,11 +887,11 @@ extern "C" int ld_transform_batch(ld_handle *h, int64_t n, const double *poses, 
   int rc;
   if ((rc = ensure_poses(h, n, false)) != LD_OK) return rc;
   CU(cudaMemcpyAsync(h->d_poses, poses, (size_t)n * cx.pose_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  const int64_t climit = chunk_limit(h);
+  const int64_t climit = chunk_limit(h, false);
   std::vector<unsigned char> lb, rb;
   for (int64_t p0 = 0; p0 < n; p0 += climit) {
     const int64_t nc = std::min(climit, n - p0);
-    if ((rc = ensure_chunk(h, nc, 1)) != LD_OK) return rc;
+    if ((rc = ensure_chunk(h, nc, 1, true)) != LD_OK) return rc;
     BatchBuffers bb{};
     bb.poses = h->d_poses + (size_t)p0 * cx.pose_len;
     bb.lig_blocks = h->d_lig_blocks;

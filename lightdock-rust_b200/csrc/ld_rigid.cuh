@@ -1,0 +1,430 @@
+// ld_rigid.cuh — DFIRE pair loop (src/dfire.rs:325-345) for a RIGID ligand (no ligand ANM modes):
+// the fast path of the library, used by the 1k4c-class workloads.
+//
+// Idea.  |r - (R l + t)| = |R^-1 (r - t) - l|: instead of moving the 3,268 ligand atoms of every pose
+// into the lab frame, each receptor atom is moved into the ligand's LOCAL frame (one 3x3 f64 product
+// per atom and pose).  There the ligand never changes, so everything that depends on it is built once
+// in ld_create and shared by all poses:
+//   * lig4[]      f32 local coordinates + table column offset, resident in shared memory for the whole
+//                 life of a CTA (no per-pose staging, no transform kernel on this path);
+//   * a uniform cell grid over the ligand's bounding box grown by the 15 A cut-off; each cell lists the
+//                 ligand tiles (8 atoms) holding at least one atom within 15 A (+slack) of the cell box.
+//                 The per-pose culling of the generic kernel (sphere tests, levels A and B) becomes one
+//                 cell lookup per receptor atom.
+// Because the cell lookup is per ATOM, receptor atoms need no spatial coherence, so they are grouped
+// by DFIRE TYPE instead: a group is <= 32 atoms (one per lane) of <= 4 types, and the <= 4 table rows
+// those types index (169 ligand types x 25 reachable distance slots x f64 = 33.8 KB each) are pulled
+// into shared memory by TMA when a CTA switches group.  The table gather of the hot loop is therefore a
+// shared-memory load; the 4.57 MB table is read from L2 only on group switches and by the exact path.
+//
+// Work decomposition: persistent CTAs (one per SM, 32 warps).  A work unit is (receptor group, range of
+// poses); CTAs pull units from a global counter, group-major, so a CTA changes rows rarely.  Inside a
+// unit every warp pulls poses from a shared-memory counter and scores (its group x that pose) alone:
+// no CTA-wide barrier inside a unit, and a pose's result never depends on the batch it came in.
+//
+// Exactness.  Same contract as the generic kernel: the distance is classified in FP32 and the decision
+// is accepted only when it is PROVABLY the reference's FP64 decision; everything else (and every pair
+// in the thin 2.4-2.5 A shell around the 2.45 A interface edge) is re-evaluated with the reference's own
+// lab-frame FP64 arithmetic (rigid_exact_pair).  See the bound next to rigid_row().
+#pragma once
+#include "ld_kernels.cuh"
+
+namespace ldb200 {
+
+#ifndef LDB200_RG_THREADS
+#define LDB200_RG_THREADS 640
+#endif
+constexpr int RG_THREADS = LDB200_RG_THREADS;
+constexpr int RG_WARPS = RG_THREADS / 32;
+constexpr int RG_SLOT0 = -1;                        // first bin-space index held in a shared-memory row: rint(t - 0.5)
+                                                    // is -1 for t < 0 (dist < 0.25), which the reference's saturating
+                                                    // `d as usize` sends to index 0, so slot -1 repeats slot 0
+constexpr int RG_SLOTS = 30;                        // indices -1..28 (29, the cut-off itself, is never decided in FP32)
+constexpr int RG_PREP = 16;                         // doubles per pose written by rigid_prep_kernel
+constexpr int RG_TB_BYTES = RG_SLOTS * 8;           // one ligand type inside a row
+constexpr int RG_ROW_BYTES = (169 * RG_TB_BYTES + 15) / 16 * 16;  // 40,560
+constexpr int RG_MAX_ROWS = 4;
+constexpr float RG_MAGIC = 12582912.0f;             // 1.5 * 2^23: x + MAGIC rounds x to the nearest integer
+constexpr unsigned RG_MAGIC_BITS = 0x4B400000u;
+
+struct RigidComplex {
+  int n_groups, n_rec_pos;  // n_rec_pos = n_groups * 32 (type-grouped receptor positions, pads interspersed)
+  int n_lig, n_lig_pad, n_lig_tiles;
+  int n_rec_modes, pose_len;
+  int rows_max;
+  const double *rec_x, *rec_y, *rec_z;  // [n_rec_pos] lab frame, pads at REC_PAD
+  const int *rec_slot;                  // [n_rec_pos] which of the group's rows this atom indexes (0..3)
+  const int *rec_toff;                  // [n_rec_pos] type * 3380 (exact path)
+  const int *group_types;               // [n_groups][RG_MAX_ROWS] DFIRE type of each row, -1 = unused
+  const int *group_order;               // groups, most expensive first
+  const double *rec_modes;              // [k][3][n_rec_pos]
+  const float4 *lig4;                   // [n_lig_pad] local f32 x,y,z + (float)(type * RG_SLOTS)
+  const double *lig_x, *lig_y, *lig_z;  // [n_lig_pad] local f64 (exact path)
+  const unsigned short *lig_tb20;       // type * 20 (exact path)
+  const double *potx;                   // [169][RG_ROW_BYTES/8]: row ta = [tb][slot], slot s <-> index s+4
+  const double *pot;                    // the reference's table (exact path)
+  float gx0, gy0, gz0, inv_h;           // cell grid in the ligand frame
+  int nx, ny, nz;
+  const uint2 *cells;                   // [nz][ny][nx] {offset into cell_tiles, count}
+  const unsigned short *cell_tiles;
+  float thr_out;                        // 225 + delta
+  float half_minus_eps;                 // 0.5 - 2.5e-5 (the f32 evaluation error of t)
+  float delta;                          // 1.02 * delta: eps_t = 1.02 * delta / sqrt(d2f) + 2.5e-5
+};
+
+__host__ __device__ inline size_t rigid_smem_bytes(int n_lig_pad, int rows) {
+  return 128 + (size_t)n_lig_pad * 16 + (size_t)rows * RG_ROW_BYTES;
+}
+
+extern __shared__ __align__(128) unsigned char smem_rigid[];
+// Loads at byte offsets of the kernel's dynamic shared memory (plain C++ so the scheduler may interleave the
+// eight pairs of an item; the array is known to live in shared memory, so these are LDS with 32-bit addresses).
+__device__ __forceinline__ double lds_f64(uint32_t off) { return *reinterpret_cast<const double *>(smem_rigid + off); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Per-pose quantities shared by the 100+ (group, pose) work items of a pose, computed once per batch:
+//   prep[0..8]  M = R^T (row major), R the rotation of q: q v q^-1 is a rotation for any q != 0 (src/qt.rs:57-61)
+//   prep[9..11] M t          -> ligand-frame position of a lab-frame point r is  M r - M t
+//   prep[12..15] q^-1 = conj(q)/norm2(q) exactly as Quaternion::inverse computes it (src/qt.rs:24-34,48-50),
+//               for the exact path.
+__global__ void __launch_bounds__(256) rigid_prep_kernel(const double *poses, int n_poses, int pose_len, double *prep) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_poses) return;
+  const double *pose = poses + (size_t)p * pose_len;
+  const double tx = pose[0], ty = pose[1], tz = pose[2];
+  const double qw = pose[3], qx = pose[4], qy = pose[5], qz = pose[6];
+  const double n2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(qw, qw), __dmul_rn(qx, qx)), __dmul_rn(qy, qy)),
+                              __dmul_rn(qz, qz));
+  const double s2 = 2.0 / n2;
+  const double xx = qx * qx * s2, yy = qy * qy * s2, zz = qz * qz * s2;
+  const double xy = qx * qy * s2, xz = qx * qz * s2, yz = qy * qz * s2;
+  const double wx = qw * qx * s2, wy = qw * qy * s2, wz = qw * qz * s2;
+  // columns of R = rows of R^T
+  const double m[9] = {1.0 - (yy + zz), xy + wz, xz - wy, xy - wz, 1.0 - (xx + zz), yz + wx, xz + wy, yz - wx,
+                       1.0 - (xx + yy)};
+  double *o = prep + (size_t)p * RG_PREP;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) o[i] = m[i];
+  o[9] = fma(m[0], tx, fma(m[1], ty, m[2] * tz));
+  o[10] = fma(m[3], tx, fma(m[4], ty, m[5] * tz));
+  o[11] = fma(m[6], tx, fma(m[7], ty, m[8] * tz));
+  o[12] = __ddiv_rn(qw, n2); o[13] = __ddiv_rn(-qx, n2); o[14] = __ddiv_rn(-qy, n2); o[15] = __ddiv_rn(-qz, n2);
+}
+
+// The reference's arithmetic for ONE pair, lab frame, never fused: src/qt.rs:57-61,174-185 (rotate),
+// src/dfire.rs:286-288 (translate), :304-320 (receptor ANM), :331-342 (distance, bin, interface).
+// Returns -1 if the pair is outside the cut-off, else bin | (interface ? 32 : 0).
+__device__ __noinline__ int rigid_exact_pair(const RigidComplex *__restrict__ rcp, const double *pose,
+                                             const double *prep, int ia, int j) {
+  const RigidComplex &rc = *rcp;  // the copy in global memory: this path is rare and must not pin registers
+  const double tx = pose[0], ty = pose[1], tz = pose[2];
+  const Quat q = {pose[3], pose[4], pose[5], pose[6]};
+  const Quat qi = {prep[12], prep[13], prep[14], prep[15]};
+  const Quat v = {0.0, rc.lig_x[j], rc.lig_y[j], rc.lig_z[j]};
+  const Quat r = qmul(qmul(q, v), qi);
+  const double lx = __dadd_rn(r.x, tx), ly = __dadd_rn(r.y, ty), lz = __dadd_rn(r.z, tz);
+  double x = rc.rec_x[ia], y = rc.rec_y[ia], z = rc.rec_z[ia];
+  for (int k = 0; k < rc.n_rec_modes; ++k) {
+    const double e = pose[7 + k];
+    const double *m = rc.rec_modes + (size_t)k * 3 * rc.n_rec_pos;
+    x = __dadd_rn(x, __dmul_rn(m[ia], e));
+    y = __dadd_rn(y, __dmul_rn(m[rc.n_rec_pos + ia], e));
+    z = __dadd_rn(z, __dmul_rn(m[2 * rc.n_rec_pos + ia], e));
+  }
+  const double ex = __dsub_rn(x, lx), ey = __dsub_rn(y, ly), ez = __dsub_rn(z, lz);
+  const double dist = __dadd_rn(__dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey)), __dmul_rn(ez, ez));
+  if (!(dist <= 225.0)) return -1;
+  const double d = __dsub_rn(__dmul_rn(__dsqrt_rn(dist), 2.0), 1.0);
+  const int bin = dfire_bin_of((int)d);
+  return bin | (d <= 3.9 ? 32 : 0);
+}
+
+// One row of <= 32 work items; an item is (receptor atom = owner lane, ligand tile of 8 atoms).
+//
+// FP32 classification.  With a = local receptor atom (f64 product rounded to f32), l = local ligand atom
+// (f64 rounded to f32), M = largest |coordinate| inside the cell grid:
+//   |d2f - dist_ref| <= 2*sqrt(3)*15.1*(2^-23 M + 2^-24*15.1) + 3*2^-24*228 + f64 noise  <  6.3e-6 M + 9e-5,
+// delta = 1.3e-5 M + 2e-4 (2x that bound).  Bin-space value t = 2 sqrt(dist) - 1 (src/dfire.rs:336):
+//   u = 2*d2f*rsqrt.approx(d2f) - 1.5 = t_f32 - 0.5,
+//   |t_f32 - t_ref| <= 2|sqrt(d2f) - sqrt(dist_ref)| + 6.4e-6 <= delta/sqrt(min(d2f, dist_ref)) + 6.4e-6
+//                   <= 1.001*delta*rsqrt(d2f) + 6.4e-6 =: E_t            (d2f >= 6.25, delta < 0.01),
+//   m = u + MAGIC  -> rint(u) in the low mantissa bits,  g = u - rint(u) = frac(t_f32) - 0.5 (exact).
+// If |g| <= 0.5 - eps_t (eps_t = 1.02*delta*rsqrt.approx(d2f) + 2.5e-5 > E_t) then floor(t_ref) = rint(u): the bin
+// is the reference's.
+// d2f <= 225 + delta together with that leaves indices 0..28 only (index 29 needs t >= 29 + eps_t, i.e.
+// d2f > 225 + delta); such a pair's table value is added in the hot loop, every other pair with
+// d2f <= 225 + delta goes to rigid_exact_pair.  The interface test t <= 3.9 (dist <= 6.0025) is kept out of
+// the hot loop: a per-item min(d2f) sends the rare items with a contact below 2.45 A + to a second pass
+// that decides it in FP32 outside 6.0025 +- delta and with rigid_exact_pair inside.
+__device__ __forceinline__ float4 lds_f4(uint32_t off) { return *reinterpret_cast<const float4 *>(smem_rigid + off); }
+
+template <bool DETAIL>
+__device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuffers &bb, uint32_t l4_addr,
+                                          uint32_t lane_sw, bool active, int o, int lt, float rxf, float ryf,
+                                          float rzf, unsigned rowoff, int p, int pos_base, double &acc0,
+                                          double &acc1, unsigned &ifr_mask, const RigidComplex *rc_dev,
+                                          const double *prep) {
+  ld_pose_detail *dt = DETAIL ? reinterpret_cast<ld_pose_detail *>(bb.detail) + p : nullptr;
+  const int lane = threadIdx.x & 31;
+  const float ax = __shfl_sync(0xffffffffu, rxf, o), ay = __shfl_sync(0xffffffffu, ryf, o),
+              az = __shfl_sync(0xffffffffu, rzf, o);
+  const unsigned rb = __shfl_sync(0xffffffffu, rowoff, o);
+  if (!active) return;
+  const float thr_out = rc.thr_out, hme = rc.half_minus_eps, delta = rc.delta;
+  const int jbase = lt * LIG_TILE;
+  // tile base (128-byte aligned) | per-lane slot: atom (k ^ lane) & 7 of the tile, so that any 8 consecutive
+  // lanes read 8 different 16-byte slots -> conflict-free LDS.128 whatever tiles the lanes hold
+  const uint32_t tile_addr = l4_addr + (uint32_t)lt * (LIG_TILE * 16);
+  unsigned slow_bits = 0u;
+  unsigned n_fast = 0;
+  float mind2 = 3.0e38f;
+#pragma unroll
+  for (int k = 0; k < LIG_TILE; ++k) {
+    const float4 a = lds_f4(tile_addr | (lane_sw ^ (uint32_t)(k << 4)));
+    const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    mind2 = fminf(mind2, d2);
+    const float rs = rsqrt_approx(d2);
+    const float d = d2 * rs;
+    const float u = fmaf(d, 2.0f, -1.5f);  // t - 0.5 in [-1.5, 28.5]: rint(u) = -1 for t < 0, see RG_SLOT0
+    const float m = __fadd_rn(u, RG_MAGIC);
+    const float g = __fsub_rn(u, __fsub_rn(m, RG_MAGIC));
+    const bool inr = d2 <= thr_out;
+    const bool fast = inr & (fmaf(delta, rs, fabsf(g)) <= hme);  // |g| + delta/d <= 0.5 - 2.5e-5
+    if (inr & !fast) slow_bits |= 1u << k;
+    // a.w = ligand type * RG_SLOTS as a float: adding it to m (both integers < 2^24) is exact and leaves
+    // MAGIC_BITS + type*RG_SLOTS + index in the mantissa -> one shift-add gives the byte address
+    const uint32_t addr = ((uint32_t)__float_as_int(__fadd_rn(m, a.w)) << 3) + rb;
+    if (fast) {
+      const double v = lds_f64(addr);
+      if (k & 1) acc1 = __dadd_rn(acc1, v);
+      else acc0 = __dadd_rn(acc0, v);
+      if (DETAIL) {
+        ++n_fast;
+        atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[dfire_bin_fast(__float_as_int(m) - (int)RG_MAGIC_BITS)]),
+                  1ull);
+      }
+    }
+  }
+  if (mind2 <= 6.0025f + delta) {  // rare: a contact near or below the 2.45 A interface edge (src/dfire.rs:339-342)
+    const double *pose = bb.poses + (size_t)p * rc_dev->pose_len;
+    for (int k = 0; k < LIG_TILE; ++k) {
+      if ((slow_bits >> k) & 1u) continue;  // the exact path below owns this pair entirely
+      const float4 a = lds_f4(tile_addr | (lane_sw ^ (uint32_t)(k << 4)));
+      const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
+      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));  // same operations as above: same bits
+      if (d2 > 6.0025f + delta) continue;
+      const int j = jbase + ((k ^ lane) & (LIG_TILE - 1));
+      bool ifc = d2 < 6.0025f - delta;  // t <= 3.9 <=> dist <= 6.0025, decided in FP32 outside +-delta
+      if (!ifc) ifc = (rigid_exact_pair(rc_dev, pose, prep, pos_base + o, j) & ~31) == 32;  // -1 -> all bits set -> false
+      if (ifc) {
+        ifr_mask |= 1u << o;
+        atomicOr(&bb.iface_lig[(size_t)p * bb.lig_words + (j >> 5)], 1u << (j & 31));
+        if (DETAIL) atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_interface_pairs), 1ull);
+      }
+    }
+  }
+  if (DETAIL) {
+    atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_pairs_tested),
+              (unsigned long long)min(LIG_TILE, rc.n_lig - jbase));
+    if (n_fast) atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_in_cutoff), (unsigned long long)n_fast);
+  }
+  if (slow_bits) {  // rare: near a decision threshold, or closer than 2.5 A
+    double extra = 0.0;
+    const int toff = rc_dev->rec_toff[pos_base + o];
+    const double *pose = bb.poses + (size_t)p * rc_dev->pose_len;
+    for (unsigned b = slow_bits; b; b &= b - 1) {
+      const int j = jbase + (((__ffs(b) - 1) ^ lane) & (LIG_TILE - 1));
+      const int r = rigid_exact_pair(rc_dev, pose, prep, pos_base + o, j);
+      if (DETAIL) atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_exact_fallback), 1ull);
+      if (r >= 0) {
+        extra = __dadd_rn(extra, __ldg(rc_dev->pot + toff + rc_dev->lig_tb20[j] + (r & 31)));
+        if (r & 32) {
+          ifr_mask |= 1u << o;
+          atomicOr(&bb.iface_lig[(size_t)p * bb.lig_words + (j >> 5)], 1u << (j & 31));
+          if (DETAIL) atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_interface_pairs), 1ull);
+        }
+        if (DETAIL) {
+          atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_in_cutoff), 1ull);
+          atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[r & 31]), 1ull);
+        }
+      }
+    }
+    acc0 = __dadd_rn(acc0, extra);
+  }
+}
+
+template <bool DETAIL>
+__global__ void __launch_bounds__(RG_THREADS, 1)
+    dfire_rigid_kernel(const RigidComplex rc, const BatchBuffers bb, int n_poses, int poses_per_unit, int n_chunks,
+                       unsigned *unit_counter, const RigidComplex *rc_dev, const double *prep_all) {
+  unsigned char *smem_raw = smem_rigid;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
+  int *s_unit = reinterpret_cast<int *>(smem_raw + 8);
+  int *s_pose_next = reinterpret_cast<int *>(smem_raw + 12);
+  float4 *l4 = reinterpret_cast<float4 *>(smem_raw + 128);
+  unsigned char *rows = smem_raw + 128 + (size_t)rc.n_lig_pad * 16;
+  const int lane = threadIdx.x & 31;
+  const uint32_t l4_addr = 128u /* byte offset of l4 in smem_rigid */, lane_sw = (uint32_t)(lane & 7) << 4;
+  const int n_units = rc.n_groups * n_chunks;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  uint32_t phase = 0;
+  bool lig_loaded = false;
+  int cur_g = -1;
+  unsigned rowoff = 0u;
+
+  for (;;) {
+    __syncthreads();  // every warp is done with the previous unit: rows and counters may be rewritten
+    if (threadIdx.x == 0) {
+      *s_unit = (int)atomicAdd(unit_counter, 1u);
+      *s_pose_next = 0;
+    }
+    __syncthreads();
+    const int u = *s_unit;
+    if (u >= n_units) break;
+    const int g = rc.group_order[u / n_chunks];
+    const int p0 = (u % n_chunks) * poses_per_unit;
+    const int p1 = min(p0 + poses_per_unit, n_poses);
+    if (g != cur_g) {  // CTA-uniform
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        uint32_t bytes = lig_loaded ? 0u : (uint32_t)rc.n_lig_pad * 16u;
+        int n_rows = 0;
+        for (int r = 0; r < rc.rows_max; ++r) n_rows += rc.group_types[g * RG_MAX_ROWS + r] >= 0;
+        bytes += (uint32_t)n_rows * RG_ROW_BYTES;
+        mbar_expect_tx(bar, bytes);
+        if (!lig_loaded) bulk_g2s(l4, rc.lig4, (uint32_t)rc.n_lig_pad * 16u, bar);
+        for (int r = 0; r < rc.rows_max; ++r) {
+          const int ty = rc.group_types[g * RG_MAX_ROWS + r];
+          if (ty >= 0)
+            bulk_g2s(rows + (size_t)r * RG_ROW_BYTES, rc.potx + (size_t)ty * (RG_ROW_BYTES / 8), RG_ROW_BYTES, bar);
+        }
+      }
+      const int ia = g * 32 + lane;
+      // byte address of (row, ligand type 0, index 4) minus what the magic-number index carries
+      const int slot = rc.rec_slot[ia];  // -1 = pad lane
+      rowoff = slot < 0 ? 0xffffffffu
+                        : (unsigned)(rows - smem_rigid) + (unsigned)slot * RG_ROW_BYTES - ((RG_MAGIC_BITS + (unsigned)RG_SLOT0) << 3);
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+      lig_loaded = true;
+      cur_g = g;
+    }
+    const int pos_base = g * 32;
+
+    for (;;) {
+      int p = 0;
+      if (lane == 0) p = atomicAdd(s_pose_next, 1);
+      p = __shfl_sync(0xffffffffu, p, 0) + p0;
+      if (p >= p1) break;
+      const double *prep = prep_all + (size_t)p * RG_PREP;
+      float fx, fy, fz;
+      unsigned my_off;
+      int my_n;
+      {
+        // receptor atom -> ligand frame: M r - M t (rigid_prep_kernel)
+        double ax = rc.rec_x[pos_base + lane], ay = rc.rec_y[pos_base + lane], az = rc.rec_z[pos_base + lane];
+        if (rc.n_rec_modes > 0) {  // src/dfire.rs:304-320 (lab frame)
+          const double *pose = bb.poses + (size_t)p * rc.pose_len;
+          for (int k = 0; k < rc.n_rec_modes; ++k) {
+            const double e = pose[7 + k];
+            const double *m = rc.rec_modes + (size_t)k * 3 * rc.n_rec_pos + pos_base + lane;
+            ax = __dadd_rn(ax, __dmul_rn(m[0], e));
+            ay = __dadd_rn(ay, __dmul_rn(m[rc.n_rec_pos], e));
+            az = __dadd_rn(az, __dmul_rn(m[2 * rc.n_rec_pos], e));
+          }
+        }
+        fx = (float)(fma(prep[0], ax, fma(prep[1], ay, fma(prep[2], az, -prep[9]))));
+        fy = (float)(fma(prep[3], ax, fma(prep[4], ay, fma(prep[5], az, -prep[10]))));
+        fz = (float)(fma(prep[6], ax, fma(prep[7], ay, fma(prep[8], az, -prep[11]))));
+        const int cxi = __float2int_rd((fx - rc.gx0) * rc.inv_h), cyi = __float2int_rd((fy - rc.gy0) * rc.inv_h),
+                  czi = __float2int_rd((fz - rc.gz0) * rc.inv_h);
+        uint2 ce = make_uint2(0u, 0u);
+        if ((unsigned)cxi < (unsigned)rc.nx && (unsigned)cyi < (unsigned)rc.ny && (unsigned)czi < (unsigned)rc.nz)
+          ce = __ldg(rc.cells + ((size_t)czi * rc.ny + cyi) * rc.nx + cxi);
+        my_off = ce.x;
+        my_n = (int)rowoff == -1 ? 0 : (int)ce.y;  // pad lanes own nothing
+      }
+
+      double acc0 = 0.0, acc1 = 0.0;
+      unsigned ifr_mask = 0u;
+      // Work items = (owner lane, ligand tile) for every entry of the 32 lanes' cell lists, scored 32 at a time.
+      //  (1) an owner with >= 32 entries fills whole rows on its own: lane i takes entry r*32 + i of its list;
+      //  (2) the tails (n mod 32 entries per owner) are pooled: an inclusive scan of the tail lengths numbers
+      //      them, item k belongs to the lane o = #{l : end_l <= k} (5-step binary search over the ends with
+      //      register shuffles) and is entry k - end_{o-1} of o's tail.
+      // The next row's (owner, tile) is produced before the current row is scored, so its list read is in flight.
+      unsigned big = __ballot_sync(0xffffffffu, my_n >= 32);
+      int big_o = 0, big_left = 0;       // current whole-row owner, entries left in whole rows
+      unsigned big_off = 0u;
+      const int tail_n = my_n & 31;
+      const unsigned tail_off = my_off + (unsigned)(my_n & ~31);
+      int end = tail_n;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, end, d);
+        if (lane >= d) end += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, end, 31);
+      int k0 = 0;
+      bool act = false, act_nxt = false;
+      int o = 0, o_nxt = 0;
+      unsigned lt = 0u, lt_nxt = 0u;
+      auto produce = [&]() -> bool {  // warp-uniform control flow; fills (act_nxt, o_nxt, lt_nxt)
+        if (big_left == 0 && big != 0u) {
+          big_o = __ffs(big) - 1;
+          big &= big - 1;
+          big_left = __shfl_sync(0xffffffffu, my_n, big_o) & ~31;
+          big_off = __shfl_sync(0xffffffffu, my_off, big_o);
+        }
+        if (big_left > 0) {
+          o_nxt = big_o;
+          lt_nxt = __ldg(rc.cell_tiles + big_off + lane);
+          act_nxt = true;
+          big_off += 32u;
+          big_left -= 32;
+          return true;
+        }
+        if (k0 < total) {
+          const int k = k0 + lane;
+          int oo = 0;
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(0xffffffffu, end, oo + step - 1);
+            if (v <= k) oo += step;
+          }
+          const int prev = __shfl_sync(0xffffffffu, end, (oo - 1) & 31);
+          const unsigned off = __shfl_sync(0xffffffffu, tail_off, oo);
+          o_nxt = oo;
+          act_nxt = k < total;
+          lt_nxt = 0u;
+          if (act_nxt) lt_nxt = __ldg(rc.cell_tiles + off + (unsigned)(k - (oo > 0 ? prev : 0)));
+          k0 += 32;
+          return true;
+        }
+        return false;
+      };
+      bool have = produce();
+      while (have) {
+        act = act_nxt; o = o_nxt; lt = lt_nxt;
+        have = produce();
+        rigid_row<DETAIL>(rc, bb, l4_addr, lane_sw, act, o, (int)lt, fx, fy, fz, rowoff, p, pos_base, acc0, acc1,
+                          ifr_mask, rc_dev, prep);
+      }
+      __syncwarp();
+      const double tsum = warp_sum(__dadd_rn(acc0, acc1));
+      const unsigned rbits = __reduce_or_sync(0xffffffffu, ifr_mask);
+      if (lane == 0) {
+        bb.partials[(size_t)p * rc.n_groups + g] = tsum;
+        bb.iface_rec[(size_t)p * rc.n_groups + g] = rbits;
+      }
+    }
+  }
+}
+
+}  // namespace ldb200

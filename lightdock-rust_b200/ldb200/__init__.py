@@ -17,7 +17,9 @@ DFIRE_TABLE_LEN = 169 * 169 * 20
 
 EXPORTS = ["ld_create", "ld_destroy", "ld_pose_len", "ld_score_batch", "ld_score_batch_device",
            "ld_score_batch_detail", "ld_transform_batch", "ld_get_stats", "ld_set_rec_splits",
-           "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version"]
+           "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version", "ld_set_path", "ld_path_info"]
+
+PATH_AUTO, PATH_GENERIC, PATH_RIGID = 0, 1, 2
 
 
 class MoleculeDesc(C.Structure):
@@ -44,7 +46,8 @@ class PoseDetail(C.Structure):
 class BatchStats(C.Structure):
     _fields_ = [("n_poses", C.c_int64), ("pair_evals_bruteforce", C.c_int64), ("kernel_launches", C.c_int32),
                 ("rec_splits", C.c_int32), ("device_ms", C.c_double), ("transform_ms", C.c_double),
-                ("pair_ms", C.c_double), ("finalize_ms", C.c_double)]
+                ("pair_ms", C.c_double), ("finalize_ms", C.c_double), ("path", C.c_int32),
+                ("pair_launches", C.c_int32)]
 
 
 class LdError(RuntimeError):
@@ -58,9 +61,10 @@ def load_library():
     """Loads the CUDA library; raises (no fallback) if it has not been built."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise LdError(f"{LIB_PATH} not built: run `make -C lightdock-rust_b200` (or __graft_entry__.build())")
-        lib = C.CDLL(LIB_PATH)
+        path = os.environ.get("LDB200_LIB", LIB_PATH)  # kernel A/B experiments load an alternative build
+        if not os.path.exists(path):
+            raise LdError(f"{path} not built: run `make -C lightdock-rust_b200` (or __graft_entry__.build())")
+        lib = C.CDLL(path)
         lib.ld_last_error.restype = C.c_char_p
         lib.ld_version.restype = C.c_char_p
         lib.ld_create.argtypes = [C.POINTER(ComplexDesc), C.POINTER(C.c_void_p)]
@@ -74,6 +78,9 @@ def load_library():
         lib.ld_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
         lib.ld_set_rec_splits.argtypes = [C.c_void_p, C.c_int32]
         lib.ld_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        lib.ld_set_path.argtypes = [C.c_void_p, C.c_int32]
+        lib.ld_path_info.argtypes = [C.c_void_p]
+        lib.ld_path_info.restype = C.c_char_p
         lib.ld_probe_peaks.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = lib
     return _lib
@@ -201,6 +208,13 @@ class Scorer:
     def set_rec_splits(self, splits):
         _check(self.lib, self.lib.ld_set_rec_splits(self.h, int(splits)))
 
+    def set_path(self, path):
+        """PATH_AUTO / PATH_GENERIC / PATH_RIGID (include/lightdock_b200.h: ld_set_path)."""
+        _check(self.lib, self.lib.ld_set_path(self.h, int(path)))
+
+    def path_info(self):
+        return self.lib.ld_path_info(self.h).decode()
+
     def set_profiling(self, on):
         _check(self.lib, self.lib.ld_set_profiling(self.h, int(bool(on))))
 
@@ -213,7 +227,8 @@ def handle_stats(lib, h):
     _check(lib, lib.ld_get_stats(h, C.byref(s)))
     return dict(n_poses=s.n_poses, pair_evals_bruteforce=s.pair_evals_bruteforce,
                 kernel_launches=s.kernel_launches, rec_splits=s.rec_splits, device_ms=s.device_ms,
-                transform_ms=s.transform_ms, pair_ms=s.pair_ms, finalize_ms=s.finalize_ms)
+                transform_ms=s.transform_ms, pair_ms=s.pair_ms, finalize_ms=s.finalize_ms, path=s.path,
+                pair_launches=s.pair_launches)
 
 
 def probe_peaks(device=0):

@@ -111,6 +111,11 @@ class Case:
     def ld_handle(self):
         return self.lib.ldh_case_handle(self.c)
 
+    def path_info(self):
+        """Which pair kernel the scoring object selected (include/lightdock_b200.h: ld_path_info)."""
+        from . import load_library
+        return load_library().ld_path_info(self.ld_handle()).decode()
+
     def energy_batch(self, poses):
         poses = np.ascontiguousarray(poses, np.float64).reshape(-1, self.pose_len)
         out = np.empty(poses.shape[0])

@@ -9,9 +9,21 @@ import numpy as np
 import pytest
 
 import oracle as O
-from helpers import ENERGY_RTOL, assert_parity, case, random_poses, scorer_from_oracle
+import ldb200
+from helpers import ENERGY_RTOL, assert_parity, case, random_poses
+from helpers import scorer_from_oracle as _scorer_auto
 
 pytestmark = pytest.mark.gpu
+
+
+def scorer_from_oracle(cx):
+    """This module pins the GENERIC pair kernels (per-pose ligand transform + sphere culling; the only path
+    for DNA/pyDock and for ligands with ANM modes).  tests/test_gpu_rigid_path.py covers the rigid-ligand
+    DFIRE kernel that AUTO selects where it applies, with the same cases."""
+    sc = _scorer_auto(cx)
+    sc.set_path(ldb200.PATH_GENERIC)
+    return sc
+
 
 CASES = [("1azp", O.DNA), ("1azp", O.PYDOCK), ("1czy", O.DFIRE), ("1ppe", O.DFIRE), ("2uuy", O.DFIRE),
          ("1k4c", O.DFIRE), ("ab_icode", O.DFIRE)]

@@ -1,0 +1,219 @@
+"""GPU parity of the rigid-ligand DFIRE path (csrc/ld_rigid.cuh) — the kernel the 1k4c-class workloads run.
+
+Same bar as test_gpu_parity.py (BASELINE.json north_star): bin indices, in-cut-off counts, interface flags,
+restraint and membrane counts bit-exact against the oracle; per-pose energies within 1e-6 relative.
+The generic path (per-pose ligand transform + sphere culling) is the second witness: both kernels must
+give the same discrete outputs on samples far larger than the oracle could check in seconds.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+import ldb200
+import oracle as O
+from helpers import ENERGY_RTOL, assert_parity, case, random_poses, scorer_from_oracle
+from ldb200 import workload
+
+pytestmark = pytest.mark.gpu
+
+RIGID_CASES = ["1ppe", "1k4c"]  # DFIRE set-ups without ligand ANM modes
+DISCRETE = ("n_in_cutoff", "n_interface_pairs", "bin_hist", "rec_rst_hit", "lig_rst_hit", "membrane_hit",
+            "iface_rec", "iface_lig")
+
+
+def _rigid(cx):
+    sc = scorer_from_oracle(cx)
+    sc.set_path(ldb200.PATH_RIGID)
+    return sc
+
+
+def test_path_selection():
+    """AUTO = RIGID where it applies; ligand ANM or DNA scoring stay on the generic kernel; forcing is an error."""
+    cx, pos, _ = case("1k4c", O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    assert sc.path_info().startswith("rigid path on"), sc.path_info()
+    sc.energy(pos[:4])
+    assert sc.stats()["path"] == ldb200.PATH_RIGID
+    sc.set_path(ldb200.PATH_GENERIC)
+    sc.energy(pos[:4])
+    assert sc.stats()["path"] == ldb200.PATH_GENERIC
+    for name, method in (("2uuy", O.DFIRE), ("1azp", O.DNA)):
+        cx2, pos2, _ = case(name, method)
+        sc2 = scorer_from_oracle(cx2)
+        assert sc2.path_info().startswith("rigid path off"), sc2.path_info()
+        sc2.energy(pos2[:4])
+        assert sc2.stats()["path"] == ldb200.PATH_GENERIC
+        with pytest.raises(ldb200.LdError):
+            sc2.set_path(ldb200.PATH_RIGID)
+
+
+@pytest.mark.parametrize("name", RIGID_CASES)
+def test_start_positions_parity_rigid(name):
+    cx, pos, _ = case(name, O.DFIRE)
+    sc = _rigid(cx)
+    n = 200 if cx.rec.n * cx.lig.n < 2_000_000 else 24
+    poses = pos[:n]
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    assert sc.stats()["path"] == ldb200.PATH_RIGID
+    e_ref, d_ref = cx.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
+    assert np.array_equal(sc.energy(poses), e_gpu), "plain and detail instantiations must give the same bits"
+
+
+@pytest.mark.parametrize("name", ["1ppe", "1k4c"])
+def test_random_close_poses_parity_rigid(name):
+    """Ligand pushed into the receptor: thousands of contacts below 2.45 A, restraints and membrane beads hit."""
+    cx, pos, _ = case(name, O.DFIRE)
+    sc = _rigid(cx)
+    rng = np.random.default_rng(17)
+    n = 48 if cx.rec.n * cx.lig.n < 2_000_000 else 12
+    poses = random_poses(rng, n, cx.pose_len, centre=cx.rec.coords.mean(axis=0), spread=10.0)
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    e_ref, d_ref = cx.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
+    assert d_ref["n_interface_pairs"].max() > 0
+
+
+def test_rigid_equals_generic_on_bench_workload():
+    """2,000 poses of the bench workload (synthetic 1k4c swarms): every discrete output identical between the
+    two kernels, energies equal to 1e-9 relative (they differ only in summation order)."""
+    cx, _, _ = case("1k4c", O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    poses = workload.synthetic_1k4c_swarms(10, 200).reshape(-1, 7)
+    sc.set_path(ldb200.PATH_RIGID)
+    e_r, d_r = sc.energy_detail(poses)
+    sc.set_path(ldb200.PATH_GENERIC)
+    e_g, d_g = sc.energy_detail(poses)
+    for k in DISCRETE:
+        np.testing.assert_array_equal(d_r[k], d_g[k], err_msg=k)
+    assert np.max(np.abs(e_r - e_g) / np.abs(e_g)) < 1e-9
+    frac = d_r["n_exact_fallback"].sum() / d_r["n_in_cutoff"].sum()
+    assert frac < 0.005, f"exact FP64 fallback should stay rare on the rigid path, got {frac}"
+    assert d_r["n_pairs_tested"].sum() < 0.05 * len(poses) * cx.rec.n * cx.lig.n, "cell lists must prune >95 %"
+
+
+def test_rigid_batch_invariant_and_deterministic():
+    """A pose's energy must not depend on the batch it is scored in (work units, pose ranges, warps that
+    pick it up) nor on the run: (group, pose) sums are warp-local and combined in group order."""
+    cx, pos, _ = case("1k4c", O.DFIRE)
+    sc = _rigid(cx)
+    poses = workload.synthetic_1k4c_swarms(3, 200).reshape(-1, 7)
+    e_all = sc.energy(poses)
+    assert np.array_equal(sc.energy(poses), e_all)
+    perm = np.random.default_rng(5).permutation(len(poses))
+    assert np.array_equal(sc.energy(poses[perm]), e_all[perm])
+    assert np.array_equal(sc.energy(poses[:7]), e_all[:7])
+    one_by_one = np.array([sc.energy(poses[i:i + 1])[0] for i in range(0, 40)])
+    assert np.array_equal(one_by_one, e_all[:40])
+
+
+def test_rigid_edge_cases():
+    cx, pos, _ = case("1ppe", O.DFIRE)
+    sc = _rigid(cx)
+    assert sc.energy(np.zeros((0, 7))).shape == (0,)
+    far = np.array([[1e4, 0, 0, 1, 0, 0, 0]], dtype=np.float64)
+    e, d = sc.energy_detail(far)
+    assert d["n_in_cutoff"][0] == 0 and e[0] == 4.7  # (0*0.0157 - 4.7) * -1, src/dfire.rs:347
+    p = pos[:8].copy()
+    p[:, 3:7] *= 1.7  # rotate() divides by norm2 (src/qt.rs:48-50)
+    p[4:, 3:7] *= 1e-3
+    e_gpu, d_gpu = sc.energy_detail(p)
+    e_ref, d_ref = cx.energy(p, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
+
+
+def test_rigid_decision_thresholds_exact():
+    """Pairs on / next to every bin edge, the 15 A cut-off (dist == 225 -> bin 20) and the 2.45 A interface
+    edge, a few ulps and small offsets either side, under rotations and tiny shifts."""
+    from test_gpu_parity import _threshold_complex
+    rec, lig = _threshold_complex()
+    pot, _ = O.real_or_synthetic_dcparams()
+    cx = O.Complex(rec, lig, O.DFIRE, False, pot)
+    sc = _rigid(cx)
+    s = np.sqrt(0.5)
+    poses = np.array([[0, 0, 0, 1, 0, 0, 0], [0, 0, 0, 0, 1, 0, 0], [0, 0, 0, s, s, 0, 0],
+                      [1e-9, 0, 0, 1, 0, 0, 0], [-1e-9, 0, 0, 1, 0, 0, 0], [3e-6, 0, 0, 1, 0, 0, 0],
+                      [0, 2e-4, 0, 1, 0, 0, 0], [0.25, 0, 0, 1, 0, 0, 0], [-0.25, 0, 0, 1, 0, 0, 0],
+                      [0, 0, 0, s, 0, 0, s], [0, 0, 0, 0.5, 0.5, 0.5, 0.5]], dtype=np.float64)
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    e_ref, d_ref = cx.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, O.DFIRE)
+    assert d_ref["bin_hist"][0][20] >= 1
+    assert d_gpu["n_exact_fallback"][0] > 0, "threshold pairs must take the exact FP64 path"
+
+
+def test_rigid_large_coordinates_stay_exact():
+    """Lab-frame coordinates 5000 A from the origin: the f64 change of frame keeps the f32 margins tight."""
+    cx, pos, _ = case("1ppe", O.DFIRE)
+    shift = np.array([5000.0, -3000.0, 2000.0])
+    rec2 = copy.copy(cx.rec)
+    rec2.coords = cx.rec.coords + shift
+    cx2 = O.Complex(rec2, cx.lig, O.DFIRE, False, cx.potential)
+    sc = _rigid(cx2)
+    p = pos[:24].copy()
+    p[:, :3] += shift
+    e_gpu, d_gpu = sc.energy_detail(p)
+    e_ref, d_ref = cx2.energy(p, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, O.DFIRE)
+
+
+def test_rigid_with_receptor_anm():
+    """use_anm with receptor modes only (anm_lig = 0): the receptor atom is displaced in the lab frame
+    (src/dfire.rs:304-320) before it is moved into the ligand frame."""
+    cx, pos, _ = case("2uuy", O.DFIRE)
+    assert cx.use_anm and cx.rec.n_modes > 0
+    lig = copy.copy(cx.lig)
+    lig.n_modes = 0
+    lig.modes = np.zeros(0)
+    cx2 = O.Complex(cx.rec, lig, O.DFIRE, True, cx.potential)
+    sc = _rigid(cx2)
+    rng = np.random.default_rng(23)
+    poses = np.vstack([pos[:40, :cx2.pose_len],
+                       random_poses(rng, 24, cx2.pose_len, centre=cx.rec.coords.mean(axis=0), spread=10.0)])
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    assert sc.stats()["path"] == ldb200.PATH_RIGID
+    e_ref, d_ref = cx2.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, O.DFIRE)
+    assert np.abs(poses[:, 7:]).max() > 0
+
+
+def test_rigid_full_size_properties():
+    """At the bench's full size (80,000 poses) the oracle cannot follow; check size-independent properties:
+    the batch equals the concatenation of its halves, and a rigid motion applied to BOTH partners
+    (receptor coordinates moved on the host, pose composed with the same motion) leaves every energy
+    unchanged to 1e-9 relative (distances are invariant)."""
+    cx, _, _ = case("1k4c", O.DFIRE)
+    sc = _rigid(cx)
+    poses = np.ascontiguousarray(workload.synthetic_1k4c_swarms(400, 200).reshape(-1, 7))
+    e = sc.energy(poses)
+    assert np.all(np.isfinite(e))
+    h = len(poses) // 2
+    assert np.array_equal(np.concatenate([sc.energy(poses[:h]), sc.energy(poses[h:])]), e)
+    # global motion g: x -> Rg x + tg.  receptor' = g(receptor); pose' = g o pose.
+    qg = np.array([0.3, -0.5, 0.1, 0.8]); qg /= np.linalg.norm(qg)
+    tg = np.array([7.0, -3.0, 11.0])
+
+    def qmul(a, b):
+        return np.stack([a[..., 0] * b[..., 0] - a[..., 1] * b[..., 1] - a[..., 2] * b[..., 2] - a[..., 3] * b[..., 3],
+                         a[..., 0] * b[..., 1] + a[..., 1] * b[..., 0] + a[..., 2] * b[..., 3] - a[..., 3] * b[..., 2],
+                         a[..., 0] * b[..., 2] - a[..., 1] * b[..., 3] + a[..., 2] * b[..., 0] + a[..., 3] * b[..., 1],
+                         a[..., 0] * b[..., 3] + a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1] + a[..., 3] * b[..., 0]], -1)
+
+    def rot(q, v):
+        qv = np.concatenate([np.zeros(v.shape[:-1] + (1,)), v], -1)
+        qc = q * np.array([1, -1, -1, -1])
+        return qmul(qmul(np.broadcast_to(q, qv.shape), qv), np.broadcast_to(qc, qv.shape))[..., 1:]
+
+    rec2 = copy.copy(cx.rec)
+    rec2.coords = rot(qg, cx.rec.coords) + tg
+    cx2 = O.Complex(rec2, cx.lig, O.DFIRE, False, cx.potential)
+    sc2 = _rigid(cx2)
+    sub = poses[::40]
+    p2 = sub.copy()
+    p2[:, :3] = rot(qg, sub[:, :3]) + tg
+    p2[:, 3:7] = qmul(np.broadcast_to(qg, sub[:, 3:7].shape), sub[:, 3:7])
+    e2 = sc2.energy(p2)
+    rel = np.abs(e2 - e[::40]) / np.abs(e[::40])
+    # a pair sitting within ~1e-12 A of a bin edge may flip under the re-computed coordinates; none expected
+    assert np.quantile(rel, 0.99) < 1e-9 and rel.max() < ENERGY_RTOL, (np.quantile(rel, 0.99), rel.max())
