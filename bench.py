@@ -308,9 +308,28 @@ def run_b200(args, rank, world, local_rank):
         # algorithmic HBM bytes per pose: ligand block written once + read once, pose row in, energy out
         lig_block = (3272 * 40 + 409 * 16 + 16)
         hbm_bytes = n_local * (2 * lig_block + 56 + 8)
+    # counters of the dominant kernel from the committed ncu capture of this same command (profiles/): DRAM
+    # traffic and executed warp instructions per pose, used for `traffic` and the instruction-issue roofline
+    traffic = issue = None
+    try:
+        cnt = json.load(open(os.path.join(ROOT, "profiles", "r1_dfire_rigid_counts.json")))
+    except OSError:
+        cnt = None
+    if cnt and path == "rigid":
+        per_pose = (cnt["dram_bytes_read_per_launch"] + cnt["dram_bytes_write_per_launch"]) / cnt["poses_per_launch"]
+        traffic = per_pose * n_local / max(1, pair_launches // args.steps)
+        sm_hz = (clk["sm_mhz"] if clk and clk.get("sm_mhz") else peaks.get("sm_max_mhz", 1965.0)) * 1e6
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        inst = cnt["warp_instructions_per_launch"] / cnt["poses_per_launch"] * n_local
+        issue = {"bound": "instruction issue (4 warp schedulers x SMs x SM clock)",
+                 "achieved_gwarp_inst_per_s": inst / (pair_ms_step * 1e-3) / 1e9,
+                 "peak_gwarp_inst_per_s": sms * 4 * sm_hz / 1e9,
+                 "frac": inst / (pair_ms_step * 1e-3) / (sms * 4 * sm_hz),
+                 "warp_inst_per_pose": cnt["warp_instructions_per_launch"] / cnt["poses_per_launch"],
+                 "source": "instruction count per pose from " + cnt["source"] + "; time measured live"}
     roofline = {
         "bound": "fp64", "kernel": pair_kernel, "path": path, "path_info": case.path_info(), "achieved": achieved_tf, "peak": fp64_tf, "unit": "TFLOP/s",
-        "frac": achieved_tf / fp64_tf, "traffic": None,
+        "frac": achieved_tf / fp64_tf, "traffic": traffic, "issue_roofline": issue,
         "peak_source": "ld_probe_peaks: non-fused DADD+DMUL rate measured on this GPU (MEASURED_PEAKS.json has no "
                        "FP64 figure; SURVEY.md 8d)",
         "algorithmic_flops_per_pair": 8, "pair_kernel_ms_per_step": pair_ms_step,

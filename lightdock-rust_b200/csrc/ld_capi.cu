@@ -9,6 +9,7 @@
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ld_kernels.cuh"
@@ -329,8 +330,8 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
 
   // cell grid over the ligand's bounding box grown by the cut-off; a cell lists every tile with an atom
   // within 15 A + slack of the cell's box (slack: f32 cell assignment + the classification margin delta)
-  double cell = 3.0;
-  if (const char *e = getenv("LDB200_CELL")) cell = std::max(1.0, std::min(8.0, atof(e)));
+  double cell = 1.0;
+  if (const char *e = getenv("LDB200_CELL")) cell = std::max(0.5, std::min(8.0, atof(e)));
   const double reach = 15.0 + 0.01;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   const std::vector<double> *LC[3] = {&L.x, &L.y, &L.z};
@@ -351,46 +352,61 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   }
   const size_t ncell = (size_t)nc[0] * nc[1] * nc[2];
   if (ncell > ((size_t)1 << 26)) { h->rigid_info = "rigid path off: cell grid too large"; return LD_OK; }
-  std::vector<std::vector<unsigned short>> lists(ncell);
+  // Two passes (count, fill) over z-slabs of the grid, one host thread per slab: a slab owns its cells, so
+  // the passes need no synchronisation, and tiles are visited in ascending order, so every list is sorted.
+  std::vector<unsigned> count(ncell, 0u);
   std::vector<int> stamp(ncell, -1);
+  std::vector<uint2> cells(ncell);
+  std::vector<unsigned short> flat;
   const double reach2 = reach * reach;
-  for (int t = 0; t < cx.n_lig_tiles; ++t)
-    for (int j = t * LIG_TILE; j < std::min((t + 1) * LIG_TILE, cx.n_lig); ++j) {
-      // the f32 value the kernel uses and the f64 one differ by < 1e-5: inside the slack
-      const double a[3] = {L.x[j], L.y[j], L.z[j]};
-      int c0[3], c1[3];
-      for (int d = 0; d < 3; ++d) {
-        c0[d] = std::max(0, (int)std::floor((a[d] - reach - (double)g0[d]) / hh));
-        c1[d] = std::min(nc[d] - 1, (int)std::floor((a[d] + reach - (double)g0[d]) / hh));
-      }
-      for (int cz = c0[2]; cz <= c1[2]; ++cz) {
-        const double bz0 = (double)g0[2] + cz * hh, ez = std::max(0.0, std::max(bz0 - a[2], a[2] - (bz0 + hh)));
-        for (int cy = c0[1]; cy <= c1[1]; ++cy) {
-          const double by0 = (double)g0[1] + cy * hh, ey = std::max(0.0, std::max(by0 - a[1], a[1] - (by0 + hh)));
-          if (ez * ez + ey * ey > reach2) continue;
-          for (int cxx = c0[0]; cxx <= c1[0]; ++cxx) {
-            const double bx0 = (double)g0[0] + cxx * hh, ex = std::max(0.0, std::max(bx0 - a[0], a[0] - (bx0 + hh)));
-            if (ex * ex + ey * ey + ez * ez > reach2) continue;
-            const size_t c = ((size_t)cz * nc[1] + cy) * nc[0] + cxx;
-            if (stamp[c] != t) {
+  auto sweep = [&](int z_lo, int z_hi, bool fill) {
+    for (int t = 0; t < cx.n_lig_tiles; ++t)
+      for (int j = t * LIG_TILE; j < std::min((t + 1) * LIG_TILE, cx.n_lig); ++j) {
+        // the f32 value the kernel uses and the f64 one differ by < 1e-5: inside the slack
+        const double a[3] = {L.x[j], L.y[j], L.z[j]};
+        int c0[3], c1[3];
+        for (int d = 0; d < 3; ++d) {
+          c0[d] = std::max(0, (int)std::floor((a[d] - reach - (double)g0[d]) / hh));
+          c1[d] = std::min(nc[d] - 1, (int)std::floor((a[d] + reach - (double)g0[d]) / hh));
+        }
+        for (int cz = std::max(c0[2], z_lo); cz <= std::min(c1[2], z_hi - 1); ++cz) {
+          const double bz0 = (double)g0[2] + cz * hh, ez = std::max(0.0, std::max(bz0 - a[2], a[2] - (bz0 + hh)));
+          for (int cy = c0[1]; cy <= c1[1]; ++cy) {
+            const double by0 = (double)g0[1] + cy * hh, ey = std::max(0.0, std::max(by0 - a[1], a[1] - (by0 + hh)));
+            const double eyz = ez * ez + ey * ey;
+            if (eyz > reach2) continue;
+            size_t c = ((size_t)cz * nc[1] + cy) * nc[0] + c0[0];
+            for (int cxx = c0[0]; cxx <= c1[0]; ++cxx, ++c) {
+              const double bx0 = (double)g0[0] + cxx * hh, ex = std::max(0.0, std::max(bx0 - a[0], a[0] - (bx0 + hh)));
+              if (ex * ex + eyz > reach2 || stamp[c] == t) continue;
               stamp[c] = t;
-              lists[c].push_back((unsigned short)t);
+              if (fill) flat[cells[c].x + count[c]] = (unsigned short)t;
+              ++count[c];
             }
           }
         }
       }
-    }
-  std::vector<uint2> cells(ncell);
+  };
+  const int n_thr = std::max(1, std::min(std::min(16, nc[2]), (int)std::thread::hardware_concurrency()));
+  auto run_pass = [&](bool fill) {
+    std::vector<std::thread> pool;
+    for (int w = 0; w < n_thr; ++w)
+      pool.emplace_back(sweep, (int)((long)nc[2] * w / n_thr), (int)((long)nc[2] * (w + 1) / n_thr), fill);
+    for (auto &th : pool) th.join();
+  };
+  run_pass(false);
   size_t total = 0, longest = 0, nonempty = 0;
   for (size_t c = 0; c < ncell; ++c) {
-    cells[c] = make_uint2((unsigned)total, (unsigned)lists[c].size());
-    total += (lists[c].size() + 1) & ~(size_t)1;  // lists start on even offsets (the kernel reads entry pairs)
-    longest = std::max(longest, lists[c].size());
-    nonempty += !lists[c].empty();
+    cells[c] = make_uint2((unsigned)total, count[c]);
+    total += count[c];
+    longest = std::max<size_t>(longest, count[c]);
+    nonempty += count[c] != 0;
   }
   if (total >= ((size_t)1 << 31)) { h->rigid_info = "rigid path off: cell lists too large"; return LD_OK; }
-  std::vector<unsigned short> flat(std::max<size_t>(total, 2), 0);
-  for (size_t c = 0; c < ncell; ++c) std::copy(lists[c].begin(), lists[c].end(), flat.begin() + cells[c].x);
+  flat.assign(std::max<size_t>(total, 1), 0);
+  std::fill(count.begin(), count.end(), 0u);
+  std::fill(stamp.begin(), stamp.end(), -1);
+  run_pass(true);
 
   int rcode;
 #define UPR(vec, field) \
