@@ -2,7 +2,13 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
+#include <exception>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <thread>
 
@@ -165,33 +171,36 @@ void Swarm::update_luciferin() {
 
 void Swarm::movement_phase(StdRng &rng) {
   const size_t n = glowworms.size();
-  std::vector<std::vector<double>> positions, anm_recs, anm_ligs;
-  std::vector<Quaternion> rotations;
-  for (const Glowworm &g : glowworms) {
-    positions.push_back(g.translation);
-    rotations.push_back(g.rotation);
-    anm_recs.push_back(g.rec_nmodes);
-    anm_ligs.push_back(g.lig_nmodes);
-  }
-  std::vector<std::vector<uint32_t>> neighbors(n);
+  // snapshot of every glowworm's pose before anybody moves (src/swarm.rs:74-86): a glowworm moves towards where
+  // its neighbour WAS at the start of the step.  Flat scratch buffers, reused from step to step.
+  const size_t nr = n ? glowworms[0].rec_nmodes.size() : 0, nl = n ? glowworms[0].lig_nmodes.size() : 0;
+  snap_positions.resize(n);
+  snap_rotations.resize(n);
+  snap_anm_recs.resize(n);
+  snap_anm_ligs.resize(n);
+  snap_luciferins.resize(n);
   for (size_t i = 0; i < n; ++i) {
-    const Glowworm &g1 = glowworms[i];
+    const Glowworm &g = glowworms[i];
+    snap_positions[i] = g.translation;  // element-wise assignment into already-sized vectors: no allocation
+    snap_rotations[i] = g.rotation;
+    if (nr || !g.rec_nmodes.empty()) snap_anm_recs[i] = g.rec_nmodes;
+    if (nl || !g.lig_nmodes.empty()) snap_anm_ligs[i] = g.lig_nmodes;
+    snap_luciferins[i] = g.luciferin;
+  }
+  for (size_t i = 0; i < n; ++i) {  // src/swarm.rs:88-103
+    Glowworm &g1 = glowworms[i];
+    g1.neighbors.clear();
     for (size_t j = 0; j < n; ++j) {
       if (i == j) continue;
       const Glowworm &g2 = glowworms[j];
-      if (g1.luciferin < g2.luciferin && distance(g1, g2) < g1.vision_range) neighbors[i].push_back(g2.id);
+      if (g1.luciferin < g2.luciferin && distance(g1, g2) < g1.vision_range) g1.neighbors.push_back(g2.id);
     }
   }
-  std::vector<double> luciferins;
-  for (const Glowworm &g : glowworms) luciferins.push_back(g.luciferin);
-  for (size_t i = 0; i < n; ++i) {
-    glowworms[i].neighbors = neighbors[i];
-    glowworms[i].compute_probability_moving_toward_neighbor(luciferins);
-  }
+  for (size_t i = 0; i < n; ++i) glowworms[i].compute_probability_moving_toward_neighbor(snap_luciferins);
   for (size_t i = 0; i < n; ++i) {
     Glowworm &g = glowworms[i];
     const uint32_t nid = g.select_random_neighbor(rng.gen_f64());  // always one draw per glowworm (:118)
-    g.move_towards(nid, positions[nid], rotations[nid], anm_recs[nid], anm_ligs[nid]);
+    g.move_towards(nid, snap_positions[nid], snap_rotations[nid], snap_anm_recs[nid], snap_anm_ligs[nid]);
     g.update_vision_range();
   }
 }
@@ -238,43 +247,120 @@ uint64_t MultiGSO::energy_calls() const {
   return n;
 }
 
-void MultiGSO::run(uint32_t steps, int host_threads) {
-  const size_t ns = runs.size();
-  host_threads = std::max(1, std::min<int>(host_threads, (int)std::max<size_t>(ns, 1)));
-  std::vector<double> rows, scores;
-  std::vector<std::vector<uint32_t>> who(ns);
-  std::vector<size_t> first(ns + 1, 0);
-  auto parallel = [&](auto &&fn) {  // fn(swarm index), swarms striped over host threads
-    if (host_threads == 1) {
-      for (size_t s = 0; s < ns; ++s) fn(s);
+namespace {
+// A fixed set of workers that run fn(i) for i in [0, n) (striped) and wait for each other; created once per
+// lane so a GSO step costs two wake-ups instead of two rounds of thread creation.
+class Workers {
+ public:
+  explicit Workers(int n) : n_(std::max(1, n)) {
+    for (int t = 1; t < n_; ++t) pool_.emplace_back([this, t] { loop(t); });
+  }
+  ~Workers() {
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      stop_ = true;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    for (auto &th : pool_) th.join();
+  }
+  template <typename F>
+  void for_each(size_t n, F &&fn) {
+    if (n_ == 1 || n < 2) {
+      for (size_t i = 0; i < n; ++i) fn(i);
       return;
     }
-    std::vector<std::thread> pool;
-    for (int t = 0; t < host_threads; ++t)
-      pool.emplace_back([&, t] {
-        for (size_t s = t; s < ns; s += host_threads) fn(s);
-      });
-    for (auto &th : pool) th.join();
-  };
-  for (uint32_t step = 1; step <= steps; ++step) {
-    rows.clear();
-    for (size_t s = 0; s < ns; ++s) {
-      who[s].clear();
-      first[s] = rows.size();
-      runs[s].swarm.gather_poses(rows, who[s]);
+    std::function<void(size_t)> f = std::ref(fn);
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      job_ = &f;
+      count_ = n;
+      pending_ = n_ - 1;
+      error_ = nullptr;
+      ++epoch_;
     }
-    first[ns] = rows.size();
-    const size_t pl = scoring->pose_len();
+    cv_.notify_all();
+    work(0);
+    std::unique_lock<std::mutex> lk(m_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+    job_ = nullptr;
+    if (error_) std::rethrow_exception(error_);
+  }
+
+ private:
+  void work(int t) {
+    try {
+      for (size_t i = (size_t)t; i < count_; i += (size_t)n_) (*job_)(i);
+    } catch (...) {
+      std::lock_guard<std::mutex> lk(m_);
+      if (!error_) error_ = std::current_exception();
+    }
+  }
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return epoch_ != seen; });
+        seen = epoch_;
+        if (stop_) return;
+      }
+      work(t);
+      {
+        std::lock_guard<std::mutex> lk(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  int n_;
+  std::vector<std::thread> pool_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(size_t)> *job_ = nullptr;
+  size_t count_ = 0;
+  int pending_ = 0;
+  uint64_t epoch_ = 0;
+  bool stop_ = false;
+  std::exception_ptr error_;
+};
+}  // namespace
+
+void MultiGSO::run_lane(const std::vector<size_t> &mine, const Score *sc, uint32_t steps, int host_threads) {
+  const size_t ns = mine.size();
+  if (ns == 0) return;
+  Workers workers(std::min<int>(std::max(1, host_threads), (int)ns));
+  const size_t pl = sc->pose_len();
+  std::vector<double> rows, scores;
+  std::vector<std::vector<uint32_t>> who(ns);
+  std::vector<std::vector<double>> swarm_rows(ns);
+  std::vector<size_t> first(ns + 1, 0);
+  for (uint32_t step = 1; step <= steps; ++step) {
+    workers.for_each(ns, [&](size_t k) {  // which glowworms must be rescored, and their pose rows
+      who[k].clear();
+      swarm_rows[k].clear();
+      runs[mine[k]].swarm.gather_poses(swarm_rows[k], who[k]);
+    });
+    for (size_t k = 0; k < ns; ++k) first[k + 1] = first[k] + swarm_rows[k].size();
+    rows.resize(first[ns]);
+    workers.for_each(ns, [&](size_t k) {
+      std::copy(swarm_rows[k].begin(), swarm_rows[k].end(), rows.begin() + first[k]);
+    });
     const size_t n = rows.size() / pl;
     scores.resize(n);
-    if (n) scoring->energy_batch(n, rows.data(), scores.data());  // ONE batched launch for all swarms
-    parallel([&](size_t s) {
-      runs[s].swarm.scatter_scores(who[s], scores.data() + first[s] / pl);
-      runs[s].swarm.movement_phase(runs[s].rng);
-      if ((step % 10 == 0 || step == 1) && !runs[s].output_directory.empty())
-        runs[s].swarm.save(step, runs[s].output_directory);
+    if (n) sc->energy_batch(n, rows.data(), scores.data());  // ONE batched launch for all swarms of the lane
+    workers.for_each(ns, [&](size_t k) {
+      GSO &r = runs[mine[k]];
+      r.swarm.scatter_scores(who[k], scores.data() + first[k] / pl);
+      r.swarm.movement_phase(r.rng);
+      if ((step % 10 == 0 || step == 1) && !r.output_directory.empty()) r.swarm.save(step, r.output_directory);
     });
   }
+}
+
+void MultiGSO::run(uint32_t steps, int host_threads) {
+  std::vector<size_t> all(runs.size());
+  for (size_t s = 0; s < all.size(); ++s) all[s] = s;
+  run_lane(all, scoring, steps, std::max(1, host_threads));
 }
 
 }  // namespace lightdock

@@ -63,6 +63,11 @@ struct Swarm {  // src/swarm.rs
   void scatter_scores(const std::vector<uint32_t> &who, const double *scores);
   void movement_phase(StdRng &rng);                           // :72-126
   void save(uint32_t step, const std::string &output_directory) const;  // :128-167
+
+ private:  // scratch of movement_phase
+  std::vector<std::vector<double>> snap_positions, snap_anm_recs, snap_anm_ligs;
+  std::vector<Quaternion> snap_rotations;
+  std::vector<double> snap_luciferins;
 };
 
 struct GSO {  // src/lib.rs:20-59
@@ -85,8 +90,15 @@ struct MultiGSO {
   explicit MultiGSO(const Score *s) : scoring(s) {}
   void add(const std::vector<std::vector<double>> &positions, uint64_t seed, bool use_anm, size_t rec_num_anm,
            size_t lig_num_anm, std::string output_directory);
+  // host_threads: persistent workers for the per-swarm host phases (gather, luciferin update, movement, save).
+  // Swarms never interact and the kernels are batch-invariant, so trajectories do not depend on it.
+  // (Measured on B200: with these phases parallel the step is >90 % device time; splitting the swarms into
+  // concurrently driven sets with cloned scoring objects did not pay and was dropped.)
   void run(uint32_t steps, int host_threads = 1);
   uint64_t energy_calls() const;
+
+ private:
+  void run_lane(const std::vector<size_t> &mine, const Score *sc, uint32_t steps, int host_threads);
 };
 
 }  // namespace lightdock

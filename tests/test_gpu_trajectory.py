@@ -85,3 +85,25 @@ def test_multi_gso_equals_single_swarm_runs():
     assert np.array_equal(multi[0], single)
     assert not np.array_equal(multi[1], single) and not np.array_equal(multi[2], single)
     assert calls > calls1
+
+
+def test_multi_gso_threads_do_not_change_trajectories(monkeypatch, tmp_path):
+    """The per-swarm host phases of MultiGSO run on a pool of workers; swarms never interact and the kernels
+    are batch-invariant, so the final state must be bit-identical whatever the number of workers."""
+    from ldb200 import host, workload
+    dc_dir, _ = workload.ensure_dcparams_dir(str(tmp_path))
+    monkeypatch.setenv("LIGHTDOCK_DATA", dc_dir)
+    c = host.Case(os.path.join(workload.GOLDEN_1K4C, "setup.json"), "dfire")
+    pos = workload.synthetic_1k4c_swarms(12, 200)
+    seeds = np.arange(12, dtype=np.uint64) + 324324
+    ref = None
+    for threads in (1, 4, 12, 16):
+        state, calls = c.multi_gso(pos, seeds, 6, host_threads=threads)
+        if ref is None:
+            ref = (state, calls)
+        assert calls == ref[1]
+        assert np.array_equal(state, ref[0]), f"threads={threads} changed a trajectory"
+    assert ref[1] > 12 * 200  # something moved and was rescored after step 1
+    # and a swarm driven alone gives the same bits as inside the 12-swarm batch
+    one, _ = c.multi_gso(pos[3:4], seeds[3:4], 6, host_threads=1)
+    assert np.array_equal(one[0], ref[0][3])
