@@ -71,6 +71,28 @@ def test_host_gso_matches_oracle_gso_dfire_anm():
     assert (np.abs(state[:, 1] - last[:, 1]) <= ENERGY_RTOL * np.abs(last[:, 1])).all()  # scoring
 
 
+@pytest.mark.parametrize("name,steps", [("1ppe", 40), ("1k4c", 6)])
+def test_host_gso_matches_oracle_gso_rigid_path(name, steps, tmp_path, monkeypatch):
+    """BASELINE configs 1ppe (shipped set-up: no ANM, active restraint) and 1k4c (membrane beads) run on the
+    rigid-ligand DFIRE kernel: product host + GPU against the oracle's GSO, same seed; every discrete field
+    of the final state exact, poses to 1e-9, scores to the north-star tolerance."""
+    from ldb200 import host
+    cx, pos, seed = case(name, O.DFIRE)
+    g = os.path.join(GOLDEN, name)
+    O.write_dcparams(str(tmp_path / "DCparams"), cx.potential)
+    monkeypatch.setenv("LIGHTDOCK_DATA", str(tmp_path))
+    c = host.Case(os.path.join(g, "setup.json"), "dfire", anm_dir=g)
+    assert c.path_info().startswith("rigid path on"), c.path_info()
+    state, calls = c.gso(os.path.join(g, "initial_positions_0.dat"), steps)
+    final, tr, ocalls = cx.gso_run(pos, seed, steps, trace=True)
+    last = tr[-1]
+    assert calls == ocalls
+    np.testing.assert_array_equal(state[:, 2], last[:, 2])            # neighbour counts
+    np.testing.assert_array_equal(state[:, 3], last[:, 3])            # vision range
+    assert np.abs(state[:, 4:] - last[:, 5:]).max() <= 1e-9            # poses
+    assert (np.abs(state[:, 1] - last[:, 1]) <= ENERGY_RTOL * np.abs(last[:, 1])).all()  # scoring
+
+
 def test_multi_gso_equals_single_swarm_runs():
     """Lock-step multi-swarm driver: every swarm's trajectory equals its stand-alone run."""
     from ldb200 import host
