@@ -582,8 +582,21 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
 // ---------------------------------------------------------------------------------------------
 // Kernel 2b: DNA / pyDock pair loop, src/dna.rs:471-512 (= src/pydock.rs:486-527).
 // powi(6)/powi(3) follow LLVM's repeated-squaring expansion (x^2, x^4, x^2*x^4 ; x*x^2).
+// Reciprocal for the two energy quotients (Coulomb q1*q2/d2, van der Waals (r/d)^6): MUFU.RCP64H seed + two
+// Newton steps in FMA (relative error < 4e-16).  The quotients feed only continuous quantities (a sum, a clamp and a
+// min whose two branches agree at the switch point), never a cut-off decision, so a last-ulp difference from the
+// reference's IEEE divide stays 1e-10 below the 1e-6 tolerance; the cut-off tests themselves use the exact,
+// never-fused d2.  Saves ~8 FP64-pipe instructions per quotient against __ddiv_rn.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  x = fma(fma(-d, x, 1.0), x, x);
+  x = fma(fma(-d, x, 1.0), x, x);
+  return x;
+}
+
 template <bool DETAIL>
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
+__global__ void __launch_bounds__(PAIR_THREADS, 2)
     dna_pair_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int pose = blockIdx.x / bb.rec_splits, split = blockIdx.x % bb.rec_splits;
@@ -646,7 +659,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
           const double dz = __dsub_rn(rz, s.lz[j]);
           const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
           if (d2 <= ELEC_DIST_CUTOFF2) {  // src/dna.rs:481-491
-            double e = __ddiv_rn(__dmul_rn(rq, s_q[j]), d2);
+            double e = __dmul_rn(__dmul_rn(rq, s_q[j]), fast_rcp(d2));
             e = e > ELEC_MAX_CUTOFF ? ELEC_MAX_CUTOFF : e;
             e = e < ELEC_MIN_CUTOFF ? ELEC_MIN_CUTOFF : e;
             acc_e = __dadd_rn(acc_e, e);
@@ -657,7 +670,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 1)
               const double vr2 = __dmul_rn(vr, vr), vr4 = __dmul_rn(vr2, vr2);
               const double vr6 = __dmul_rn(vr2, vr4);
               const double d6 = __dmul_rn(d2, __dmul_rn(d2, d2));
-              const double p6 = __ddiv_rn(vr6, d6);
+              const double p6 = __dmul_rn(vr6, fast_rcp(d6));
               double k = __dmul_rn(ve, __dsub_rn(__dmul_rn(p6, p6), __dmul_rn(2.0, p6)));
               k = k > 1.0 ? 1.0 : k;
               acc_v = __dadd_rn(acc_v, k);
