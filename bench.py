@@ -352,7 +352,7 @@ def run_b200(args, rank, world, local_rank):
     # ---- CPU baseline (oracle port on this box's host cores, bounded sample) -------------------
     cores = host_cores()
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported at N=1 only (rank 0's host cores are shared at N>1)
         cx = oracle_complex()
         rate, n_cpu, dt = cpu_rate(cx, np.ascontiguousarray(all_poses.reshape(-1, 7)[:: max(1, n_total // 8192)]),
                                    cores, args.cpu_seconds)
