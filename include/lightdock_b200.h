@@ -161,6 +161,10 @@ int ld_set_profiling(ld_handle *h, int32_t on);
 int ld_probe_peaks(int32_t device, double *fp64_nonfma_tflops, double *fp32_nonfma_tflops,
                    double *l2_gather_gloads);
 
+/* Number of CUDA devices visible to the process (0 if none / no driver): the multi-swarm driver shards swarms
+ * over them (swarm s -> device s mod count). */
+int ld_device_count(void);
+
 const char *ld_last_error(void);
 const char *ld_version(void);
 

@@ -32,6 +32,10 @@ static int fail(int code, const std::string &msg) {
   } while (0)
 
 extern "C" const char *ld_last_error(void) { return g_err.c_str(); }
+extern "C" int ld_device_count(void) {
+  int n = 0;
+  return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
 extern "C" const char *ld_version(void) { return "lightdock_b200 0.1 (sm_100a)"; }
 
 // ---------------------------------------------------------------------------------------------

@@ -17,7 +17,7 @@ DFIRE_TABLE_LEN = 169 * 169 * 20
 
 EXPORTS = ["ld_create", "ld_destroy", "ld_pose_len", "ld_score_batch", "ld_score_batch_device",
            "ld_score_batch_detail", "ld_transform_batch", "ld_get_stats", "ld_set_rec_splits",
-           "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version", "ld_set_path", "ld_path_info"]
+           "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version", "ld_set_path", "ld_path_info", "ld_device_count"]
 
 PATH_AUTO, PATH_GENERIC, PATH_RIGID = 0, 1, 2
 

@@ -129,3 +129,51 @@ def test_multi_gso_threads_do_not_change_trajectories(monkeypatch, tmp_path):
     # and a swarm driven alone gives the same bits as inside the 12-swarm batch
     one, _ = c.multi_gso(pos[3:4], seeds[3:4], 6, host_threads=1)
     assert np.array_equal(one[0], ref[0][3])
+
+
+def test_multi_cli_equals_single_cli(tmp_path):
+    """lightdock-rust-multi (all swarms of a run in one process; replaces the ant_thony fan-out of
+    example/1czy/execution.sh) writes byte-identical swarm_N/gso_*.out files to N runs of the single-swarm CLI,
+    both from an ant_thony task list and from explicit arguments."""
+    from ldb200 import host
+    g = os.path.join(GOLDEN, "1azp")
+    multi_cli = os.path.join(os.path.dirname(host.CLI_PATH), "lightdock-rust-multi")
+    base = open(os.path.join(g, "initial_positions_0.dat")).read().splitlines()
+    rng = np.random.default_rng(3)
+    for mode in ("single", "tasklist", "args"):
+        d = tmp_path / mode
+        os.makedirs(d / "init")
+        for f in ("rec_nm.npy", "lig_nm.npy"):
+            shutil.copy(os.path.join(g, f), d / f)
+    files = []
+    for k in (0, 3, 11):  # swarm ids need not be contiguous
+        rows = [[float(x) for x in l.split(" ")] for l in base]
+        if k:
+            for r in rows:
+                r[0] += rng.normal(0, 0.5); r[1] += rng.normal(0, 0.5); r[2] += rng.normal(0, 0.5)
+        text = "\n".join(" ".join(repr(v) for v in r) for r in rows) + "\n"
+        for mode in ("single", "tasklist", "args"):
+            (tmp_path / mode / "init" / f"initial_positions_{k}.dat").write_text(text)
+        files.append(f"init/initial_positions_{k}.dat")
+    setup = os.path.join(g, "setup.json")
+    for f in files:
+        r = subprocess.run([host.CLI_PATH, setup, f, "12", "dna"], cwd=tmp_path / "single", capture_output=True,
+                           text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+    (tmp_path / "tasklist" / "task.list").write_text("".join(f"./lightdock-rust {setup} {f} 12 dna;\n" for f in files))
+    r = subprocess.run([multi_cli, "task.list"], cwd=tmp_path / "tasklist", capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert "3 swarms, 12 steps" in r.stdout
+    r = subprocess.run([multi_cli, setup, "12", "dna"] + files, cwd=tmp_path / "args", capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr
+    for k in (0, 3, 11):
+        for step in (1, 10):
+            want = (tmp_path / "single" / f"swarm_{k}" / f"gso_{step}.out").read_bytes()
+            for mode in ("tasklist", "args"):
+                got = (tmp_path / mode / f"swarm_{k}" / f"gso_{step}.out").read_bytes()
+                assert got == want, f"{mode}: swarm {k} step {step} differs from the single-swarm CLI"
+    # a malformed task list is refused, not half-run
+    (tmp_path / "tasklist" / "bad.list").write_text(f"./lightdock-rust {setup} {files[0]} 12 dna;\n./lightdock-rust {setup} {files[1]} 13 dna;\n")
+    r = subprocess.run([multi_cli, "bad.list"], cwd=tmp_path / "tasklist", capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "must share" in r.stderr
