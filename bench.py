@@ -123,7 +123,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except OSError:
@@ -140,7 +140,7 @@ class ClockSampler:
         sm, mx, reasons = [], [], set()
         for ts, line in self.rows:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 7 or not (t0 <= ts <= t1 + 0.2):
+            if len(f) < 7 or not (t0 <= ts <= t1):
                 continue
             try:
                 sm.append(float(f[0])); mx.append(float(f[1]))
@@ -222,7 +222,6 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     t_wall1 = time.perf_counter()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    clk = clocks.summary(t_wall0, t_wall1) if clocks else None
     launches_per_step = ldb200.handle_stats(lib, h)["kernel_launches"]
     value = n_total * args.steps / (ms_total * 1e-3)
     e_dev = d_energy.cpu().numpy()
@@ -252,7 +251,12 @@ def run_b200(args, rank, world, local_rank):
         ldb200._check(lib, lib.ld_score_batch(h, n_local, poses.ctypes.data, e_host.ctypes.data))
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    t_wall2 = time.perf_counter()
     barrier()
+    # clocks sampled over every timed leg of the step (device-resident, per-kernel, host-buffer): all under load
+    clk = clocks.summary(t_wall0, t_wall2) if clocks else None
+    if clk is not None:
+        clk["window"] = "value + per-kernel + e2e legs (%.0f ms), nvidia-smi every 20 ms" % ((t_wall2 - t_wall0) * 1e3)
     e2e_value = n_total * args.steps / e2e_s
     if not np.array_equal(e_host, e_dev):
         raise SystemExit("bench.py: host-buffer and device-buffer paths disagree")
