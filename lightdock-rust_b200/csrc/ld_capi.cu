@@ -311,17 +311,6 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
     for (int k = R.rst_offsets[r]; k < R.rst_offsets[r + 1]; ++k) rst_idx.push_back(inv[R.rst_atoms[k]]);
   for (int k = 0; k < R.n_membrane; ++k) mem_idx.push_back(inv[R.membrane[k]]);
 
-  // table rows re-indexed by the truncated bin-space value (indices 4..28 -> DIST_TO_BINS, src/dfire.rs:49-53,337)
-  const size_t row8 = RG_ROW_BYTES / 8;
-  std::vector<double> potx(169 * row8, 0.0);
-  for (int ta = 0; ta < 169; ++ta)
-    for (int tb = 0; tb < 169; ++tb)
-      for (int sidx = 0; sidx < RG_SLOTS; ++sidx) {
-        const int idx = sidx + RG_SLOT0;
-        const int bin = idx <= 2 ? 0 : (idx <= 15 ? idx - 2 : 13 + ((idx - 15) >> 1));  // idx -1 -> 0
-        potx[ta * row8 + (size_t)tb * RG_SLOTS + sidx] = desc->dfire_potential[(size_t)ta * DFIRE_ROW + tb * 20 + bin];
-      }
-
   // ligand, local frame, f32 + column offset
   std::vector<float4> l4(cx.n_lig_pad);
   for (int j = 0; j < cx.n_lig_pad; ++j) {
@@ -417,12 +406,12 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   if ((rcode = upload(h, vec, &rc.field)) != LD_OK) return rcode
   UPR(x, rec_x); UPR(y, rec_y); UPR(z, rec_z); UPR(slot, rec_slot); UPR(toff, rec_toff);
   UPR(gtypes, group_types); UPR(order, group_order); UPR(modes, rec_modes);
-  UPR(l4, lig4); UPR(potx, potx); UPR(cells, cells); UPR(flat, cell_tiles);
+  UPR(l4, lig4); UPR(cells, cells); UPR(flat, cell_tiles);
 #undef UPR
   rc.n_groups = ng; rc.n_rec_pos = npos;
   rc.n_lig = cx.n_lig; rc.n_lig_pad = cx.n_lig_pad; rc.n_lig_tiles = cx.n_lig_tiles;
   rc.n_rec_modes = nrm; rc.pose_len = cx.pose_len; rc.rows_max = rows_max;
-  rc.lig_x = cx.lig_x; rc.lig_y = cx.lig_y; rc.lig_z = cx.lig_z; rc.lig_tb20 = cx.lig_tb20; rc.pot = cx.pot;
+  rc.lig_x = cx.lig_x; rc.lig_y = cx.lig_y; rc.lig_z = cx.lig_z; rc.lig_tb20 = cx.lig_tb20; rc.pot = cx.pot; rc.potx = cx.potx;
   rc.gx0 = g0[0]; rc.gy0 = g0[1]; rc.gz0 = g0[2]; rc.inv_h = inv_h;
   rc.nx = nc[0]; rc.ny = nc[1]; rc.nz = nc[2];
   const double delta = 2.0e-4 + 1.3e-5 * maxabs;  // 2x the |d2f - dist_ref| bound derived at rigid_row()
@@ -515,6 +504,22 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
   if (method == 0) {
     std::vector<double> pot(desc->dfire_potential, desc->dfire_potential + LD_DFIRE_TABLE_LEN);
     UP(pot, pot);
+    // the table re-indexed by the truncated bin-space value idx = -1..28 (DIST_TO_BINS applied here once,
+    // src/dfire.rs:49-53,337; idx -1 = the saturated `d as usize` of a negative d = index 0)
+    const size_t row8 = RG_ROW_BYTES / 8;
+    std::vector<double> potx(169 * row8, 0.0);
+    for (int ta = 0; ta < 169; ++ta)
+      for (int tb = 0; tb < 169; ++tb)
+        for (int sidx = 0; sidx < RG_SLOTS; ++sidx) {
+          const int idx = sidx + RG_SLOT0;
+          const int bin = idx <= 2 ? 0 : (idx <= 15 ? idx - 2 : 13 + ((idx - 15) >> 1));
+          potx[ta * row8 + (size_t)tb * RG_SLOTS + sidx] = pot[(size_t)ta * DFIRE_ROW + tb * 20 + bin];
+        }
+    UP(potx, potx);
+    std::vector<unsigned> rowx(R.n_pad, 0u);
+    for (int i = 0; i < R.n; ++i)
+      rowx[i] = (unsigned)(R.toff[i] / DFIRE_ROW) * (unsigned)row8 - (unsigned)RG_SLOT0 - RG_MAGIC_BITS;
+    UP(rowx, rec_rowx);
   }
 #undef UP
   h->lig_block = lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles);

@@ -30,6 +30,19 @@ constexpr int DFIRE_ROW = 169 * 20;  // src/dfire.rs:338  atoma*169*20
 constexpr double REC_PAD = 1.0e30;   // coordinates of padding atoms: never within any cut-off
 constexpr double LIG_PAD = -1.0e30;
 
+// DFIRE table re-indexed by the truncated bin-space value idx = floor(2*sqrt(dist) - 1) instead of the bin
+// (`potx`, built by ld_create): both DFIRE kernels classify a pair by rounding t - 0.5 with the magic-number add
+// x + 1.5*2^23, which leaves MAGIC_BITS + rint(x) in the float's bit pattern.
+constexpr int RG_SLOT0 = -1;                        // first bin-space index held in a shared-memory row: rint(t - 0.5)
+                                                    // is -1 for t < 0 (dist < 0.25), which the reference's saturating
+                                                    // `d as usize` sends to index 0, so slot -1 repeats slot 0
+constexpr int RG_SLOTS = 30;                        // indices -1..28 (29, the cut-off itself, is never decided in FP32)
+constexpr int RG_PREP = 16;                         // doubles per pose written by rigid_prep_kernel
+constexpr int RG_TB_BYTES = RG_SLOTS * 8;           // one ligand type inside a row
+constexpr int RG_ROW_BYTES = (169 * RG_TB_BYTES + 15) / 16 * 16;  // 40,560
+constexpr float RG_MAGIC = 12582912.0f;             // 1.5 * 2^23: x + MAGIC rounds x to the nearest integer
+constexpr unsigned RG_MAGIC_BITS = 0x4B400000u;
+
 struct DeviceComplex {
   int method;  // 0 DFIRE, 1 DNA/pyDock
   int n_rec, n_lig;
@@ -39,7 +52,9 @@ struct DeviceComplex {
   int pose_len;
   // receptor (sorted order)
   const double *rec_x, *rec_y, *rec_z;
-  const int *rec_toff;                      // DFIRE: type * 3380
+  const int *rec_toff;                      // DFIRE: type * 3380 (exact path)
+  const unsigned *rec_rowx;                 // DFIRE: type * (RG_ROW_BYTES/8) - RG_SLOT0 - RG_MAGIC_BITS (mod 2^32): element
+                                            // index into potx = bits(m + w) + rec_rowx, see dfire_items()
   const double *rec_q, *rec_eps, *rec_rad;  // DNA
   const float4 *rec_sphere;                 // static tile spheres (used when n_rec_modes == 0)
   float rec_maxabs;                         // max |coordinate| of the static receptor
@@ -49,7 +64,8 @@ struct DeviceComplex {
   const unsigned short *lig_tb20;           // DFIRE: type * 20
   const double *lig_q, *lig_eps, *lig_rad;  // DNA
   const double *lig_modes;                  // [k][3][n_lig_pad]
-  const double *pot;                        // DFIRE table
+  const double *pot;                        // DFIRE table as the reference indexes it
+  const double *potx;                       // [169][RG_ROW_BYTES/8]: row ta = [tb][RG_SLOTS], slot s <-> idx s + RG_SLOT0
   // restraints (sorted atom positions) and membrane beads
   int n_rec_rst, n_lig_rst, n_membrane;
   const int *rec_rst_off, *rec_rst_idx, *lig_rst_off, *lig_rst_idx, *membrane_idx;

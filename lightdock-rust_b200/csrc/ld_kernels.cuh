@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, 
   float lmax = 0.f, rmax = 0.f;
   for (int i = threadIdx.x; i < cx.n_lig_pad; i += blockDim.x) {
     double x = LIG_PAD, y = LIG_PAD, z = LIG_PAD;
-    int tb = 0;
+    float tw = 0.f;  // DFIRE: (float)(type * RG_SLOTS), see dfire_items()
     if (i < cx.n_lig) {
       // rotate(): self * (0, v) * self.inverse(), src/qt.rs:57-61
       const Quat v = {0.0, cx.lig_x[i], cx.lig_y[i], cx.lig_z[i]};
@@ -149,10 +149,10 @@ __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, 
         z = __dadd_rn(z, __dmul_rn(m[2 * cx.n_lig_pad + i], e));
       }
       lmax = fmaxf(lmax, fmaxf(fabsf((float)x), fmaxf(fabsf((float)y), fabsf((float)z))));
-      if (cx.method == 0) tb = cx.lig_tb20[i];
+      if (cx.method == 0) tw = (float)((cx.lig_tb20[i] / 20) * RG_SLOTS);
     }
     ox[i] = x; oy[i] = y; oz[i] = z;
-    of4[i] = make_float4((float)x, (float)y, (float)z, __int_as_float(tb));
+    of4[i] = make_float4((float)x, (float)y, (float)z, tw);
   }
   double *rx = nullptr, *ry = nullptr, *rz = nullptr;
   float4 *rsph = nullptr, *rmeta = nullptr;
@@ -232,7 +232,7 @@ __host__ __device__ inline size_t pair_smem_bytes(int method, int n_lig_pad, int
   }
   o += align16((size_t)lig_words * 4);
   o += align16((size_t)tiles_per_split * 8 * (method == 0 ? 1 : 2));
-  if (method == 0) o += (size_t)(PAIR_THREADS / 32) * RING * 4 + 32 * 8;  // work-item rings + decision table
+  if (method == 0) o += (size_t)(PAIR_THREADS / 32) * RING * 4;  // work-item rings
   return o;
 }
 __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceComplex &cx, const BatchBuffers &bb) {
@@ -355,10 +355,6 @@ __device__ __noinline__ int dfire_exact_pair(const double *gx, const double *gy,
   return bin | (d <= 3.9 ? 32 : 0);      // INTERFACE_CUTOFF on the bin-space value, src/dfire.rs:339
 }
 
-// Decision table of the FP32 classification, one float2 per truncated bin-space index idx = (int)(2*sqrt(d2)-1):
-// a pair whose d2f lies strictly inside (lo, hi) — the index's interval ((idx+1)/2)^2 .. ((idx+2)/2)^2 shrunk by
-// delta on both sides — provably has that index in the reference's FP64 arithmetic.  idx 0 has no lower edge
-// (d < 1 saturates to 0) and idx 29 (d2 >= 225) is never decided in FP32.
 __device__ __forceinline__ float rsqrt_approx(float x) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -367,87 +363,102 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
 // DIST_TO_BINS[idx]-1 without branches: idx-2 below the knee at 15, (idx+11)/2 above it, clamped at 0.
 __device__ __forceinline__ int dfire_bin_fast(int idx) { return min(max(idx - 2, 0), (idx + 11) >> 1); }
 
+// One row of <= 32 work items (receptor atom = owner lane, ligand tile of 8 atoms), one item per lane.
+// Classification in bin space, t = 2*sqrt(dist) - 1 (src/dfire.rs:336):
+//   u = 2*d2f*rsqrt.approx(d2f) - 1.5 = t_f32 - 0.5;  m = u + 1.5*2^23 holds rint(u) in its low mantissa bits;
+//   g = u - rint(u) = frac(t_f32) - 0.5 exactly.
+//   |t_f32 - t_ref| <= 2|sqrt(d2f) - sqrt(dist_ref)| + 6.4e-6 <= 1.02*delta/sqrt(d2f) + 6.4e-6 for d2f >= 3.9 and
+//   delta <= 0.3, so |g| + 1.02*delta*rsqrt(d2f) <= 0.5 - 2.5e-5 proves floor(t_ref) = rint(u) there; below d2f = 3.9
+//   every candidate index (t < 3) is bin 0 anyway (DIST_TO_BINS, src/dfire.rs:49-53), and rint(u) = -1 for t < 0,
+//   where the reference's `d as usize` saturates to index 0, is slot -1 = slot 0 of the re-indexed table potx.
+// A pair with d2f <= 225 + delta that fails the test is re-evaluated exactly (dfire_exact_pair); the interface test
+// (d <= 3.9 <=> dist <= 6.0025) is decided outside the hot loop: a per-item min(d2f) sends the rare items with a
+// contact near or below 2.45 A to a second pass that decides it in FP32 outside 6.0025 +- delta, exactly inside.
+// The table value is one 8-byte gather from potx: element bits(m + w) + rowx, w = (float)(type_lig * RG_SLOTS).
 template <bool DETAIL>
-__device__ __forceinline__ void dfire_items(const PairSmem &s, const float2 *tab, const unsigned *ring, int head,
-                                            int n_active, float rxf, float ryf, float rzf, int toff, int tile_base,
-                                            const double *gx, const double *gy, const double *gz,
-                                            const double *glx, const double *gly, const double *glz,
-                                            const double *__restrict__ pot, float delta, int n_lig, double &acc0,
-                                            double &acc1, unsigned &ifr_mask, unsigned &n_in, unsigned &n_if,
-                                            unsigned &n_tested, unsigned &n_amb) {
+__device__ __forceinline__ void dfire_items(const PairSmem &s, const unsigned *ring, int head, int n_active, float rxf,
+                                            float ryf, float rzf, unsigned rowx, int toff, int tile_base,
+                                            const double *gx, const double *gy, const double *gz, const double *glx,
+                                            const double *gly, const double *glz, const double *__restrict__ pot,
+                                            const double *__restrict__ potx, const unsigned short *lig_tb20,
+                                            float delta, float hme, int n_lig, double &acc0, double &acc1,
+                                            unsigned &ifr_mask, unsigned &n_in, unsigned &n_if, unsigned &n_tested,
+                                            unsigned &n_amb) {
   const int lane = threadIdx.x & 31;
   const bool active = lane < n_active;
   unsigned item = active ? ring[(head + lane) & (RING - 1)] : (unsigned)(lane << 16);
   const int i = item >> 16, lt = item & 0xffffu;
   const float ax = __shfl_sync(0xffffffffu, rxf, i), ay = __shfl_sync(0xffffffffu, ryf, i),
               az = __shfl_sync(0xffffffffu, rzf, i);
+  const unsigned rx = __shfl_sync(0xffffffffu, rowx, i);
   const int at = __shfl_sync(0xffffffffu, toff, i);
   if (!active) return;
-  const float thr_out = 225.0f + delta;
+  const float thr_out = 225.0f + delta, delta102 = 1.02f * delta;
   if (DETAIL) n_tested += min(LIG_TILE, n_lig - lt * LIG_TILE);
-  // pass 1 is branch-free so the 8 independent chains interleave: classify each pair in FP32;
-  // pass 2 issues the 8 table gathers back to back; pass 3 accumulates (+0.0 for pairs that are out).
-  int addr[LIG_TILE];
-  unsigned ifc_bits = 0u, amb_bits = 0u;
   const int jbase = lt * LIG_TILE;
+  unsigned slow_bits = 0u;
+  float mind2 = 3.0e38f;
 #pragma unroll
   for (int k = 0; k < LIG_TILE; ++k) {
-    const int j = jbase + ((k + lane) & (LIG_TILE - 1));
-    const float4 a = s.l4[j];
+    const float4 a = s.l4[jbase + ((k + lane) & (LIG_TILE - 1))];  // rotated start: conflict-free LDS.128
     const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
-    const float d2f = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-    // any estimate of idx will do: the interval test is what proves it (d2f == 0 gives NaN -> 0)
-    int idx = __float2int_rz(fmaf(d2f + d2f, rsqrt_approx(d2f), -1.0f));
-    idx = max(0, min(idx, 29));
-    const float2 e = tab[idx];
-    const bool inr = d2f <= thr_out;
-    const bool sure = d2f > e.x && d2f < e.y && fabsf(d2f - 6.0025f) > delta;
-    addr[k] = (inr && sure) ? at + __float_as_int(a.w) + dfire_bin_fast(idx) : -1;
-    ifc_bits |= ((inr && sure && d2f < 6.0025f) ? 1u : 0u) << k;
-    amb_bits |= ((inr && !sure) ? 1u : 0u) << k;
+    const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    mind2 = fminf(mind2, d2);
+    const float rs = rsqrt_approx(d2);
+    const float u = fmaf(d2 * rs, 2.0f, -1.5f);
+    const float m = __fadd_rn(u, RG_MAGIC);
+    const float g = __fsub_rn(u, __fsub_rn(m, RG_MAGIC));
+    const bool inr = d2 <= thr_out;
+    const bool fast = inr & (fmaf(delta102, rs, fabsf(g)) <= hme);
+    if (inr & !fast) slow_bits |= 1u << k;
+    if (fast) {
+      const double v = __ldg(potx + (unsigned)((unsigned)__float_as_int(__fadd_rn(m, a.w)) + rx));
+      if (k & 1) acc1 = __dadd_rn(acc1, v);
+      else acc0 = __dadd_rn(acc0, v);
+      if (DETAIL) {
+        ++n_in;
+        atomicAdd(&s.hist[dfire_bin_fast(__float_as_int(m) - (int)RG_MAGIC_BITS)], 1u);
+      }
+    }
   }
-  double val[LIG_TILE];
-#pragma unroll
-  for (int k = 0; k < LIG_TILE; ++k) val[k] = addr[k] >= 0 ? __ldg(pot + addr[k]) : 0.0;
-  double extra = 0.0;
-  if (amb_bits) {  // rare: too close to a decision threshold -> exact FP64 re-evaluation
-    for (unsigned b = amb_bits; b; b &= b - 1) {
-      const int k = __ffs(b) - 1;
+  if (mind2 <= 6.0025f + delta) {  // rare: a contact near or below the 2.45 A interface edge (src/dfire.rs:339-342)
+    for (int k = 0; k < LIG_TILE; ++k) {
+      if ((slow_bits >> k) & 1u) continue;  // the exact path below owns this pair entirely
       const int j = jbase + ((k + lane) & (LIG_TILE - 1));
+      const float4 a = s.l4[j];
+      const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
+      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));  // same operations as above: same bits
+      if (d2 > 6.0025f + delta) continue;
+      bool ifc = d2 < 6.0025f - delta;
+      if (!ifc) ifc = (dfire_exact_pair(gx, gy, gz, glx, gly, glz, tile_base + i, j) & ~31) == 32;  // -1 -> false
+      if (ifc) {
+        ifr_mask |= 1u << i;
+        atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
+        if (DETAIL) ++n_if;
+      }
+    }
+  }
+  if (slow_bits) {  // rare: too close to a decision threshold -> the reference's FP64 arithmetic for that pair
+    double extra = 0.0;
+    for (unsigned b = slow_bits; b; b &= b - 1) {
+      const int j = jbase + ((__ffs(b) - 1 + lane) & (LIG_TILE - 1));
       if (DETAIL) ++n_amb;
       const int r = dfire_exact_pair(gx, gy, gz, glx, gly, glz, tile_base + i, j);
       if (r >= 0) {
-        extra = __dadd_rn(extra, __ldg(pot + at + __float_as_int(s.l4[j].w) + (r & 31)));
-        if (r & 32) ifc_bits |= 1u << k;
+        extra = __dadd_rn(extra, __ldg(pot + at + lig_tb20[j] + (r & 31)));
+        if (r & 32) {
+          ifr_mask |= 1u << i;
+          atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
+          if (DETAIL) ++n_if;
+        }
         if (DETAIL) {
           ++n_in;
           atomicAdd(&s.hist[r & 31], 1u);
         }
       }
     }
+    acc0 = __dadd_rn(acc0, extra);
   }
-  if (ifc_bits) {  // rare: a contact closer than 2.45 A (src/dfire.rs:339-342)
-    ifr_mask |= 1u << i;
-    for (unsigned b = ifc_bits; b; b &= b - 1) {
-      const int j = jbase + ((__ffs(b) - 1 + lane) & (LIG_TILE - 1));
-      atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
-      if (DETAIL) ++n_if;
-    }
-  }
-  if (DETAIL) {
-#pragma unroll
-    for (int k = 0; k < LIG_TILE; ++k)
-      if (addr[k] >= 0) {
-        ++n_in;
-        atomicAdd(&s.hist[(addr[k] - at) % 20], 1u);  // at and tb are multiples of 20; bin 20 aliases to 0 of tb+1
-      }
-  }
-#pragma unroll
-  for (int k = 0; k < LIG_TILE; k += 2) {
-    acc0 = __dadd_rn(acc0, val[k]);
-    acc1 = __dadd_rn(acc1, val[k + 1]);
-  }
-  acc0 = __dadd_rn(acc0, extra);
 }
 
 template <bool DETAIL>
@@ -476,15 +487,11 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
   }
   const float delta = 5.0e-4f + 2.0e-5f * maxabs;  // |d2f - dist| bound (see above)
   const float lin = 1.0e-4f + 2.4e-7f * maxabs;    // error of an f32 atom-to-sphere-centre distance
-  float2 *tab = reinterpret_cast<float2 *>(s.rings + (PAIR_THREADS / 32) * RING);
-  if (threadIdx.x < 30) {
-    const int idx = threadIdx.x;
-    const float kf = (float)(idx + 1);
-    tab[idx] = make_float2(idx == 0 ? -INFINITY : 0.25f * kf * kf + delta,
-                           idx == 29 ? -INFINITY : 0.25f * (kf + 1.0f) * (kf + 1.0f) - delta);
-  }
-  __syncthreads();
+  // the bin-space test of dfire_items needs delta <= 0.3 (coordinates below ~15,000 A); beyond that nothing is
+  // decided in FP32 (hme < 0 sends every in-range pair to the exact path)
+  const float hme = delta <= 0.3f ? 0.5f - 2.5e-5f : -1.0f;
   const double *__restrict__ pot = cx.pot;
+  const double *__restrict__ potx = cx.potx;
   unsigned *iface_rec_out = bb.iface_rec + (size_t)pose * cx.n_rec_tiles;
   const unsigned lt_mask = (1u << lane) - 1u;
 
@@ -496,6 +503,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
     const int ia = t * REC_TILE + lane;
     const float rxf = (float)gx[ia], ryf = (float)gy[ia], rzf = (float)gz[ia];
     const int toff = cx.rec_toff[ia];
+    const unsigned rowx = cx.rec_rowx[ia];
     const float4 rs = gsph[t];
     double acc0 = 0.0, acc1 = 0.0;
     unsigned ifr_mask = 0u, n_in = 0, n_if = 0, n_tested = 0, n_amb = 0;
@@ -528,8 +536,9 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
           q_count += __popc(pm);
           __syncwarp();
           if (q_count >= 32) {  // C: a full row of work items
-            dfire_items<DETAIL>(s, tab, ring, q_head, 32, rxf, ryf, rzf, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz, pot,
-                                delta, cx.n_lig, acc0, acc1, ifr_mask, n_in, n_if, n_tested, n_amb);
+            dfire_items<DETAIL>(s, ring, q_head, 32, rxf, ryf, rzf, rowx, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz,
+                                pot, potx, cx.lig_tb20, delta, hme, cx.n_lig, acc0, acc1, ifr_mask, n_in, n_if, n_tested,
+                                n_amb);
             q_head = (q_head + 32) & (RING - 1);
             q_count -= 32;
             __syncwarp();
@@ -538,8 +547,8 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
       }
     }
     if (q_count > 0)
-      dfire_items<DETAIL>(s, tab, ring, q_head, q_count, rxf, ryf, rzf, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz, pot,
-                          delta, cx.n_lig, acc0, acc1, ifr_mask, n_in, n_if, n_tested, n_amb);
+      dfire_items<DETAIL>(s, ring, q_head, q_count, rxf, ryf, rzf, rowx, toff, t * REC_TILE, gx, gy, gz, glx, gly, glz,
+                          pot, potx, cx.lig_tb20, delta, hme, cx.n_lig, acc0, acc1, ifr_mask, n_in, n_if, n_tested, n_amb);
     __syncwarp();
     const double tsum = warp_sum(__dadd_rn(acc0, acc1));
     const unsigned rbits = __reduce_or_sync(0xffffffffu, ifr_mask);

@@ -36,16 +36,7 @@ namespace ldb200 {
 #endif
 constexpr int RG_THREADS = LDB200_RG_THREADS;
 constexpr int RG_WARPS = RG_THREADS / 32;
-constexpr int RG_SLOT0 = -1;                        // first bin-space index held in a shared-memory row: rint(t - 0.5)
-                                                    // is -1 for t < 0 (dist < 0.25), which the reference's saturating
-                                                    // `d as usize` sends to index 0, so slot -1 repeats slot 0
-constexpr int RG_SLOTS = 30;                        // indices -1..28 (29, the cut-off itself, is never decided in FP32)
-constexpr int RG_PREP = 16;                         // doubles per pose written by rigid_prep_kernel
-constexpr int RG_TB_BYTES = RG_SLOTS * 8;           // one ligand type inside a row
-constexpr int RG_ROW_BYTES = (169 * RG_TB_BYTES + 15) / 16 * 16;  // 40,560
 constexpr int RG_MAX_ROWS = 4;
-constexpr float RG_MAGIC = 12582912.0f;             // 1.5 * 2^23: x + MAGIC rounds x to the nearest integer
-constexpr unsigned RG_MAGIC_BITS = 0x4B400000u;
 
 struct RigidComplex {
   int n_groups, n_rec_pos;  // n_rec_pos = n_groups * 32 (type-grouped receptor positions, pads interspersed)
