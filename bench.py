@@ -239,6 +239,12 @@ def run_b200(args, rank, world, local_rank):
     path = {ldb200.PATH_GENERIC: "generic", ldb200.PATH_RIGID: "rigid"}[st_last["path"]]
     pair_kernel = "dfire_rigid_kernel" if path == "rigid" else "dfire_pair_kernel"
     pair_ms_step = max_over_ranks(pair_ms / args.steps)
+    pair_ms_ranks = [pair_ms / args.steps]
+    if world > 1:  # reporting only: how evenly the static swarm -> GPU map loads the ranks
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = pair_ms / args.steps
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        pair_ms_ranks = [float(x) for x in t.cpu()]
 
     # ---- end to end through the C ABI with host buffers (`e2e`) --------------------------------
     e_host = np.empty(n_local)
@@ -337,6 +343,7 @@ def run_b200(args, rank, world, local_rank):
         "peak_source": "ld_probe_peaks: non-fused DADD+DMUL rate measured on this GPU (MEASURED_PEAKS.json has no "
                        "FP64 figure; SURVEY.md 8d)",
         "algorithmic_flops_per_pair": 8, "pair_kernel_ms_per_step": pair_ms_step,
+        "pair_kernel_ms_per_step_by_rank": pair_ms_ranks,
         "pair_kernel_launches_timed": pair_launches,
         "executed_pair_test_fraction": tested, "in_cutoff_fraction": in_cut,
         "executed_frac_of_fp64_peak": achieved_tf * tested / fp64_tf,

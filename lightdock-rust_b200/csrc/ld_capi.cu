@@ -739,7 +739,8 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       CU(cudaMemsetAsync(h->d_iface_lig, 0, (size_t)nc * lig_words * sizeof(unsigned), st));
       CU(cudaMemsetAsync(h->d_unit_counter, 0, sizeof(unsigned), st));
       // work units: (group, range of poses); ~16 units per SM and group changes kept rare
-      int64_t ppu = (nc * rg.n_groups + (int64_t)h->sm_count * 16 - 1) / ((int64_t)h->sm_count * 16);
+      static const int units_per_sm = [] { const char *e = getenv("LDB200_UNITS_PER_SM"); return e ? std::max(1, atoi(e)) : 16; }();
+      int64_t ppu = (nc * rg.n_groups + (int64_t)h->sm_count * units_per_sm - 1) / ((int64_t)h->sm_count * units_per_sm);
       ppu = std::max<int64_t>(RG_WARPS, std::min<int64_t>(ppu, 1024));
       const int n_chunks = (int)((nc + ppu - 1) / ppu);
       const int64_t n_units = (int64_t)n_chunks * rg.n_groups;
