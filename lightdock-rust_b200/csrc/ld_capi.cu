@@ -795,8 +795,8 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
         if (detail) dfire_pair_kernel<true><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
         else dfire_pair_kernel<false><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
       } else {
-        if (detail) dna_pair_kernel<true><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
-        else dna_pair_kernel<false><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
+        if (detail) dna_pair_kernel<true><<<grid, DNA_THREADS, smem, st>>>(cx, bb, (int)nc);
+        else dna_pair_kernel<false><<<grid, DNA_THREADS, smem, st>>>(cx, bb, (int)nc);
       }
       ++launches;
       ++pair_launches;

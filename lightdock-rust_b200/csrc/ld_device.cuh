@@ -25,7 +25,12 @@ namespace ldb200 {
 
 constexpr int REC_TILE = 32;  // receptor atoms per tile = lanes of a warp
 constexpr int LIG_TILE = 8;   // ligand atoms per tile (unit of sphere culling)
-constexpr int PAIR_THREADS = 512;
+constexpr int PAIR_THREADS = 512;  // generic DFIRE pair kernel
+#ifndef LDB200_DNA_THREADS
+#define LDB200_DNA_THREADS 256
+#endif
+constexpr int DNA_THREADS = LDB200_DNA_THREADS;  // DNA/pyDock pair kernel: small complexes (1azp: 35 receptor tiles), so
+                                                 // smaller CTAs (more per SM) balance the tiles over the warps better
 constexpr int DFIRE_ROW = 169 * 20;  // src/dfire.rs:338  atoma*169*20
 constexpr double REC_PAD = 1.0e30;   // coordinates of padding atoms: never within any cut-off
 constexpr double LIG_PAD = -1.0e30;

@@ -605,7 +605,7 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }
 
 template <bool DETAIL>
-__global__ void __launch_bounds__(PAIR_THREADS, 2)
+__global__ void __launch_bounds__(DNA_THREADS, 1024 / DNA_THREADS)
     dna_pair_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int pose = blockIdx.x / bb.rec_splits, split = blockIdx.x % bb.rec_splits;
