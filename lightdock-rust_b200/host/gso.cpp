@@ -5,6 +5,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <exception>
 #include <functional>
 #include <memory>
@@ -169,6 +170,26 @@ void Swarm::update_luciferin() {
   scatter_scores(who, scores.data());
 }
 
+// Squared distances from (x1, y1, z1) to every glowworm and the candidate flags `luciferin test && d2 <= hi`,
+// element-wise and in the reference's operation order ((x1-x2)*(x1-x2) + (y1-y2)*(y1-y2) + (z1-z2)*(z1-z2), never
+// fused: the file is built with -ffp-contract=off), so SIMD lanes compute exactly what the scalar loop would.
+// Compiled for AVX2 and baseline x86-64; the loader picks at run time.
+__attribute__((target_clones("avx2", "default"), optimize("O3"))) static unsigned neighbour_candidates(
+    const double *__restrict__ px, const double *__restrict__ py, const double *__restrict__ pz,
+    const double *__restrict__ lum, size_t n, double x1, double y1, double z1, double l1, double hi,
+    double *__restrict__ d2s, unsigned char *__restrict__ flag) {
+  unsigned any = 0;
+  for (size_t j = 0; j < n; ++j) {
+    const double dx = x1 - px[j], dy = y1 - py[j], dz = z1 - pz[j];
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    d2s[j] = d2;
+    const unsigned char f = (unsigned char)((l1 < lum[j]) & (d2 <= hi));
+    flag[j] = f;
+    any |= f;
+  }
+  return any;
+}
+
 void Swarm::movement_phase(StdRng &rng) {
   const size_t n = glowworms.size();
   // snapshot of every glowworm's pose before anybody moves (src/swarm.rs:74-86): a glowworm moves towards where
@@ -187,13 +208,41 @@ void Swarm::movement_phase(StdRng &rng) {
     if (nl || !g.lig_nmodes.empty()) snap_anm_ligs[i] = g.lig_nmodes;
     snap_luciferins[i] = g.luciferin;
   }
-  for (size_t i = 0; i < n; ++i) {  // src/swarm.rs:88-103
+  // Neighbour search, src/swarm.rs:88-103: j is a neighbour of i iff luciferin_i < luciferin_j and
+  // distance(i, j) < vision_range_i, distance = sqrt(dx*dx + dy*dy + dz*dz) (src/glowworm.rs:193-202).
+  // O(n^2) per swarm and step and the bulk of the host time, so it runs over flat copies of the positions and
+  // without the square root: with v2 = v*v and eps = 2^-53, d2 < v2*(1 - 4 eps) implies sqrt(d2) < v and
+  // d2 > v2*(1 + 4 eps) implies the opposite whatever the roundings of sqrt and of v*v; only inside that sliver
+  // (relative width 1e-15) is the reference's expression evaluated.  The decisions are exactly the reference's.
+  flat_xyz.resize(3 * n);
+  for (size_t i = 0; i < n; ++i) {
+    flat_xyz[i] = glowworms[i].translation[0];
+    flat_xyz[n + i] = glowworms[i].translation[1];
+    flat_xyz[2 * n + i] = glowworms[i].translation[2];
+  }
+  const double *px = flat_xyz.data(), *py = px + n, *pz = py + n, *lum = snap_luciferins.data();
+  constexpr double kSliver = 4.0 * 1.1102230246251565e-16;
+  scratch_d2.resize(n);
+  scratch_flag.assign((n + 7) / 8 * 8, 0);  // padded to whole 8-byte words
+  double *d2s = scratch_d2.data();
+  unsigned char *flag = scratch_flag.data();
+  for (size_t i = 0; i < n; ++i) {
     Glowworm &g1 = glowworms[i];
     g1.neighbors.clear();
-    for (size_t j = 0; j < n; ++j) {
-      if (i == j) continue;
-      const Glowworm &g2 = glowworms[j];
-      if (g1.luciferin < g2.luciferin && distance(g1, g2) < g1.vision_range) g1.neighbors.push_back(g2.id);
+    const double x1 = px[i], y1 = py[i], z1 = pz[i], l1 = lum[i], v = g1.vision_range;
+    const double v2 = v * v, lo = v2 * (1.0 - kSliver), hi = v2 * (1.0 + kSliver);
+    // pass 1, branch-free (the luciferin test is a coin flip: a branch on it mispredicts half the time)
+    const unsigned any = neighbour_candidates(px, py, pz, lum, n, x1, y1, z1, l1, hi, d2s, flag);
+    if (!any) continue;
+    // pass 2: the few candidates, in index order (flags scanned eight at a time)
+    for (size_t j0 = 0; j0 < n; j0 += 8) {
+      uint64_t w;
+      std::memcpy(&w, flag + j0, 8);
+      if (!w) continue;
+      for (size_t j = j0; j < std::min(n, j0 + 8); ++j) {
+        if (!flag[j] || j == i) continue;
+        if (d2s[j] < lo || std::sqrt(d2s[j]) < v) g1.neighbors.push_back(glowworms[j].id);
+      }
     }
   }
   for (size_t i = 0; i < n; ++i) glowworms[i].compute_probability_moving_toward_neighbor(snap_luciferins);

@@ -67,7 +67,8 @@ struct Swarm {  // src/swarm.rs
  private:  // scratch of movement_phase
   std::vector<std::vector<double>> snap_positions, snap_anm_recs, snap_anm_ligs;
   std::vector<Quaternion> snap_rotations;
-  std::vector<double> snap_luciferins;
+  std::vector<double> snap_luciferins, flat_xyz, scratch_d2;
+  std::vector<unsigned char> scratch_flag;
 };
 
 struct GSO {  // src/lib.rs:20-59
