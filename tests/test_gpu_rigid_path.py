@@ -123,6 +123,25 @@ def test_rigid_edge_cases():
     assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
 
 
+def test_degenerate_quaternions_match_the_reference_semantics():
+    """A zero quaternion makes rotate() divide by zero (src/qt.rs:48-50): every coordinate is NaN, no pair passes
+    `dist <= 225` and the score is (0*0.0157 - 4.7) * -1 = 4.7.  Both kernels must follow the oracle there, and a
+    huge / tiny but finite norm must change nothing."""
+    cx, pos, _ = case("1ppe", O.DFIRE)
+    p = pos[:6].copy()
+    p[0, 3:7] = 0.0
+    p[1, 3:7] *= 1e150
+    p[2, 3:7] *= 1e-150
+    e_ref, d_ref = cx.energy(p, detail=True)
+    assert e_ref[0] == 4.7 and d_ref["n_in_cutoff"][0] == 0
+    sc = scorer_from_oracle(cx)
+    for path in (ldb200.PATH_RIGID, ldb200.PATH_GENERIC):
+        sc.set_path(path)
+        e, d = sc.energy_detail(p)
+        assert e[0] == 4.7 and d["n_in_cutoff"][0] == 0
+        assert_parity(e[1:], {k: v[1:] for k, v in d.items()}, e_ref[1:], {k: v[1:] for k, v in d_ref.items()}, cx.method)
+
+
 def test_rigid_decision_thresholds_exact():
     """Pairs on / next to every bin edge, the 15 A cut-off (dist == 225 -> bin 20) and the 2.45 A interface
     edge, a few ulps and small offsets either side, under rotations and tiny shifts."""
