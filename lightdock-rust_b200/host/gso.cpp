@@ -190,24 +190,10 @@ __attribute__((target_clones("avx2", "default"), optimize("O3"))) static unsigne
   return any;
 }
 
-void Swarm::movement_phase(StdRng &rng) {
+void Swarm::find_neighbors() {
   const size_t n = glowworms.size();
-  // snapshot of every glowworm's pose before anybody moves (src/swarm.rs:74-86): a glowworm moves towards where
-  // its neighbour WAS at the start of the step.  Flat scratch buffers, reused from step to step.
-  const size_t nr = n ? glowworms[0].rec_nmodes.size() : 0, nl = n ? glowworms[0].lig_nmodes.size() : 0;
-  snap_positions.resize(n);
-  snap_rotations.resize(n);
-  snap_anm_recs.resize(n);
-  snap_anm_ligs.resize(n);
   snap_luciferins.resize(n);
-  for (size_t i = 0; i < n; ++i) {
-    const Glowworm &g = glowworms[i];
-    snap_positions[i] = g.translation;  // element-wise assignment into already-sized vectors: no allocation
-    snap_rotations[i] = g.rotation;
-    if (nr || !g.rec_nmodes.empty()) snap_anm_recs[i] = g.rec_nmodes;
-    if (nl || !g.lig_nmodes.empty()) snap_anm_ligs[i] = g.lig_nmodes;
-    snap_luciferins[i] = g.luciferin;
-  }
+  for (size_t i = 0; i < n; ++i) snap_luciferins[i] = glowworms[i].luciferin;
   // Neighbour search, src/swarm.rs:88-103: j is a neighbour of i iff luciferin_i < luciferin_j and
   // distance(i, j) < vision_range_i, distance = sqrt(dx*dx + dy*dy + dz*dz) (src/glowworm.rs:193-202).
   // O(n^2) per swarm and step and the bulk of the host time, so it runs over flat copies of the positions and
@@ -245,6 +231,27 @@ void Swarm::movement_phase(StdRng &rng) {
       }
     }
   }
+}
+
+void Swarm::movement_phase(StdRng &rng) {
+  const size_t n = glowworms.size();
+  // snapshot of every glowworm's pose before anybody moves (src/swarm.rs:74-86): a glowworm moves towards where
+  // its neighbour WAS at the start of the step.  Flat scratch buffers, reused from step to step.
+  const size_t nr = n ? glowworms[0].rec_nmodes.size() : 0, nl = n ? glowworms[0].lig_nmodes.size() : 0;
+  snap_positions.resize(n);
+  snap_rotations.resize(n);
+  snap_anm_recs.resize(n);
+  snap_anm_ligs.resize(n);
+  snap_luciferins.resize(n);
+  for (size_t i = 0; i < n; ++i) {
+    const Glowworm &g = glowworms[i];
+    snap_positions[i] = g.translation;  // element-wise assignment into already-sized vectors: no allocation
+    snap_rotations[i] = g.rotation;
+    if (nr || !g.rec_nmodes.empty()) snap_anm_recs[i] = g.rec_nmodes;
+    if (nl || !g.lig_nmodes.empty()) snap_anm_ligs[i] = g.lig_nmodes;
+    snap_luciferins[i] = g.luciferin;
+  }
+  find_neighbors();
   for (size_t i = 0; i < n; ++i) glowworms[i].compute_probability_moving_toward_neighbor(snap_luciferins);
   for (size_t i = 0; i < n; ++i) {
     Glowworm &g = glowworms[i];

@@ -62,6 +62,7 @@ struct Swarm {  // src/swarm.rs
   size_t gather_poses(std::vector<double> &rows, std::vector<uint32_t> &who) const;
   void scatter_scores(const std::vector<uint32_t> &who, const double *scores);
   void movement_phase(StdRng &rng);                           // :72-126
+  void find_neighbors();                                      // :85-103, fills Glowworm::neighbors
   void save(uint32_t step, const std::string &output_directory) const;  // :128-167
 
  private:  // scratch of movement_phase

@@ -174,6 +174,29 @@ int ldh_case_multi_gso(ldh_case *c, int n_swarms, int n_glowworms, const double 
 }
 
 // Host-only pieces, testable without a GPU ------------------------------------------------------
+// The neighbour search of Swarm::movement_phase on a given swarm state.  xyz [n][3]; out_offsets [n+1];
+// out_idx must hold n*(n-1) entries.  Returns the total number of neighbours.
+int ldh_find_neighbors(int n, const double *xyz, const double *luciferin, const double *vision_range, int *out_offsets,
+                       int *out_idx) {
+  LDH_TRY
+  Swarm sw;
+  for (int i = 0; i < n; ++i) {
+    sw.glowworms.emplace_back((uint32_t)i, std::vector<double>{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]},
+                              Quaternion(1.0, 0.0, 0.0, 0.0), std::vector<double>(), std::vector<double>(), nullptr, false);
+    sw.glowworms.back().luciferin = luciferin[i];
+    sw.glowworms.back().vision_range = vision_range[i];
+  }
+  sw.find_neighbors();
+  int k = 0;
+  for (int i = 0; i < n; ++i) {
+    out_offsets[i] = k;
+    for (uint32_t id : sw.glowworms[i].neighbors) out_idx[k++] = (int)id;
+  }
+  out_offsets[n] = k;
+  return k;
+  LDH_CATCH(-1)
+}
+
 double ldh_rng_draws(unsigned long long seed, int n, double *out) {
   StdRng r = StdRng::seed_from_u64(seed);
   double last = 0;

@@ -38,6 +38,7 @@ def load_host_library():
         lib.ldh_rng_draws.argtypes = [C.c_ulonglong, C.c_int, C.c_void_p]
         lib.ldh_slerp.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         lib.ldh_rotate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ldh_find_neighbors.argtypes = [C.c_int] + [C.c_void_p] * 5
         lib.ldh_build_model.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p] + [C.c_void_p] * 10
         _lib = lib
     return _lib
@@ -63,6 +64,21 @@ def rotate(q, v):
     q, v, out = np.asarray(q, np.float64), np.asarray(v, np.float64), np.empty(3)
     load_host_library().ldh_rotate(q.ctypes.data, v.ctypes.data, out.ctypes.data)
     return out
+
+
+def find_neighbors(xyz, luciferin, vision_range):
+    """Host-only: the neighbour search of Swarm::movement_phase (src/swarm.rs:85-103) on a given swarm state."""
+    lib = load_host_library()
+    xyz = np.ascontiguousarray(xyz, np.float64).reshape(-1, 3)
+    n = xyz.shape[0]
+    lum = np.ascontiguousarray(luciferin, np.float64)
+    vr = np.ascontiguousarray(vision_range, np.float64)
+    off = np.zeros(n + 1, np.int32)
+    idx = np.zeros(max(1, n * (n - 1)), np.int32)
+    k = lib.ldh_find_neighbors(n, xyz.ctypes.data, lum.ctypes.data, vr.ctypes.data, off.ctypes.data, idx.ctypes.data)
+    if k < 0:
+        raise _err(lib)
+    return [idx[off[i]:off[i + 1]].tolist() for i in range(n)]
 
 
 def build_model(pdb_path, method, active_restraints=()):

@@ -113,3 +113,48 @@ def test_cli_argument_errors_match_reference(tmp_path):
     bad.write_text('{"anm_seed": 1}')
     r = subprocess.run([cli, str(bad), "initial_positions_0.dat", "10", "dna"], capture_output=True, text=True)
     assert r.returncode == 0 and "missing field" in r.stderr
+
+
+def test_neighbour_search_equals_the_reference_expression():
+    """Swarm::movement_phase's neighbour rule (src/swarm.rs:85-103): j is a neighbour of i iff
+    luciferin_i < luciferin_j and sqrt(dx*dx + dy*dy + dz*dz) < vision_range_i, listed in index order.
+    The host evaluates it without the square root outside a 1e-15 sliver and with SIMD; the lists must be
+    identical to the literal expression, including distances EXACTLY equal to the vision range, zero vision
+    ranges, equal luciferins and coincident glowworms."""
+    import math
+    from ldb200 import host
+    rng = np.random.default_rng(12)
+
+    def literal(xyz, lum, vr):
+        out = []
+        for i in range(len(xyz)):
+            nb = []
+            for j in range(len(xyz)):
+                if i == j or not (lum[i] < lum[j]):
+                    continue
+                x1, y1, z1 = xyz[i]; x2, y2, z2 = xyz[j]
+                d = math.sqrt((x1 - x2) * (x1 - x2) + (y1 - y2) * (y1 - y2) + (z1 - z2) * (z1 - z2))
+                if d < vr[i]:
+                    nb.append(j)
+            out.append(nb)
+        return out
+
+    for trial in range(6):
+        n = [200, 200, 37, 1, 2, 203][trial]
+        xyz = rng.normal(0, 3.0, size=(n, 3))
+        lum = rng.uniform(0, 10, size=n)
+        vr = rng.uniform(0, 5, size=n)
+        if n >= 37:
+            lum[5] = lum[6] = lum[7]          # equal luciferins: strict < fails both ways
+            xyz[9] = xyz[8]                   # coincident glowworms: distance 0
+            vr[10] = 0.0                      # fmax(0, ...) in update_vision_range can produce it
+            # distances exactly on the vision range and one ulp either side
+            for k, (a, b) in enumerate([(11, 12), (13, 14), (15, 16)]):
+                d = math.sqrt(sum((xyz[a] - xyz[b]) ** 2))
+                dd = math.sqrt((xyz[a][0] - xyz[b][0]) * (xyz[a][0] - xyz[b][0]) + (xyz[a][1] - xyz[b][1]) * (xyz[a][1] - xyz[b][1])
+                               + (xyz[a][2] - xyz[b][2]) * (xyz[a][2] - xyz[b][2]))
+                vr[a] = [dd, np.nextafter(dd, 0), np.nextafter(dd, 100)][k]
+                lum[a], lum[b] = 1.0, 2.0
+            xyz[17] = [0.0, 0.0, 0.0]; xyz[18] = [3.0, 4.0, 0.0]; vr[17] = 5.0; lum[17], lum[18] = 1.0, 2.0   # exactly 5
+            xyz[19] = [0.0, 0.0, 0.0]; xyz[20] = [3.0, 4.0, 0.0]; vr[19] = np.nextafter(5.0, 6); lum[19], lum[20] = 1.0, 2.0
+        assert host.find_neighbors(xyz, lum, vr) == literal(xyz, lum, vr), f"trial {trial}"
