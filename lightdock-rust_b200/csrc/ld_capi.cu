@@ -629,15 +629,31 @@ static int regrow(T **p, size_t count) {
   return LD_OK;
 }
 
+// Receptor tile ranges per pose (= CTAs per pose) for the generic kernels when a batch is too small to fill the
+// GPU with one CTA per pose (one swarm = 200 poses).  A CTA's warps take tiles from a queue, so its time is
+// ceil(tiles per CTA / warps) tile-times plus a fixed prologue (ligand staging, barriers: about half a tile-time);
+// the launch takes ceil(CTAs / resident CTAs) such waves.  Pick the split count that minimises that product —
+// e.g. 51 tiles over 3 CTAs of 16 warps is 17 tiles each, i.e. TWO rounds; 4 CTAs of 13 tiles is one.
 static int choose_splits(const ld_handle *h, int64_t n) {
   const int tiles = std::max(1, h->cx.n_rec_tiles);
   if (h->forced_splits > 0) return std::min(h->forced_splits, tiles);
-  const int64_t target = (int64_t)h->sm_count * 4;  // CTAs wanted to fill the machine with 2 waves of 2 CTA/SM
-  if (n >= target) return 1;
-  int64_t s = (target + n - 1) / std::max<int64_t>(n, 1);
-  // keep at least 4 tiles per CTA so the ligand staging is amortised
-  s = std::min<int64_t>(s, std::max(1, tiles / 4));
-  return (int)std::max<int64_t>(1, s);
+  const bool dna = h->cx.method != 0;
+  const int warps = (dna ? DNA_THREADS : PAIR_THREADS) / 32;
+  const int64_t resident = (int64_t)h->sm_count * (dna ? 1024 / DNA_THREADS : 2);
+  if (n >= 2 * resident) return 1;
+  double best = 1e300;
+  int best_s = 1;
+  for (int s = 1; s <= tiles; ++s) {
+    const int tps = (tiles + s - 1) / s;
+    const double rounds = (double)((tps + warps - 1) / warps) + 0.5;
+    const double waves = (double)((n * s + resident - 1) / resident);
+    const double cost = rounds * waves;
+    if (cost < best - 1e-9) {
+      best = cost;
+      best_s = s;
+    }
+  }
+  return best_s;
 }
 
 static bool use_rigid(const ld_handle *h) { return h->rigid_ok && h->path_mode != LD_PATH_GENERIC; }
