@@ -119,6 +119,16 @@ int ld_pose_len(const ld_handle *h);
  * Replaces the loop of Swarm::update_luciferin over Score::energy (src/swarm.rs:66-70). */
 int ld_score_batch(ld_handle *h, int64_t n_poses, const double *poses, double *energies);
 
+/* The same call split in two so a caller can keep LD_SLOTS batches in flight: _begin copies the pose rows into
+ * the slot's pinned staging buffer and enqueues the copies and kernels on the slot's own stream, then returns;
+ * _end waits for that slot and writes the energies.  The pose buffer may be reused as soon as _begin returns.
+ * Typical use (host/gso.cpp, MultiGSO): while the device scores one half of the swarms the host runs the GSO
+ * movement phase of the other half.  One batch per slot at a time; a slot with a batch pending must be ended before
+ * it is begun again, and before any other scoring call on the handle uses slot 0. */
+#define LD_SLOTS 2
+int ld_score_batch_begin(ld_handle *h, int32_t slot, int64_t n_poses, const double *poses);
+int ld_score_batch_end(ld_handle *h, int32_t slot, double *energies);
+
 /* Same, with device-resident poses/energies on a caller-provided CUDA stream (cudaStream_t passed
  * as void*; NULL = the handle's own stream).  Asynchronous with respect to the host. */
 int ld_score_batch_device(ld_handle *h, int64_t n_poses, const double *d_poses, double *d_energies,

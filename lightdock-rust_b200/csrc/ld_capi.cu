@@ -39,29 +39,12 @@ extern "C" int ld_device_count(void) {
 extern "C" const char *ld_version(void) { return "lightdock_b200 0.1 (sm_100a)"; }
 
 // ---------------------------------------------------------------------------------------------
-struct ld_handle {
-  int device = 0;
+// Everything one batch in flight needs: a stream, pinned staging, device pose/energy buffers and the kernels'
+// work buffers.  A handle owns LD_SLOTS of them so ld_score_batch_begin/_end can keep two batches in flight (the
+// host prepares the next batch while the device scores the current one); the synchronous calls use slot 0.
+struct Workspace {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  DeviceComplex cx{};
-  std::vector<void *> owned;  // device allocations of the complex
-  std::vector<int> rec_perm, lig_perm;  // sorted position -> original atom index
-  std::vector<double> rec_xyz_orig;     // original receptor coordinates (for ld_transform_batch)
-  int use_anm = 0;
-  int forced_splits = 0;
-  size_t lig_block = 0, rec_block = 0;
-  // work buffers
-  // rigid-ligand DFIRE path (ld_rigid.cuh): type-grouped receptor + ligand-frame cell lists
-  bool rigid_ok = false;
-  int path_mode = LD_PATH_AUTO;
-  RigidComplex rc{};
-  DeviceComplex cxr{};                  // what finalize_kernel sees on the rigid path (groups as tiles)
-  std::vector<int> rec_perm_r;          // grouped position -> original atom index, -1 = pad lane
-  unsigned *d_unit_counter = nullptr;
-  RigidComplex *d_rc = nullptr;         // device copy of rc for the rare exact path
-  double *d_prep = nullptr;             // [cap_chunk][RG_PREP] per-pose rotation data (rigid path)
-  int64_t cap_prep = 0;
-  std::string rigid_info;
   int64_t cap_poses = 0;   // capacity of poses/energies/detail buffers
   int64_t cap_chunk = 0;   // capacity (poses) of partial/bitmap buffers
   int64_t cap_blocks = 0;  // capacity (poses) of the per-pose coordinate blocks (generic path only)
@@ -73,14 +56,39 @@ struct ld_handle {
   unsigned *d_iface_rec = nullptr, *d_iface_lig = nullptr;
   double *h_poses = nullptr, *h_energies = nullptr;  // pinned
   int64_t cap_pinned = 0;
-  int max_smem_optin = 0;
-  int sm_count = 0;
+  unsigned *d_unit_counter = nullptr;   // rigid path: work-unit counter
+  double *d_prep = nullptr;             // rigid path: [cap_prep][RG_PREP] per-pose rotation data
+  int64_t cap_prep = 0;
   ld_batch_stats stats{};
   // profiling: events bracketing every kernel of the last call (4 per chunk)
-  bool profiling = false;
   std::vector<cudaEvent_t> prof_events;
   size_t prof_used = 0;
   cudaStream_t last_stream = nullptr;
+  int64_t pending = -1;                 // poses of the batch begun on this slot and not yet ended (-1 = none)
+};
+
+struct ld_handle {
+  int device = 0;
+  Workspace ws[LD_SLOTS];
+  Workspace *w = &ws[0];                // the slot the current call works on (one host thread per handle)
+  DeviceComplex cx{};
+  std::vector<void *> owned;  // device allocations of the complex
+  std::vector<int> rec_perm, lig_perm;  // sorted position -> original atom index
+  std::vector<double> rec_xyz_orig;     // original receptor coordinates (for ld_transform_batch)
+  int use_anm = 0;
+  int forced_splits = 0;
+  size_t lig_block = 0, rec_block = 0;
+  // rigid-ligand DFIRE path (ld_rigid.cuh): type-grouped receptor + ligand-frame cell lists
+  bool rigid_ok = false;
+  int path_mode = LD_PATH_AUTO;
+  RigidComplex rc{};
+  DeviceComplex cxr{};                  // what finalize_kernel sees on the rigid path (groups as tiles)
+  std::vector<int> rec_perm_r;          // grouped position -> original atom index, -1 = pad lane
+  RigidComplex *d_rc = nullptr;         // device copy of rc for the rare exact path
+  std::string rigid_info;
+  int max_smem_optin = 0;
+  int sm_count = 0;
+  bool profiling = false;
 };
 
 template <typename T>
@@ -208,19 +216,22 @@ static SortedMol sort_molecule(const ld_molecule_desc &m, int method, int tile, 
 extern "C" int ld_destroy(ld_handle *h) {
   if (!h) return LD_OK;
   cudaSetDevice(h->device);
+  for (Workspace &w : h->ws) {
+    if (w.stream) cudaStreamSynchronize(w.stream);
+    cudaFree(w.d_poses); cudaFree(w.d_energies); cudaFree(w.d_detail);
+    cudaFree(w.d_lig_blocks); cudaFree(w.d_rec_blocks); cudaFree(w.d_partials);
+    cudaFree(w.d_iface_rec); cudaFree(w.d_iface_lig); cudaFree(w.d_unit_counter); cudaFree(w.d_prep);
+    cudaFreeHost(w.h_poses); cudaFreeHost(w.h_energies);
+    for (cudaEvent_t e : w.prof_events) cudaEventDestroy(e);
+    if (w.ev0) cudaEventDestroy(w.ev0);
+    if (w.ev1) cudaEventDestroy(w.ev1);
+    if (w.stream) cudaStreamDestroy(w.stream);
+  }
   for (void *p : h->owned) cudaFree(p);
-  cudaFree(h->d_poses); cudaFree(h->d_energies); cudaFree(h->d_detail);
-  cudaFree(h->d_lig_blocks); cudaFree(h->d_rec_blocks); cudaFree(h->d_partials);
-  cudaFree(h->d_iface_rec); cudaFree(h->d_iface_lig); cudaFree(h->d_unit_counter); cudaFree(h->d_rc); cudaFree(h->d_prep);
-  cudaFreeHost(h->h_poses); cudaFreeHost(h->h_energies);
-  for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
-  if (h->ev0) cudaEventDestroy(h->ev0);
-  if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaFree(h->d_rc);
   delete h;
   return LD_OK;
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // Rigid-ligand DFIRE path (ld_rigid.cuh): everything below is built once per complex.
@@ -426,7 +437,6 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   h->cxr.n_rec_pad = npos;
   if ((rcode = upload(h, rst_idx, &h->cxr.rec_rst_idx)) != LD_OK) return rcode;
   if ((rcode = upload(h, mem_idx, &h->cxr.membrane_idx)) != LD_OK) return rcode;
-  CU(cudaMalloc(reinterpret_cast<void **>(&h->d_unit_counter), sizeof(unsigned)));
   CU(cudaMalloc(reinterpret_cast<void **>(&h->d_rc), sizeof(RigidComplex)));
   CU(cudaMemcpy(h->d_rc, &rc, sizeof(RigidComplex), cudaMemcpyHostToDevice));
   CU(cudaFuncSetAttribute(dfire_rigid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
@@ -460,9 +470,11 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
                               "; this library is built for sm_100a only");
   h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   h->sm_count = prop.multiProcessorCount;
-  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-  CU(cudaEventCreate(&h->ev0));
-  CU(cudaEventCreate(&h->ev1));
+  for (Workspace &w : h->ws) {
+    CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&w.ev0));
+    CU(cudaEventCreate(&w.ev1));
+  }
 
   const int nrm = h->use_anm ? desc->receptor.n_modes : 0, nlm = h->use_anm ? desc->ligand.n_modes : 0;
   SortedMol R = sort_molecule(desc->receptor, desc->method == LD_METHOD_DFIRE ? LD_METHOD_DFIRE : LD_METHOD_DNA,
@@ -590,32 +602,33 @@ extern "C" int ld_set_profiling(ld_handle *h, int32_t on) {
 
 extern "C" int ld_get_stats(ld_handle *h, ld_batch_stats *out) {
   if (!h || !out) return fail(LD_EINVAL, "ld_get_stats: NULL argument");
-  if (h->profiling && h->prof_used >= 4) {
+  h->w = &h->ws[0];
+  if (h->profiling && h->w->prof_used >= 4) {
     CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->last_stream));
+    CU(cudaStreamSynchronize(h->w->last_stream));
     double t[3] = {0, 0, 0};
-    for (size_t c = 0; c + 4 <= h->prof_used; c += 4)
+    for (size_t c = 0; c + 4 <= h->w->prof_used; c += 4)
       for (int k = 0; k < 3; ++k) {
         float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, h->prof_events[c + k], h->prof_events[c + k + 1]));
+        CU(cudaEventElapsedTime(&ms, h->w->prof_events[c + k], h->w->prof_events[c + k + 1]));
         t[k] += ms;
       }
-    h->stats.transform_ms = t[0];
-    h->stats.pair_ms = t[1];
-    h->stats.finalize_ms = t[2];
+    h->w->stats.transform_ms = t[0];
+    h->w->stats.pair_ms = t[1];
+    h->w->stats.finalize_ms = t[2];
   }
-  *out = h->stats;
+  *out = h->w->stats;
   return LD_OK;
 }
 
 static int prof_mark(ld_handle *h, cudaStream_t st) {
   if (!h->profiling) return LD_OK;
-  if (h->prof_used == h->prof_events.size()) {
+  if (h->w->prof_used == h->w->prof_events.size()) {
     cudaEvent_t e;
     CU(cudaEventCreate(&e));
-    h->prof_events.push_back(e);
+    h->w->prof_events.push_back(e);
   }
-  CU(cudaEventRecord(h->prof_events[h->prof_used++], st));
+  CU(cudaEventRecord(h->w->prof_events[h->w->prof_used++], st));
   return LD_OK;
 }
 
@@ -667,43 +680,43 @@ static int64_t chunk_limit(const ld_handle *h, bool rigid) {
 
 static int ensure_chunk(ld_handle *h, int64_t chunk, int splits, bool need_blocks) {
   int rc;
-  if (need_blocks && chunk > h->cap_blocks) {
-    if ((rc = regrow(&h->d_lig_blocks, (size_t)chunk * h->lig_block)) != LD_OK) return rc;
-    if ((rc = regrow(&h->d_rec_blocks, (size_t)chunk * h->rec_block)) != LD_OK) return rc;
-    h->cap_blocks = chunk;
+  if (need_blocks && chunk > h->w->cap_blocks) {
+    if ((rc = regrow(&h->w->d_lig_blocks, (size_t)chunk * h->lig_block)) != LD_OK) return rc;
+    if ((rc = regrow(&h->w->d_rec_blocks, (size_t)chunk * h->rec_block)) != LD_OK) return rc;
+    h->w->cap_blocks = chunk;
   }
-  if (chunk <= h->cap_chunk && splits <= h->cap_splits) return LD_OK;
-  chunk = std::max(chunk, h->cap_chunk);
-  splits = std::max(splits, h->cap_splits);
+  if (chunk <= h->w->cap_chunk && splits <= h->w->cap_splits) return LD_OK;
+  chunk = std::max(chunk, h->w->cap_chunk);
+  splits = std::max(splits, h->w->cap_splits);
   const int lig_words = (h->cx.n_lig_pad + 31) / 32;
   const int tiles = std::max(1, std::max(h->cx.n_rec_tiles, h->rigid_ok ? h->rc.n_groups : 0));
-  if ((rc = regrow(&h->d_partials, (size_t)chunk * tiles * 2)) != LD_OK) return rc;
-  if ((rc = regrow(&h->d_iface_rec, (size_t)chunk * tiles)) != LD_OK) return rc;
-  if ((rc = regrow(&h->d_iface_lig, (size_t)chunk * splits * std::max(1, lig_words))) != LD_OK) return rc;
-  h->cap_chunk = chunk;
-  h->cap_splits = splits;
+  if ((rc = regrow(&h->w->d_partials, (size_t)chunk * tiles * 2)) != LD_OK) return rc;
+  if ((rc = regrow(&h->w->d_iface_rec, (size_t)chunk * tiles)) != LD_OK) return rc;
+  if ((rc = regrow(&h->w->d_iface_lig, (size_t)chunk * splits * std::max(1, lig_words))) != LD_OK) return rc;
+  h->w->cap_chunk = chunk;
+  h->w->cap_splits = splits;
   return LD_OK;
 }
 
 static int ensure_poses(ld_handle *h, int64_t n, bool detail) {
-  if (n > h->cap_poses) {
+  if (n > h->w->cap_poses) {
     int rc;
-    if ((rc = regrow(&h->d_poses, (size_t)n * h->cx.pose_len)) != LD_OK) return rc;
-    if ((rc = regrow(&h->d_energies, (size_t)n)) != LD_OK) return rc;
-    if (h->d_detail) { cudaFree(h->d_detail); h->d_detail = nullptr; }
-    h->cap_poses = n;
+    if ((rc = regrow(&h->w->d_poses, (size_t)n * h->cx.pose_len)) != LD_OK) return rc;
+    if ((rc = regrow(&h->w->d_energies, (size_t)n)) != LD_OK) return rc;
+    if (h->w->d_detail) { cudaFree(h->w->d_detail); h->w->d_detail = nullptr; }
+    h->w->cap_poses = n;
   }
-  if (detail && !h->d_detail) {
+  if (detail && !h->w->d_detail) {
     int rc;
-    if ((rc = regrow(&h->d_detail, (size_t)h->cap_poses)) != LD_OK) return rc;
+    if ((rc = regrow(&h->w->d_detail, (size_t)h->w->cap_poses)) != LD_OK) return rc;
   }
-  if (n > h->cap_pinned) {
-    cudaFreeHost(h->h_poses); cudaFreeHost(h->h_energies);
-    h->h_poses = h->h_energies = nullptr;
-    CU(cudaHostAlloc(reinterpret_cast<void **>(&h->h_poses), (size_t)n * h->cx.pose_len * sizeof(double),
+  if (n > h->w->cap_pinned) {
+    cudaFreeHost(h->w->h_poses); cudaFreeHost(h->w->h_energies);
+    h->w->h_poses = h->w->h_energies = nullptr;
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&h->w->h_poses), (size_t)n * h->cx.pose_len * sizeof(double),
                      cudaHostAllocDefault));
-    CU(cudaHostAlloc(reinterpret_cast<void **>(&h->h_energies), (size_t)n * sizeof(double), cudaHostAllocDefault));
-    h->cap_pinned = n;
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&h->w->h_energies), (size_t)n * sizeof(double), cudaHostAllocDefault));
+    h->w->cap_pinned = n;
   }
   return LD_OK;
 }
@@ -713,11 +726,11 @@ static int ensure_poses(ld_handle *h, int64_t n, bool detail) {
 static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_energies, cudaStream_t st,
                       ld_pose_detail *d_detail, std::vector<unsigned> *host_ifr, std::vector<unsigned> *host_ifl) {
   const DeviceComplex &cx = h->cx;
-  h->stats = ld_batch_stats{};
-  h->stats.n_poses = n;
-  h->stats.pair_evals_bruteforce = n * (int64_t)cx.n_rec * (int64_t)cx.n_lig;
-  h->prof_used = 0;
-  h->last_stream = st;
+  h->w->stats = ld_batch_stats{};
+  h->w->stats.n_poses = n;
+  h->w->stats.pair_evals_bruteforce = n * (int64_t)cx.n_rec * (int64_t)cx.n_lig;
+  h->w->prof_used = 0;
+  h->w->last_stream = st;
   if (n == 0) return LD_OK;
   const int64_t climit = chunk_limit(h, use_rigid(h));
   const int lig_words = (cx.n_lig_pad + 31) / 32;
@@ -733,27 +746,28 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       const RigidComplex &rg = h->rc;
       BatchBuffers bb{};
       bb.poses = d_poses + (size_t)p0 * cx.pose_len;
-      bb.partials = h->d_partials;
-      bb.iface_rec = h->d_iface_rec;
-      bb.iface_lig = h->d_iface_lig;
+      bb.partials = h->w->d_partials;
+      bb.iface_rec = h->w->d_iface_rec;
+      bb.iface_lig = h->w->d_iface_lig;
       bb.energies = d_energies + p0;
       bb.detail = detail ? (void *)(d_detail + p0) : nullptr;
       bb.rec_splits = 1;
       bb.tiles_per_split = rg.n_groups;
       bb.lig_words = lig_words;
-      h->stats.rec_splits = 1;
-      h->stats.path = LD_PATH_RIGID;
-      if (nc > h->cap_prep) {
-        if ((rc = regrow(&h->d_prep, (size_t)nc * RG_PREP)) != LD_OK) return rc;
-        h->cap_prep = nc;
+      h->w->stats.rec_splits = 1;
+      h->w->stats.path = LD_PATH_RIGID;
+      if (!h->w->d_unit_counter) CU(cudaMalloc(reinterpret_cast<void **>(&h->w->d_unit_counter), sizeof(unsigned)));
+      if (nc > h->w->cap_prep) {
+        if ((rc = regrow(&h->w->d_prep, (size_t)nc * RG_PREP)) != LD_OK) return rc;
+        h->w->cap_prep = nc;
       }
       if ((rc = prof_mark(h, st)) != LD_OK) return rc;
       // per-pose rotation data (the only "transform" on this path: nothing is moved per atom)
-      rigid_prep_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(bb.poses, (int)nc, cx.pose_len, h->d_prep);
+      rigid_prep_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(bb.poses, (int)nc, cx.pose_len, h->w->d_prep);
       ++launches;
       if ((rc = prof_mark(h, st)) != LD_OK) return rc;
-      CU(cudaMemsetAsync(h->d_iface_lig, 0, (size_t)nc * lig_words * sizeof(unsigned), st));
-      CU(cudaMemsetAsync(h->d_unit_counter, 0, sizeof(unsigned), st));
+      CU(cudaMemsetAsync(h->w->d_iface_lig, 0, (size_t)nc * lig_words * sizeof(unsigned), st));
+      CU(cudaMemsetAsync(h->w->d_unit_counter, 0, sizeof(unsigned), st));
       // work units: (group, range of poses); ~16 units per SM and group changes kept rare
       static const int units_per_sm = [] { const char *e = getenv("LDB200_UNITS_PER_SM"); return e ? std::max(1, atoi(e)) : 16; }();
       int64_t ppu = (nc * rg.n_groups + (int64_t)h->sm_count * units_per_sm - 1) / ((int64_t)h->sm_count * units_per_sm);
@@ -763,11 +777,11 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       const unsigned grid = (unsigned)std::min<int64_t>(h->sm_count, n_units);
       const size_t smem = rigid_smem_bytes(rg.n_lig_pad, rg.rows_max);
       if (detail)
-        dfire_rigid_kernel<true><<<grid, RG_THREADS, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->d_unit_counter,
-                                                             h->d_rc, h->d_prep);
+        dfire_rigid_kernel<true><<<grid, RG_THREADS, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->w->d_unit_counter,
+                                                             h->d_rc, h->w->d_prep);
       else
-        dfire_rigid_kernel<false><<<grid, RG_THREADS, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->d_unit_counter,
-                                                             h->d_rc, h->d_prep);
+        dfire_rigid_kernel<false><<<grid, RG_THREADS, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->w->d_unit_counter,
+                                                             h->d_rc, h->w->d_prep);
       ++launches;
       ++pair_launches;
       if ((rc = prof_mark(h, st)) != LD_OK) return rc;
@@ -778,28 +792,28 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       if ((rc = prof_mark(h, st)) != LD_OK) return rc;
       CU(cudaGetLastError());
       if (host_ifr) {
-        CU(cudaMemcpyAsync(host_ifr->data() + (size_t)p0 * rg.n_groups, h->d_iface_rec,
+        CU(cudaMemcpyAsync(host_ifr->data() + (size_t)p0 * rg.n_groups, h->w->d_iface_rec,
                            (size_t)nc * rg.n_groups * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(host_ifl->data() + (size_t)p0 * lig_words, h->d_iface_lig,
+        CU(cudaMemcpyAsync(host_ifl->data() + (size_t)p0 * lig_words, h->w->d_iface_lig,
                            (size_t)nc * lig_words * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
       }
       continue;
     }
-    h->stats.path = LD_PATH_GENERIC;
+    h->w->stats.path = LD_PATH_GENERIC;
     BatchBuffers bb{};
     bb.poses = d_poses + (size_t)p0 * cx.pose_len;
-    bb.lig_blocks = h->d_lig_blocks;
-    bb.rec_blocks = h->d_rec_blocks;
-    bb.partials = h->d_partials;
-    bb.iface_rec = h->d_iface_rec;
-    bb.iface_lig = h->d_iface_lig;
+    bb.lig_blocks = h->w->d_lig_blocks;
+    bb.rec_blocks = h->w->d_rec_blocks;
+    bb.partials = h->w->d_partials;
+    bb.iface_rec = h->w->d_iface_rec;
+    bb.iface_lig = h->w->d_iface_lig;
     bb.energies = d_energies + p0;
     bb.detail = detail ? (void *)(d_detail + p0) : nullptr;
     bb.rec_splits = splits;
     bb.tiles_per_split = (std::max(1, cx.n_rec_tiles) + splits - 1) / splits;
     bb.lig_words = lig_words;
-    h->stats.rec_splits = splits;
+    h->w->stats.rec_splits = splits;
     if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     transform_kernel<<<(unsigned)nc, 256, 0, st>>>(cx, bb, (int)nc);
     ++launches;
@@ -818,7 +832,7 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       ++pair_launches;
     } else {
       
-      CU(cudaMemsetAsync(h->d_iface_lig, 0, (size_t)nc * splits * std::max(1, lig_words) * sizeof(unsigned), st));
+      CU(cudaMemsetAsync(h->w->d_iface_lig, 0, (size_t)nc * splits * std::max(1, lig_words) * sizeof(unsigned), st));
     }
     if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     const unsigned fgrid = (unsigned)((nc + 3) / 4);
@@ -830,9 +844,9 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
     if (host_ifr) {
       // detail mode: fetch this chunk's bitmaps (OR over splits for the ligand) before they are overwritten
       std::vector<unsigned> lig_tmp((size_t)nc * splits * lig_words);
-      CU(cudaMemcpyAsync(host_ifr->data() + (size_t)p0 * cx.n_rec_tiles, h->d_iface_rec,
+      CU(cudaMemcpyAsync(host_ifr->data() + (size_t)p0 * cx.n_rec_tiles, h->w->d_iface_rec,
                          (size_t)nc * cx.n_rec_tiles * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-      CU(cudaMemcpyAsync(lig_tmp.data(), h->d_iface_lig, lig_tmp.size() * sizeof(unsigned), cudaMemcpyDeviceToHost,
+      CU(cudaMemcpyAsync(lig_tmp.data(), h->w->d_iface_lig, lig_tmp.size() * sizeof(unsigned), cudaMemcpyDeviceToHost,
                          st));
       CU(cudaStreamSynchronize(st));
       for (int64_t p = 0; p < nc; ++p)
@@ -841,8 +855,8 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
             (*host_ifl)[(size_t)(p0 + p) * lig_words + w] |= lig_tmp[((size_t)p * splits + c) * lig_words + w];
     }
   }
-  h->stats.kernel_launches = launches;
-  h->stats.pair_launches = pair_launches;
+  h->w->stats.kernel_launches = launches;
+  h->w->stats.pair_launches = pair_launches;
   return LD_OK;
 }
 
@@ -850,17 +864,21 @@ extern "C" int ld_score_batch_device(ld_handle *h, int64_t n_poses, const double
                                      void *stream) {
   if (!h || n_poses < 0 || (n_poses > 0 && (!d_poses || !d_energies)))
     return fail(LD_EINVAL, "ld_score_batch_device: bad argument");
+  h->w = &h->ws[0];
+  if (h->w->pending >= 0) return fail(LD_EINVAL, "ld_score_batch_device: slot 0 has a batch pending");
   CU(cudaSetDevice(h->device));
-  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : h->w->stream;
   return run_device(h, n_poses, d_poses, d_energies, st, nullptr, nullptr, nullptr);
 }
 
 static int score_host(ld_handle *h, int64_t n, const double *poses, double *energies, ld_pose_detail *detail,
                       uint8_t *iface_rec, uint8_t *iface_lig) {
   if (!h || n < 0 || (n > 0 && (!poses || !energies))) return fail(LD_EINVAL, "ld_score_batch: bad argument");
+  h->w = &h->ws[0];
+  if (h->w->pending >= 0) return fail(LD_EINVAL, "ld_score_batch: slot 0 has a batch pending (ld_score_batch_end it first)");
   CU(cudaSetDevice(h->device));
   if (n == 0) {
-    h->stats = ld_batch_stats{};
+    h->w->stats = ld_batch_stats{};
     return LD_OK;
   }
   const DeviceComplex &cx = h->cx;
@@ -868,10 +886,10 @@ static int score_host(ld_handle *h, int64_t n, const double *poses, double *ener
   int rc;
   if ((rc = ensure_poses(h, n, want_detail)) != LD_OK) return rc;
   const size_t pose_bytes = (size_t)n * cx.pose_len * sizeof(double);
-  std::memcpy(h->h_poses, poses, pose_bytes);
-  CU(cudaEventRecord(h->ev0, h->stream));
-  CU(cudaMemcpyAsync(h->d_poses, h->h_poses, pose_bytes, cudaMemcpyHostToDevice, h->stream));
-  if (want_detail) CU(cudaMemsetAsync(h->d_detail, 0, (size_t)n * sizeof(ld_pose_detail), h->stream));
+  std::memcpy(h->w->h_poses, poses, pose_bytes);
+  CU(cudaEventRecord(h->w->ev0, h->w->stream));
+  CU(cudaMemcpyAsync(h->w->d_poses, h->w->h_poses, pose_bytes, cudaMemcpyHostToDevice, h->w->stream));
+  if (want_detail) CU(cudaMemsetAsync(h->w->d_detail, 0, (size_t)n * sizeof(ld_pose_detail), h->w->stream));
   const int lig_words = (cx.n_lig_pad + 31) / 32;
   std::vector<unsigned> ifr, ifl;
   const bool want_iface = want_detail && (iface_rec || iface_lig);
@@ -881,18 +899,18 @@ static int score_host(ld_handle *h, int64_t n, const double *poses, double *ener
     ifr.assign((size_t)n * std::max(1, rec_tiles), 0u);
     ifl.assign((size_t)n * std::max(1, lig_words), 0u);
   }
-  rc = run_device(h, n, h->d_poses, h->d_energies, h->stream, want_detail ? h->d_detail : nullptr,
+  rc = run_device(h, n, h->w->d_poses, h->w->d_energies, h->w->stream, want_detail ? h->w->d_detail : nullptr,
                   want_iface ? &ifr : nullptr, want_iface ? &ifl : nullptr);
   if (rc != LD_OK) return rc;
-  CU(cudaMemcpyAsync(h->h_energies, h->d_energies, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(h->w->h_energies, h->w->d_energies, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->w->stream));
   if (want_detail)
-    CU(cudaMemcpyAsync(detail, h->d_detail, (size_t)n * sizeof(ld_pose_detail), cudaMemcpyDeviceToHost, h->stream));
-  CU(cudaEventRecord(h->ev1, h->stream));
-  CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpyAsync(detail, h->w->d_detail, (size_t)n * sizeof(ld_pose_detail), cudaMemcpyDeviceToHost, h->w->stream));
+  CU(cudaEventRecord(h->w->ev1, h->w->stream));
+  CU(cudaStreamSynchronize(h->w->stream));
   float ms = 0.f;
-  CU(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  h->stats.device_ms = ms;
-  std::memcpy(energies, h->h_energies, (size_t)n * sizeof(double));
+  CU(cudaEventElapsedTime(&ms, h->w->ev0, h->w->ev1));
+  h->w->stats.device_ms = ms;
+  std::memcpy(energies, h->w->h_energies, (size_t)n * sizeof(double));
   if (want_iface) {
     for (int64_t p = 0; p < n; ++p) {
       if (iface_rec) {
@@ -914,6 +932,47 @@ extern "C" int ld_score_batch(ld_handle *h, int64_t n_poses, const double *poses
   return score_host(h, n_poses, poses, energies, nullptr, nullptr, nullptr);
 }
 
+extern "C" int ld_score_batch_begin(ld_handle *h, int32_t slot, int64_t n, const double *poses) {
+  if (!h || slot < 0 || slot >= LD_SLOTS || n < 0 || (n > 0 && !poses))
+    return fail(LD_EINVAL, "ld_score_batch_begin: bad argument");
+  Workspace *w = &h->ws[slot];
+  if (w->pending >= 0) return fail(LD_EINVAL, "ld_score_batch_begin: the slot already has a batch pending");
+  h->w = w;
+  CU(cudaSetDevice(h->device));
+  if (n > 0) {
+    int rc;
+    if ((rc = ensure_poses(h, n, false)) != LD_OK) return rc;
+    const size_t pose_bytes = (size_t)n * h->cx.pose_len * sizeof(double);
+    std::memcpy(w->h_poses, poses, pose_bytes);
+    CU(cudaEventRecord(w->ev0, w->stream));
+    CU(cudaMemcpyAsync(w->d_poses, w->h_poses, pose_bytes, cudaMemcpyHostToDevice, w->stream));
+    if ((rc = run_device(h, n, w->d_poses, w->d_energies, w->stream, nullptr, nullptr, nullptr)) != LD_OK) return rc;
+    CU(cudaMemcpyAsync(w->h_energies, w->d_energies, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
+    CU(cudaEventRecord(w->ev1, w->stream));
+  } else {
+    w->stats = ld_batch_stats{};
+  }
+  w->pending = n;
+  return LD_OK;
+}
+
+extern "C" int ld_score_batch_end(ld_handle *h, int32_t slot, double *energies) {
+  if (!h || slot < 0 || slot >= LD_SLOTS) return fail(LD_EINVAL, "ld_score_batch_end: bad argument");
+  Workspace *w = &h->ws[slot];
+  if (w->pending < 0) return fail(LD_EINVAL, "ld_score_batch_end: no batch pending on the slot");
+  const int64_t n = w->pending;
+  w->pending = -1;
+  if (n == 0) return LD_OK;
+  if (!energies) return fail(LD_EINVAL, "ld_score_batch_end: energies is NULL");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(w->stream));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
+  w->stats.device_ms = ms;
+  std::memcpy(energies, w->h_energies, (size_t)n * sizeof(double));
+  return LD_OK;
+}
+
 extern "C" int ld_score_batch_detail(ld_handle *h, int64_t n_poses, const double *poses, double *energies,
                                      ld_pose_detail *detail, uint8_t *iface_rec, uint8_t *iface_lig) {
   if (!detail) return fail(LD_EINVAL, "ld_score_batch_detail: detail is NULL");
@@ -923,30 +982,32 @@ extern "C" int ld_score_batch_detail(ld_handle *h, int64_t n_poses, const double
 extern "C" int ld_transform_batch(ld_handle *h, int64_t n, const double *poses, double *rec_coords,
                                   double *lig_coords) {
   if (!h || n < 0 || (n > 0 && !poses)) return fail(LD_EINVAL, "ld_transform_batch: bad argument");
+  h->w = &h->ws[0];
+  if (h->w->pending >= 0) return fail(LD_EINVAL, "ld_transform_batch: slot 0 has a batch pending");
   CU(cudaSetDevice(h->device));
   if (n == 0) return LD_OK;
   const DeviceComplex &cx = h->cx;
   int rc;
   if ((rc = ensure_poses(h, n, false)) != LD_OK) return rc;
-  CU(cudaMemcpyAsync(h->d_poses, poses, (size_t)n * cx.pose_len * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->w->d_poses, poses, (size_t)n * cx.pose_len * sizeof(double), cudaMemcpyHostToDevice, h->w->stream));
   const int64_t climit = chunk_limit(h, false);
   std::vector<unsigned char> lb, rb;
   for (int64_t p0 = 0; p0 < n; p0 += climit) {
     const int64_t nc = std::min(climit, n - p0);
     if ((rc = ensure_chunk(h, nc, 1, true)) != LD_OK) return rc;
     BatchBuffers bb{};
-    bb.poses = h->d_poses + (size_t)p0 * cx.pose_len;
-    bb.lig_blocks = h->d_lig_blocks;
-    bb.rec_blocks = h->d_rec_blocks;
-    transform_kernel<<<(unsigned)nc, 256, 0, h->stream>>>(cx, bb, (int)nc);
+    bb.poses = h->w->d_poses + (size_t)p0 * cx.pose_len;
+    bb.lig_blocks = h->w->d_lig_blocks;
+    bb.rec_blocks = h->w->d_rec_blocks;
+    transform_kernel<<<(unsigned)nc, 256, 0, h->w->stream>>>(cx, bb, (int)nc);
     CU(cudaGetLastError());
     lb.resize((size_t)nc * h->lig_block);
-    CU(cudaMemcpyAsync(lb.data(), h->d_lig_blocks, lb.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(lb.data(), h->w->d_lig_blocks, lb.size(), cudaMemcpyDeviceToHost, h->w->stream));
     if (h->rec_block) {
       rb.resize((size_t)nc * h->rec_block);
-      CU(cudaMemcpyAsync(rb.data(), h->d_rec_blocks, rb.size(), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaMemcpyAsync(rb.data(), h->w->d_rec_blocks, rb.size(), cudaMemcpyDeviceToHost, h->w->stream));
     }
-    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaStreamSynchronize(h->w->stream));
     for (int64_t p = 0; p < nc; ++p) {
       if (lig_coords) {
         const double *x = reinterpret_cast<const double *>(lb.data() + (size_t)p * h->lig_block);

@@ -383,34 +383,57 @@ class Workers {
 
 void MultiGSO::run_lane(const std::vector<size_t> &mine, const Score *sc, uint32_t steps, int host_threads) {
   const size_t ns = mine.size();
-  if (ns == 0) return;
+  if (ns == 0 || steps == 0) return;
   Workers workers(std::min<int>(std::max(1, host_threads), (int)ns));
   const size_t pl = sc->pose_len();
-  std::vector<double> rows, scores;
+  // The swarms are split into `nh` sets that leapfrog: while the device scores one set's batch the host runs the
+  // other set's luciferin update, movement phase and gather.  Every swarm still sees gather -> score -> update ->
+  // move once per step, in that order, so its trajectory is what the one-set loop (and a stand-alone run) gives.
+  const int nh = (sc->slots() >= 2 && ns >= 2) ? 2 : 1;
+  struct Half {
+    size_t lo = 0, hi = 0;  // range of `mine`
+    std::vector<double> rows, scores;
+    std::vector<size_t> first;
+  } half[2];
+  for (int k = 0; k < nh; ++k) {
+    half[k].lo = ns * k / nh;
+    half[k].hi = ns * (k + 1) / nh;
+    half[k].first.assign(half[k].hi - half[k].lo + 1, 0);
+  }
   std::vector<std::vector<uint32_t>> who(ns);
   std::vector<std::vector<double>> swarm_rows(ns);
-  std::vector<size_t> first(ns + 1, 0);
-  for (uint32_t step = 1; step <= steps; ++step) {
-    workers.for_each(ns, [&](size_t k) {  // which glowworms must be rescored, and their pose rows
-      who[k].clear();
-      swarm_rows[k].clear();
-      runs[mine[k]].swarm.gather_poses(swarm_rows[k], who[k]);
+  auto gather_and_begin = [&](int k) {
+    Half &h = half[k];
+    workers.for_each(h.hi - h.lo, [&](size_t i) {  // which glowworms must be rescored, and their pose rows
+      const size_t s = h.lo + i;
+      who[s].clear();
+      swarm_rows[s].clear();
+      runs[mine[s]].swarm.gather_poses(swarm_rows[s], who[s]);
     });
-    for (size_t k = 0; k < ns; ++k) first[k + 1] = first[k] + swarm_rows[k].size();
-    rows.resize(first[ns]);
-    workers.for_each(ns, [&](size_t k) {
-      std::copy(swarm_rows[k].begin(), swarm_rows[k].end(), rows.begin() + first[k]);
+    for (size_t i = 0; i < h.hi - h.lo; ++i) h.first[i + 1] = h.first[i] + swarm_rows[h.lo + i].size();
+    h.rows.resize(h.first.back());
+    workers.for_each(h.hi - h.lo, [&](size_t i) {
+      std::copy(swarm_rows[h.lo + i].begin(), swarm_rows[h.lo + i].end(), h.rows.begin() + h.first[i]);
     });
-    const size_t n = rows.size() / pl;
-    scores.resize(n);
-    if (n) sc->energy_batch(n, rows.data(), scores.data());  // ONE batched launch for all swarms of the lane
-    workers.for_each(ns, [&](size_t k) {
-      GSO &r = runs[mine[k]];
-      r.swarm.scatter_scores(who[k], scores.data() + first[k] / pl);
+    h.scores.resize(h.rows.size() / pl);
+    sc->energy_batch_begin(k, h.scores.size(), h.rows.data());  // ONE batched launch for all swarms of the set
+  };
+  auto end_and_move = [&](int k, uint32_t step) {
+    Half &h = half[k];
+    sc->energy_batch_end(k, h.scores.data());
+    workers.for_each(h.hi - h.lo, [&](size_t i) {
+      GSO &r = runs[mine[h.lo + i]];
+      r.swarm.scatter_scores(who[h.lo + i], h.scores.data() + h.first[i] / pl);
       r.swarm.movement_phase(r.rng);
       if ((step % 10 == 0 || step == 1) && !r.output_directory.empty()) r.swarm.save(step, r.output_directory);
     });
-  }
+  };
+  for (int k = 0; k < nh; ++k) gather_and_begin(k);
+  for (uint32_t step = 1; step <= steps; ++step)
+    for (int k = 0; k < nh; ++k) {
+      end_and_move(k, step);
+      if (step < steps) gather_and_begin(k);
+    }
 }
 
 void MultiGSO::run(uint32_t steps, int host_threads) {

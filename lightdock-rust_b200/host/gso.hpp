@@ -94,8 +94,8 @@ struct MultiGSO {
            size_t lig_num_anm, std::string output_directory);
   // host_threads: persistent workers for the per-swarm host phases (gather, luciferin update, movement, save).
   // Swarms never interact and the kernels are batch-invariant, so trajectories do not depend on it.
-  // (Measured on B200: with these phases parallel the step is >90 % device time; splitting the swarms into
-  // concurrently driven sets with cloned scoring objects did not pay and was dropped.)
+  // The swarms leapfrog in two sets over Score::energy_batch_begin/_end, so one set's host phases overlap the
+  // other set's device scoring.
   void run(uint32_t steps, int host_threads = 1);
   uint64_t energy_calls() const;
 

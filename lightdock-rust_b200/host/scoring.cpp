@@ -175,6 +175,16 @@ void CudaScore::energy_batch(size_t n, const double *poses, double *energies) co
     throw std::runtime_error(std::string("lightdock_b200: ") + ld_last_error());
 }
 
+void CudaScore::energy_batch_begin(int slot, size_t n, const double *poses) const {
+  if (ld_score_batch_begin(handle_, slot, (int64_t)n, poses) != LD_OK)
+    throw std::runtime_error(std::string("lightdock_b200: ") + ld_last_error());
+}
+
+void CudaScore::energy_batch_end(int slot, double *energies) const {
+  if (ld_score_batch_end(handle_, slot, energies) != LD_OK)
+    throw std::runtime_error(std::string("lightdock_b200: ") + ld_last_error());
+}
+
 double CudaScore::energy(const std::vector<double> &translation, const Quaternion &rotation,
                          const std::vector<double> &rec_nmodes, const std::vector<double> &lig_nmodes) const {
   std::vector<double> row(pose_len_, 0.0);

@@ -32,6 +32,24 @@ class Score {
   // poses: n rows of pose_len() doubles (tx,ty,tz,qw,qx,qy,qz, rec extents, lig extents)
   virtual void energy_batch(size_t n, const double *poses, double *energies) const = 0;
   virtual size_t pose_len() const = 0;
+  // energy_batch in two halves, so a caller can keep `slots()` batches in flight: begin enqueues the batch and
+  // returns (the pose buffer may be reused at once), end waits for it and writes the energies.  The default is
+  // the synchronous call at `end`; CudaScore maps them to ld_score_batch_begin / _end.
+  virtual int slots() const { return 1; }
+  virtual void energy_batch_begin(int slot, size_t n, const double *poses) const {
+    (void)slot;
+    pending_.assign(poses, poses + n * pose_len());
+    pending_n_ = n;
+  }
+  virtual void energy_batch_end(int slot, double *energies) const {
+    (void)slot;
+    if (pending_n_) energy_batch(pending_n_, pending_.data(), energies);
+    pending_n_ = 0;
+  }
+
+ private:
+  mutable std::vector<double> pending_;
+  mutable size_t pending_n_ = 0;
 };
 
 // Numeric content of DFIREDockingModel / DNADockingModel / PYDOCKDockingModel.
@@ -69,6 +87,9 @@ class CudaScore : public Score {
                 const std::vector<double> &rec_nmodes, const std::vector<double> &lig_nmodes) const override;
   void energy_batch(size_t n, const double *poses, double *energies) const override;
   size_t pose_len() const override { return pose_len_; }
+  int slots() const override { return LD_SLOTS; }
+  void energy_batch_begin(int slot, size_t n, const double *poses) const override;
+  void energy_batch_end(int slot, double *energies) const override;
 
   const DockingModel &receptor() const { return receptor_; }
   const DockingModel &ligand() const { return ligand_; }

@@ -17,7 +17,7 @@ DFIRE_TABLE_LEN = 169 * 169 * 20
 
 EXPORTS = ["ld_create", "ld_destroy", "ld_pose_len", "ld_score_batch", "ld_score_batch_device",
            "ld_score_batch_detail", "ld_transform_batch", "ld_get_stats", "ld_set_rec_splits",
-           "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version", "ld_set_path", "ld_path_info", "ld_device_count"]
+           "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version", "ld_set_path", "ld_path_info", "ld_device_count", "ld_score_batch_begin", "ld_score_batch_end"]
 
 PATH_AUTO, PATH_GENERIC, PATH_RIGID = 0, 1, 2
 
@@ -78,6 +78,8 @@ def load_library():
         lib.ld_get_stats.argtypes = [C.c_void_p, C.POINTER(BatchStats)]
         lib.ld_set_rec_splits.argtypes = [C.c_void_p, C.c_int32]
         lib.ld_set_profiling.argtypes = [C.c_void_p, C.c_int32]
+        lib.ld_score_batch_begin.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p]
+        lib.ld_score_batch_end.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         lib.ld_set_path.argtypes = [C.c_void_p, C.c_int32]
         lib.ld_path_info.argtypes = [C.c_void_p]
         lib.ld_path_info.restype = C.c_char_p
@@ -167,6 +169,17 @@ class Scorer:
         poses = self._poses(poses)
         e = np.empty(poses.shape[0], dtype=np.float64)
         _check(self.lib, self.lib.ld_score_batch(self.h, poses.shape[0], _p(poses), _p(e)))
+        return e
+
+    def energy_begin(self, slot, poses):
+        """Enqueue a batch on `slot` (0 or 1) and return at once; energy_end(slot) collects it."""
+        poses = self._poses(poses)
+        _check(self.lib, self.lib.ld_score_batch_begin(self.h, int(slot), poses.shape[0], _p(poses)))
+        return poses.shape[0]
+
+    def energy_end(self, slot, n):
+        e = np.empty(n, dtype=np.float64)
+        _check(self.lib, self.lib.ld_score_batch_end(self.h, int(slot), _p(e) if n else None))
         return e
 
     def energy_detail(self, poses):

@@ -236,3 +236,30 @@ def test_rigid_full_size_properties():
     rel = np.abs(e2 - e[::40]) / np.abs(e[::40])
     # a pair sitting within ~1e-12 A of a bin edge may flip under the re-computed coordinates; none expected
     assert np.quantile(rel, 0.99) < 1e-9 and rel.max() < ENERGY_RTOL, (np.quantile(rel, 0.99), rel.max())
+
+
+def test_begin_end_slots_equal_the_synchronous_call():
+    """ld_score_batch_begin/_end keep two batches in flight on one handle (MultiGSO's leapfrog); results must be
+    the synchronous call's bits, in any interleaving, and misuse must be refused rather than corrupt a batch."""
+    for name, method in (("1k4c", O.DFIRE), ("2uuy", O.DFIRE), ("1azp", O.DNA)):
+        cx, pos, _ = case(name, method)
+        sc = scorer_from_oracle(cx)
+        a, b = pos[:120], pos[60:200]
+        ea, eb = sc.energy(a), sc.energy(b)
+        na = sc.energy_begin(0, a)
+        nb = sc.energy_begin(1, b)
+        assert np.array_equal(sc.energy_end(1, nb), eb)      # out of order on purpose
+        nb2 = sc.energy_begin(1, a[:7])                      # slot 1 reused while slot 0 is still pending
+        assert np.array_equal(sc.energy_end(0, na), ea)
+        assert np.array_equal(sc.energy_end(1, nb2), ea[:7])
+        n0 = sc.energy_begin(0, np.zeros((0, cx.pose_len)))  # empty batches are legal
+        assert sc.energy_end(0, n0).shape == (0,)
+        sc.energy_begin(0, a)
+        with pytest.raises(ldb200.LdError):
+            sc.energy_begin(0, b)                            # slot busy
+        with pytest.raises(ldb200.LdError):
+            sc.energy(b)                                     # the synchronous call needs slot 0
+        assert np.array_equal(sc.energy_end(0, len(a)), ea)
+        with pytest.raises(ldb200.LdError):
+            sc.energy_end(0, 1)                              # nothing pending
+        assert np.array_equal(sc.energy(b), eb)
