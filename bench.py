@@ -282,7 +282,8 @@ def run_b200(args, rank, world, local_rank):
         gso = {"steps": args.gso_steps, "swarms": args.swarms, "energy_calls": int(calls_t.item()),
                "wall_s": gso_s, "poses_per_s": calls_t.item() / gso_s, "host_threads_per_rank": threads,
                "moved_fraction": calls_t.item() / (n_total * args.gso_steps),
-               "what": "lightdock host GSO (C++ MultiGSO) + one ld_score_batch per step, wall clock incl. host movement phase"}
+               "what": "lightdock host GSO (C++ MultiGSO): real control flow and RNG streams, moved-only rescoring, two swarm sets "
+                       "leapfrogging over ld_score_batch_begin/_end; wall clock incl. every host phase"}
 
     if rank != 0:
         if world > 1:
