@@ -398,7 +398,7 @@ def main():
     ap.add_argument("--glowworms", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gso-steps", type=int, default=10, help="steps of the real GSO loop for the gso_run figure (0 = skip)")
+    ap.add_argument("--gso-steps", type=int, default=20, help="steps of the real GSO loop for the gso_run figure (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
