@@ -346,16 +346,24 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
     }
   float g0[3];
   int nc[3];
-  const float inv_h = (float)(1.0 / cell);
-  const double hh = 1.0 / (double)inv_h;  // the cell size the device's (f - g0) * inv_h implies
-  double maxabs = 0.0;
-  for (int d = 0; d < 3; ++d) {
-    g0[d] = (float)(lo[d] - reach - 0.05);
-    nc[d] = (int)std::floor((hi[d] + reach + 0.05 - (double)g0[d]) / hh) + 1;
-    maxabs = std::max(maxabs, std::max(std::fabs((double)g0[d]), std::fabs((double)g0[d] + nc[d] * hh)));
+  float inv_h = 0.f;
+  double hh = 0.0, maxabs = 0.0;
+  size_t ncell = 0;
+  // 1 A cells by default; a ligand so large that the grid would pass 2^24 cells (~270 MB of host scratch, ~130 MB
+  // of offsets on the device) gets proportionally coarser cells instead of losing the fast path
+  for (;; cell *= 1.25) {
+    inv_h = (float)(1.0 / cell);
+    hh = 1.0 / (double)inv_h;  // the cell size the device's (f - g0) * inv_h implies
+    maxabs = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      g0[d] = (float)(lo[d] - reach - 0.05);
+      nc[d] = (int)std::floor((hi[d] + reach + 0.05 - (double)g0[d]) / hh) + 1;
+      maxabs = std::max(maxabs, std::max(std::fabs((double)g0[d]), std::fabs((double)g0[d] + nc[d] * hh)));
+    }
+    ncell = (size_t)nc[0] * nc[1] * nc[2];
+    if (ncell <= ((size_t)1 << 24) || cell > 16.0) break;
   }
-  const size_t ncell = (size_t)nc[0] * nc[1] * nc[2];
-  if (ncell > ((size_t)1 << 26)) { h->rigid_info = "rigid path off: cell grid too large"; return LD_OK; }
+  if (ncell > ((size_t)1 << 24)) { h->rigid_info = "rigid path off: cell grid too large"; return LD_OK; }
   // Two passes (count, fill) over z-slabs of the grid, one host thread per slab: a slab owns its cells, so
   // the passes need no synchronisation, and tiles are visited in ascending order, so every list is sorted.
   std::vector<unsigned> count(ncell, 0u);
