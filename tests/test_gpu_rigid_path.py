@@ -263,3 +263,22 @@ def test_begin_end_slots_equal_the_synchronous_call():
         with pytest.raises(ldb200.LdError):
             sc.energy_end(0, 1)                              # nothing pending
         assert np.array_equal(sc.energy(b), eb)
+
+
+def test_rigid_huge_sparse_ligand_coarsens_the_grid():
+    """A ligand whose bounding box would need more than 2^24 one-angstrom cells gets coarser cells, a larger
+    coordinate magnitude M and therefore a wider FP32 margin; parity must hold all the same."""
+    cx, pos, _ = case("1ppe", O.DFIRE)
+    lig2 = copy.copy(cx.lig)
+    lig2.coords = cx.lig.coords * 13.0    # ~250 x 250 x 310 A: more than 2^24 one-angstrom cells with the 15 A margins
+    cx2 = O.Complex(cx.rec, lig2, O.DFIRE, False, cx.potential)
+    sc = _rigid(cx2)
+    info = sc.path_info()
+    cell = float(info.split("cell ")[1].split(" A")[0])
+    assert cell > 1.0, info
+    rng = np.random.default_rng(31)
+    poses = random_poses(rng, 32, 7, centre=cx.rec.coords.mean(axis=0), spread=40.0)
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    e_ref, d_ref = cx2.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, O.DFIRE)
+    assert d_ref["n_in_cutoff"].max() > 0
