@@ -383,9 +383,45 @@ def run_b200(args, rank, world, local_rank):
                    "api": "ld_score_batch (C ABI, host buffers)"},
            "gpu_launches": launches_per_step * args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
            "gso_run": gso}
+    if world == 1 and not args.no_single_swarm_runs:
+        out["single_swarm_runs"] = single_swarm_runs(dc_dir)
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# README.md:27-147 of the reference: whole-run wall clock, 1 swarm x 200 glowworms x 100 steps, one M3 Pro core
+README_M3_SECONDS = {"1k4c": 112.132, "1ppe": 4.252, "2uuy": 8.108, "1czy": 1.580, "1azp": 14.228}
+
+
+def single_swarm_runs(dc_dir):
+    """BASELINE configs 0-3 as a reference user runs them: the drop-in CLI, one swarm, 100 steps, whole-process wall
+    clock (CUDA start-up, model building and the 11 output files included), next to the README's M3 Pro times."""
+    import shutil
+    from ldb200 import host
+    golden = os.path.join(ROOT, "tests", "golden")
+    out = {}
+    # the first entry runs twice: the first process of a fresh box pays one-off costs (driver / page cache)
+    for k, (name, method) in enumerate((("1czy", "dfire"), ("1czy", "dfire"), ("1ppe", "dfire"), ("2uuy", "dfire"),
+                                        ("1azp", "dna"), ("1k4c", "dfire"))):
+        g = os.path.join(golden, name)
+        start = os.path.join(g, "initial_positions_0.dat")
+        if not os.path.exists(start):
+            start = os.path.join(g, "init", "initial_positions_0.dat")
+        with tempfile.TemporaryDirectory() as tmp:
+            for f in ("rec_nm.npy", "lig_nm.npy"):
+                if os.path.exists(os.path.join(g, f)):
+                    shutil.copy(os.path.join(g, f), os.path.join(tmp, f))
+            env = dict(os.environ, LIGHTDOCK_DATA=dc_dir)
+            t = time.perf_counter()
+            r = subprocess.run([host.CLI_PATH, os.path.join(g, "setup.json"), start, "100", method], cwd=tmp, env=env,
+                               capture_output=True, text=True)
+            dt = time.perf_counter() - t
+            ok = r.returncode == 0 and os.path.exists(os.path.join(tmp, "swarm_0", "gso_100.out"))
+        if k == 0:
+            continue
+        out[name] = {"method": method, "wall_s": dt if ok else None, "readme_m3pro_1core_wall_s": README_M3_SECONDS[name]}
+    return out
 
 
 def main():
@@ -398,6 +434,8 @@ def main():
     ap.add_argument("--glowworms", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-swarm-runs", action="store_true",
+                    help="skip the five 100-step single-swarm CLI runs (BASELINE configs 0-3) reported at N=1")
     ap.add_argument("--gso-steps", type=int, default=20, help="steps of the real GSO loop for the gso_run figure (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
