@@ -280,7 +280,8 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   if (cx.n_rec == 0 || cx.n_lig == 0) { h->rigid_info = "rigid path off: empty partner"; return LD_OK; }
   if (cx.n_lig_tiles > 65535) { h->rigid_info = "rigid path off: ligand tile ids exceed 16 bits"; return LD_OK; }
   const long avail = (long)h->max_smem_optin - (long)rigid_smem_bytes(cx.n_lig_pad, 0);
-  const int rows_max = (int)std::min<long>(RG_MAX_ROWS, avail / RG_ROW_BYTES);
+  int rows_max = (int)std::min<long>(RG_MAX_ROWS, avail / RG_ROW_BYTES);
+  if (const char *e = getenv("LDB200_ROWS")) rows_max = std::max(1, std::min(rows_max, atoi(e)));  // tuning aid
   if (rows_max < 1) { h->rigid_info = "rigid path off: ligand + one table row exceed shared memory"; return LD_OK; }
 
   RigidComplex &rc = h->rc;
