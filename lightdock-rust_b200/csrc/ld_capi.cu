@@ -89,6 +89,7 @@ struct ld_handle {
   int max_smem_optin = 0;
   int sm_count = 0;
   bool profiling = false;
+  bool prof_continue = false;  // second part of a two-part call: keep the first part's profiling events
 };
 
 template <typename T>
@@ -738,7 +739,7 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
   h->w->stats = ld_batch_stats{};
   h->w->stats.n_poses = n;
   h->w->stats.pair_evals_bruteforce = n * (int64_t)cx.n_rec * (int64_t)cx.n_lig;
-  h->w->prof_used = 0;
+  if (!h->prof_continue) h->w->prof_used = 0;
   h->w->last_stream = st;
   if (n == 0) return LD_OK;
   const int64_t climit = chunk_limit(h, use_rigid(h));
@@ -895,9 +896,28 @@ static int score_host(ld_handle *h, int64_t n, const double *poses, double *ener
   int rc;
   if ((rc = ensure_poses(h, n, want_detail)) != LD_OK) return rc;
   const size_t pose_bytes = (size_t)n * cx.pose_len * sizeof(double);
-  std::memcpy(h->w->h_poses, poses, pose_bytes);
+  // Large plain batches go in two parts so that staging the bulk of the pose rows into pinned memory overlaps the
+  // kernels of a small first part instead of preceding all device work (the two parts are ordinary sub-batches:
+  // results do not depend on the split).
+  const int64_t n_head = (!want_detail && n >= 65536) ? n / 8 : 0;  // smaller batches: a second launch costs more
+  ld_batch_stats head_stats{};
   CU(cudaEventRecord(h->w->ev0, h->w->stream));
-  CU(cudaMemcpyAsync(h->w->d_poses, h->w->h_poses, pose_bytes, cudaMemcpyHostToDevice, h->w->stream));
+  if (n_head > 0) {
+    const size_t head_bytes = (size_t)n_head * cx.pose_len * sizeof(double);
+    std::memcpy(h->w->h_poses, poses, head_bytes);
+    CU(cudaMemcpyAsync(h->w->d_poses, h->w->h_poses, head_bytes, cudaMemcpyHostToDevice, h->w->stream));
+    if ((rc = run_device(h, n_head, h->w->d_poses, h->w->d_energies, h->w->stream, nullptr, nullptr, nullptr)) != LD_OK)
+      return rc;
+    head_stats = h->w->stats;
+    std::memcpy(reinterpret_cast<char *>(h->w->h_poses) + head_bytes, reinterpret_cast<const char *>(poses) + head_bytes,
+                pose_bytes - head_bytes);
+    CU(cudaMemcpyAsync(reinterpret_cast<char *>(h->w->d_poses) + head_bytes,
+                       reinterpret_cast<char *>(h->w->h_poses) + head_bytes, pose_bytes - head_bytes,
+                       cudaMemcpyHostToDevice, h->w->stream));
+  } else {
+    std::memcpy(h->w->h_poses, poses, pose_bytes);
+    CU(cudaMemcpyAsync(h->w->d_poses, h->w->h_poses, pose_bytes, cudaMemcpyHostToDevice, h->w->stream));
+  }
   if (want_detail) CU(cudaMemsetAsync(h->w->d_detail, 0, (size_t)n * sizeof(ld_pose_detail), h->w->stream));
   const int lig_words = (cx.n_lig_pad + 31) / 32;
   std::vector<unsigned> ifr, ifl;
@@ -908,9 +928,17 @@ static int score_host(ld_handle *h, int64_t n, const double *poses, double *ener
     ifr.assign((size_t)n * std::max(1, rec_tiles), 0u);
     ifl.assign((size_t)n * std::max(1, lig_words), 0u);
   }
-  rc = run_device(h, n, h->w->d_poses, h->w->d_energies, h->w->stream, want_detail ? h->w->d_detail : nullptr,
-                  want_iface ? &ifr : nullptr, want_iface ? &ifl : nullptr);
+  h->prof_continue = n_head > 0;
+  rc = run_device(h, n - n_head, h->w->d_poses + (size_t)n_head * cx.pose_len, h->w->d_energies + n_head, h->w->stream,
+                  want_detail ? h->w->d_detail : nullptr, want_iface ? &ifr : nullptr, want_iface ? &ifl : nullptr);
+  h->prof_continue = false;
   if (rc != LD_OK) return rc;
+  if (n_head > 0) {  // the call's counters cover both parts
+    h->w->stats.n_poses += head_stats.n_poses;
+    h->w->stats.pair_evals_bruteforce += head_stats.pair_evals_bruteforce;
+    h->w->stats.kernel_launches += head_stats.kernel_launches;
+    h->w->stats.pair_launches += head_stats.pair_launches;
+  }
   CU(cudaMemcpyAsync(h->w->h_energies, h->w->d_energies, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->w->stream));
   if (want_detail)
     CU(cudaMemcpyAsync(detail, h->w->d_detail, (size_t)n * sizeof(ld_pose_detail), cudaMemcpyDeviceToHost, h->w->stream));
