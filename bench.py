@@ -272,6 +272,7 @@ def run_b200(args, rank, world, local_rank):
     if args.gso_steps > 0:
         threads = max(1, min(32, host_cores() // world))
         seeds = np.full(len(mine), 324324, dtype=np.uint64)  # every swarm is seeded like a stand-alone reference process
+        case.multi_gso(all_poses[mine], seeds, 1, host_threads=threads)  # warm-up: sizes both slots' buffers
         barrier()
         t0 = time.perf_counter()
         _, calls = case.multi_gso(all_poses[mine], seeds, args.gso_steps, host_threads=threads)
