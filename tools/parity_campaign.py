@@ -55,3 +55,22 @@ for name in ("1k4c", "1ppe"):
 print(f"OK: {total_pairs:,} in-cut-off pair classifications identical between the rigid and the generic kernel; "
       f"exact-path pairs rigid {total_fallback[0]:,} / generic {total_fallback[1]:,}; largest energy difference "
       f"{worst:.1e} of the summed magnitude; {time.time() - t0:.0f} s")
+
+# ---- second leg: the rigid kernel against the CPU oracle (energies only, all host cores) --------------------------
+ncores = len(os.sched_getaffinity(0))
+for name, n in (("1ppe", 60000), ("1k4c", 12000)):
+    cx, pos, _ = case(name, O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    sc.set_path(ldb200.PATH_RIGID)
+    rng = np.random.default_rng(77)
+    poses = np.vstack([random_poses(rng, n // 2, 7, centre=cx.rec.coords.mean(axis=0), spread=14.0),
+                       np.tile(pos, (n // 2 // len(pos) + 1, 1))[:n // 2] + np.concatenate(
+                           [rng.normal(0, 1.5, size=(n // 2, 3)), np.zeros((n // 2, 4))], axis=1)])
+    t = time.time()
+    e_ref = cx.energy_mt(poses, ncores)
+    dt = time.time() - t
+    e_gpu = sc.energy(poses)
+    # tolerance of the north star: 1e-6 relative; scores that cancel to ~0 are judged against the sum's size
+    err = np.abs(e_gpu - e_ref) / np.maximum(np.abs(e_ref), 1.0)
+    assert err.max() < 1e-9, err.max()
+    print(f"{name}: {n} poses, rigid kernel vs oracle ({ncores} threads, {dt:.0f} s): max |dE|/max(|E|,1) = {err.max():.1e}", flush=True)
