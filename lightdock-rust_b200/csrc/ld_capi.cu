@@ -493,6 +493,54 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
                               LIG_TILE, LIG_PAD, nlm);
   h->rec_perm = R.perm;
   h->lig_perm = L.perm;
+  // DNA/pyDock: sqrt(eps_r * eps_l) (src/dna.rs:496) as sqrt(eps_r) * sqrt(eps_l) with the roots taken once here;
+  // a negative vdw energy keeps the reference's form (the product of two negatives has a real root)
+  // DNA/pyDock van der Waals term by type pair: ve (p6^2 - 2 p6) = x6 (A x6 - B) with x6 = 1/d^6,
+  // A = sqrt(e_r e_l) (r_r + r_l)^12, B = 2 sqrt(e_r e_l) (r_r + r_l)^6 (src/dna.rs:495-499), tabulated over the distinct
+  // (energy, radius) pairs of each partner; built from the caller's values before the roots are taken below
+  std::vector<double2> vdw_tab;
+  std::vector<int> rec_vt(R.n_pad, 0), lig_vt(L.n_pad, 0);
+  int vdw_nr = 0, vdw_nl = 0;
+  if (method != 0) {
+    std::vector<std::pair<double, double>> tr, tl;
+    auto type_of = [](std::vector<std::pair<double, double>> &types, double e, double r) {
+      for (size_t k = 0; k < types.size(); ++k)
+        if (types[k].first == e && types[k].second == r) return (int)k;
+      types.emplace_back(e, r);
+      return (int)types.size() - 1;
+    };
+    bool ok = true;
+    for (int i = 0; i < R.n && ok; ++i) { rec_vt[i] = type_of(tr, R.eps[i], R.rad[i]); ok = tr.size() <= 1024; }
+    for (int j = 0; j < L.n && ok; ++j) { lig_vt[j] = type_of(tl, L.eps[j], L.rad[j]); ok = tl.size() <= 1024; }
+    if (ok && !tr.empty() && !tl.empty() && tr.size() * tl.size() <= 1024) {
+      vdw_nr = (int)tr.size(); vdw_nl = (int)tl.size();
+      vdw_tab.resize((size_t)vdw_nr * vdw_nl);
+      for (int b = 0; b < vdw_nl; ++b)
+        for (int a = 0; a < vdw_nr; ++a) {
+          const double ve = std::sqrt(tr[a].first * tl[b].first), vr = tr[a].second + tl[b].second;
+          const double vr2 = vr * vr, vr6 = vr2 * (vr2 * vr2);
+          vdw_tab[(size_t)b * vdw_nr + a] = make_double2(ve * vr6 * vr6, 2.0 * ve * vr6);
+        }
+      for (int &v : rec_vt) v *= 16;
+      for (int &v : lig_vt) v *= vdw_nr * 16;
+    }
+  }
+  bool eps_nonneg = true;
+  for (double v : R.eps) eps_nonneg = eps_nonneg && v >= 0.0;
+  for (double v : L.eps) eps_nonneg = eps_nonneg && v >= 0.0;
+  if (eps_nonneg) {
+    for (double &v : R.eps) v = std::sqrt(v);
+    for (double &v : L.eps) v = std::sqrt(v);
+  }
+  h->cx.vdw_sqrt_hoisted = eps_nonneg ? 1 : 0;
+  {
+    // a tile pair further apart than this holds no vdW / interface pair (10 A) and no Coulomb term that reaches the
+    // +-4/332 clamp: |q_r q_l| / d2 > C needs d2 < 83 |q_r| |q_l| (the 1.001 covers the 1e-12 error of the kernel's quotient)
+    double qr = 0.0, ql = 0.0;
+    for (double v : R.q) qr = std::max(qr, std::fabs(v));
+    for (double v : L.q) ql = std::max(ql, std::fabs(v));
+    h->cx.dna_close_reach = (float)(std::max(10.0, std::sqrt(83.0 * 1.001 * qr * ql)) * 1.0001 + 1e-3);
+  }
   h->rec_xyz_orig.assign(desc->receptor.coords, desc->receptor.coords + (size_t)3 * desc->receptor.n_atoms);
 
   DeviceComplex &cx = h->cx;
@@ -506,11 +554,13 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
 #define UP(vec, field) \
   if ((rc = upload(h, vec, &cx.field)) != LD_OK) return rc
   UP(R.x, rec_x); UP(R.y, rec_y); UP(R.z, rec_z);
-  UP(R.toff, rec_toff); UP(R.q, rec_q); UP(R.eps, rec_eps); UP(R.rad, rec_rad); UP(R.modes, rec_modes);
+  UP(R.toff, rec_toff); UP(R.q, rec_q); UP(R.eps, rec_seps); UP(R.rad, rec_rad); UP(R.modes, rec_modes);
   UP(L.x, lig_x); UP(L.y, lig_y); UP(L.z, lig_z);
-  UP(L.tb20, lig_tb20); UP(L.q, lig_q); UP(L.eps, lig_eps); UP(L.rad, lig_rad); UP(L.modes, lig_modes);
+  UP(L.tb20, lig_tb20); UP(L.q, lig_q); UP(L.eps, lig_seps); UP(L.rad, lig_rad); UP(L.modes, lig_modes);
   UP(R.rst_off, rec_rst_off); UP(R.rst_idx, rec_rst_idx); UP(L.rst_off, lig_rst_off); UP(L.rst_idx, lig_rst_idx);
   UP(R.mem_idx, membrane_idx);
+  cx.vdw_nr = vdw_nr; cx.vdw_nl = vdw_nl;
+  if (!vdw_tab.empty()) { UP(vdw_tab, vdw_tab); UP(rec_vt, rec_vt); UP(lig_vt, lig_vt); }
   cx.n_rec_rst = desc->receptor.n_restraints;
   cx.n_lig_rst = desc->ligand.n_restraints;
   cx.n_membrane = desc->receptor.n_membrane;
@@ -544,20 +594,22 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
     UP(rowx, rec_rowx);
   }
 #undef UP
-  h->lig_block = lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  h->lig_block = lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles, cx.method);
   h->rec_block = nrm > 0 ? rec_block_bytes(cx.n_rec_pad, cx.n_rec_tiles) : 0;
   if (h->lig_block >= (1u << 20)) return fail(LD_ELIMIT, "ligand too large for one bulk copy");
 
   // the pair kernels need opt-in dynamic shared memory; check the worst case (one split) fits
   const int lig_words = (cx.n_lig_pad + 31) / 32;
-  const size_t need = pair_smem_bytes(method, cx.n_lig_pad, cx.n_lig_tiles, lig_words, cx.n_rec_tiles);
+  const size_t need = pair_smem_bytes(method, cx.n_lig_pad, cx.n_lig_tiles, lig_words, cx.n_rec_tiles, cx.vdw_nr * cx.vdw_nl);
   if (need > (size_t)h->max_smem_optin)
     return fail(LD_ELIMIT, "ligand of " + std::to_string(cx.n_lig) + " atoms needs " + std::to_string(need) +
                                " B of shared memory per CTA; limit is " + std::to_string(h->max_smem_optin));
   CU(cudaFuncSetAttribute(dfire_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CU(cudaFuncSetAttribute(dfire_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CU(cudaFuncSetAttribute(dna_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CU(cudaFuncSetAttribute(dna_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CU(cudaFuncSetAttribute(dna_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CU(cudaFuncSetAttribute(dna_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CU(cudaFuncSetAttribute(dna_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  CU(cudaFuncSetAttribute(dna_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   if (const char *e = getenv("LDB200_PATH")) {  // benchmarking aid; ld_set_path() is the API
     if (!strcmp(e, "generic")) h->path_mode = LD_PATH_GENERIC;
   }
@@ -662,7 +714,7 @@ static int choose_splits(const ld_handle *h, int64_t n) {
   if (h->forced_splits > 0) return std::min(h->forced_splits, tiles);
   const bool dna = h->cx.method != 0;
   const int warps = (dna ? DNA_THREADS : PAIR_THREADS) / 32;
-  const int64_t resident = (int64_t)h->sm_count * (dna ? 1024 / DNA_THREADS : 2);
+  const int64_t resident = (int64_t)h->sm_count * (dna ? DNA_CTAS_PER_SM : 2);
   if (n >= 2 * resident) return 1;
   double best = 1e300;
   int best_s = 1;
@@ -829,14 +881,17 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
     ++launches;
     if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     if (cx.n_rec_tiles > 0) {
-      const size_t smem = pair_smem_bytes(cx.method, cx.n_lig_pad, cx.n_lig_tiles, lig_words, bb.tiles_per_split);
+      const size_t smem = pair_smem_bytes(cx.method, cx.n_lig_pad, cx.n_lig_tiles, lig_words, bb.tiles_per_split, cx.vdw_nr * cx.vdw_nl);
       const unsigned grid = (unsigned)(nc * splits);
       if (cx.method == 0) {
         if (detail) dfire_pair_kernel<true><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
         else dfire_pair_kernel<false><<<grid, PAIR_THREADS, smem, st>>>(cx, bb, (int)nc);
       } else {
-        if (detail) dna_pair_kernel<true><<<grid, DNA_THREADS, smem, st>>>(cx, bb, (int)nc);
-        else dna_pair_kernel<false><<<grid, DNA_THREADS, smem, st>>>(cx, bb, (int)nc);
+        const bool tab = cx.vdw_tab != nullptr;
+        if (detail && tab) dna_pair_kernel<true, true><<<grid, DNA_THREADS, smem, st>>>(cx, bb, (int)nc);
+        else if (detail) dna_pair_kernel<true, false><<<grid, DNA_THREADS, smem, st>>>(cx, bb, (int)nc);
+        else if (tab) dna_pair_kernel<false, true><<<grid, DNA_THREADS, smem, st>>>(cx, bb, (int)nc);
+        else dna_pair_kernel<false, false><<<grid, DNA_THREADS, smem, st>>>(cx, bb, (int)nc);
       }
       ++launches;
       ++pair_launches;

@@ -10,12 +10,13 @@
 //   DFIRE potential: 571,220 f64 (4.57 MB) — stays resident in the 126 MB L2.
 // Per batch: one "ligand block" per pose written by the transform kernel (16-byte aligned, contiguous):
 //     [x f64][y f64][z f64]  exact transformed coordinates (n_lig_pad each)
-//     [float4 xyzt]          the same coordinates rounded to f32 + the DFIRE column offset (type*20) as int bits
+//     [float4 xyzt]          DFIRE: the same coordinates rounded to f32 + the table column offset (type * RG_SLOTS) as a float
+//     [double4 xyzq]         DNA/pyDock instead: the exact coordinates + the atom's charge, interleaved per atom
 //     [float4 sphere]        one conservative bounding sphere per ligand tile
 //     [float4 meta]          meta.x = max |coordinate| of the pose's ligand (sets the rigorous f32 margins)
 //   The pair kernels pull the part they need into shared memory with cp.async.bulk (TMA) copies:
 //   DFIRE takes [xyzt|sphere|meta] (its f64 coordinates are touched only by the rare exact fallback, from
-//   L2), DNA takes [x|y|z] and [sphere|meta].  A "receptor block" ([x][y][z][sphere][meta]) exists per
+//   L2), DNA takes [xyzq|sphere|meta].  A "receptor block" ([x][y][z][sphere][meta]) exists per
 //   pose only when receptor ANM is active.
 #pragma once
 #include <cuda_runtime.h>
@@ -29,6 +30,11 @@ constexpr int PAIR_THREADS = 512;  // generic DFIRE pair kernel
 #ifndef LDB200_DNA_THREADS
 #define LDB200_DNA_THREADS 256
 #endif
+#ifndef LDB200_DNA_CTAS
+#define LDB200_DNA_CTAS 4
+#endif
+constexpr int DNA_CTAS_PER_SM = LDB200_DNA_CTAS;  // measured on 1azp (20,000 poses): 4 x 256 threads (64 registers, a few
+                                                  // spilled words) 11.6 ms, 3 x 256 (80 registers) 12.6 ms, 2 x 256 (126) 12.0 ms
 constexpr int DNA_THREADS = LDB200_DNA_THREADS;  // DNA/pyDock pair kernel: small complexes (1azp: 35 receptor tiles), so
                                                  // smaller CTAs (more per SM) balance the tiles over the warps better
 constexpr int DFIRE_ROW = 169 * 20;  // src/dfire.rs:338  atoma*169*20
@@ -60,14 +66,22 @@ struct DeviceComplex {
   const int *rec_toff;                      // DFIRE: type * 3380 (exact path)
   const unsigned *rec_rowx;                 // DFIRE: type * (RG_ROW_BYTES/8) - RG_SLOT0 - RG_MAGIC_BITS (mod 2^32): element
                                             // index into potx = bits(m + w) + rec_rowx, see dfire_items()
-  const double *rec_q, *rec_eps, *rec_rad;  // DNA
+  const double *rec_q, *rec_seps, *rec_rad;  // DNA: charge, sqrt(vdw energy) (the energy itself if !vdw_sqrt_hoisted), radius
+  // DNA: van der Waals (A, B) = (sqrt(e_r e_l) (r_r + r_l)^12, 2 sqrt(e_r e_l) (r_r + r_l)^6) per pair of distinct
+  // (energy, radius) types, [vdw_nl][vdw_nr]; nullptr when there are more than 1024 pairs (the kernel then evaluates
+  // the term from the per-atom parameters); rec_vt = type * 16, lig_vt = type * vdw_nr * 16 (byte offsets)
+  const double2 *vdw_tab;
+  const int *rec_vt, *lig_vt;
+  int vdw_nr, vdw_nl;
+  float dna_close_reach;                    // DNA: max(10 A, largest distance at which q_r q_l / d2 can reach the +-4/332 clamp)
+  int vdw_sqrt_hoisted;                     // DNA: 1 = *_seps hold square roots (every vdw energy >= 0)
   const float4 *rec_sphere;                 // static tile spheres (used when n_rec_modes == 0)
   float rec_maxabs;                         // max |coordinate| of the static receptor
   const double *rec_modes;                  // [k][3][n_rec_pad]
   // ligand (sorted order, local frame)
   const double *lig_x, *lig_y, *lig_z;
   const unsigned short *lig_tb20;           // DFIRE: type * 20
-  const double *lig_q, *lig_eps, *lig_rad;  // DNA
+  const double *lig_q, *lig_seps, *lig_rad;  // DNA
   const double *lig_modes;                  // [k][3][n_lig_pad]
   const double *pot;                        // DFIRE table as the reference indexes it
   const double *potx;                       // [169][RG_ROW_BYTES/8]: row ta = [tb][RG_SLOTS], slot s <-> idx s + RG_SLOT0
@@ -76,11 +90,17 @@ struct DeviceComplex {
   const int *rec_rst_off, *rec_rst_idx, *lig_rst_off, *lig_rst_idx, *membrane_idx;
 };
 
-// byte offsets inside one ligand block
+// byte offsets inside one ligand block; `wide` = bytes per atom of the staged part: 16 for DFIRE (float4 x,y,z,type
+// offset), 32 for DNA/pyDock (double x,y | z,charge: the pair loop reads an atom with two broadcast LDS.128)
+__host__ __device__ inline int lig_wide(int method) { return method == 0 ? 16 : 32; }
 __host__ __device__ inline size_t lig_off_f4(int n_pad) { return (size_t)n_pad * 24; }
-__host__ __device__ inline size_t lig_off_sph(int n_pad) { return (size_t)n_pad * 40; }
-__host__ __device__ inline size_t lig_off_meta(int n_pad, int n_tiles) { return (size_t)n_pad * 40 + (size_t)n_tiles * 16; }
-__host__ __device__ inline size_t lig_block_bytes(int n_pad, int n_tiles) { return lig_off_meta(n_pad, n_tiles) + 16; }
+__host__ __device__ inline size_t lig_off_sph(int n_pad, int method) { return (size_t)n_pad * (24 + lig_wide(method)); }
+__host__ __device__ inline size_t lig_off_meta(int n_pad, int n_tiles, int method) {
+  return lig_off_sph(n_pad, method) + (size_t)n_tiles * 16;
+}
+__host__ __device__ inline size_t lig_block_bytes(int n_pad, int n_tiles, int method) {
+  return lig_off_meta(n_pad, n_tiles, method) + 16;
+}
 // receptor block (ANM only): x,y,z f64 [n_pad], float4 spheres [n_tiles], float4 meta
 __host__ __device__ inline size_t rec_block_bytes(int n_pad, int n_tiles) {
   return (size_t)n_pad * 24 + (size_t)n_tiles * 16 + 16;

@@ -125,11 +125,12 @@ __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, 
   const double *rec_ext = pose + 7;
   const double *lig_ext = pose + 7 + cx.n_rec_modes;
 
-  unsigned char *lb = bb.lig_blocks + (size_t)p * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  unsigned char *lb = bb.lig_blocks + (size_t)p * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles, cx.method);
   double *ox = reinterpret_cast<double *>(lb), *oy = ox + cx.n_lig_pad, *oz = oy + cx.n_lig_pad;
-  float4 *of4 = reinterpret_cast<float4 *>(lb + lig_off_f4(cx.n_lig_pad));
-  float4 *osph = reinterpret_cast<float4 *>(lb + lig_off_sph(cx.n_lig_pad));
-  float4 *ometa = reinterpret_cast<float4 *>(lb + lig_off_meta(cx.n_lig_pad, cx.n_lig_tiles));
+  float4 *of4 = reinterpret_cast<float4 *>(lb + lig_off_f4(cx.n_lig_pad));    // DFIRE
+  double2 *od4 = reinterpret_cast<double2 *>(lb + lig_off_f4(cx.n_lig_pad));  // DNA/pyDock
+  float4 *osph = reinterpret_cast<float4 *>(lb + lig_off_sph(cx.n_lig_pad, cx.method));
+  float4 *ometa = reinterpret_cast<float4 *>(lb + lig_off_meta(cx.n_lig_pad, cx.n_lig_tiles, cx.method));
   float lmax = 0.f, rmax = 0.f;
   for (int i = threadIdx.x; i < cx.n_lig_pad; i += blockDim.x) {
     double x = LIG_PAD, y = LIG_PAD, z = LIG_PAD;
@@ -152,7 +153,12 @@ __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, 
       if (cx.method == 0) tw = (float)((cx.lig_tb20[i] / 20) * RG_SLOTS);
     }
     ox[i] = x; oy[i] = y; oz[i] = z;
-    of4[i] = make_float4((float)x, (float)y, (float)z, tw);
+    if (cx.method == 0) {
+      of4[i] = make_float4((float)x, (float)y, (float)z, tw);
+    } else {
+      od4[2 * i] = make_double2(x, y);
+      od4[2 * i + 1] = make_double2(z, cx.lig_q[i]);  // pads carry charge 0
+    }
   }
   double *rx = nullptr, *ry = nullptr, *rz = nullptr;
   float4 *rsph = nullptr, *rmeta = nullptr;
@@ -201,9 +207,10 @@ __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, 
 // ---------------------------------------------------------------------------------------------
 // shared-memory carve-up of the pair kernels
 //   [0,8) mbarrier | [8,12) next-tile counter | [16,48) 4 u64 detail counters | [48,144) 24 u32 histogram
-//   [144, ...)   TMA destination(s): DFIRE float4 xyzt[n_lig_pad] + spheres + meta ; DNA x,y,z f64 + spheres + meta
-//   DNA only:    ligand charge / eps / radius (f64 each)
+//   [144, ...)   TMA destination: DFIRE float4 xyzt[n_lig_pad] + spheres + meta ; DNA double4 xyzq[n_lig_pad] + same
+//   DNA only:    ligand sqrt(eps) / radius (f64 each)
 //   iface_lig bitmap | per-tile sums | DFIRE: per-warp work-item rings (64 u32 each)
+//   DNA only:    van der Waals (A, B) table [lig types][rec types] (double2) + per ligand atom row offset (bytes)
 struct PairSmem {
   uint64_t *bar;
   int *next_tile;
@@ -211,28 +218,31 @@ struct PairSmem {
   unsigned *hist;                // detail: 21 bins (+pad)
   unsigned char *tma;            // start of the TMA-filled region
   const float4 *l4;              // DFIRE: f32 coordinates + type*20 bits
-  const double *lx, *ly, *lz;    // DNA: exact coordinates
+  const double *lxyzq;           // DNA: exact coordinates + charge, {x, y, z, q} per atom
   const float4 *lsph;
   const float4 *lmeta;
-  double *lig_static;            // DNA: q, eps, rad
+  double *lig_static;            // DNA: sqrt(eps) (or eps), rad
   unsigned *iface_lig;           // [lig_words]
   double *tile_sum;              // [tiles_per_split] (x2 for DNA)
   unsigned *rings;               // DFIRE: [warps][64]
+  const unsigned char *vtab;     // DNA: (A, B) pairs, row = ligand type, column = receptor type
+  const int *lig_vt;             // DNA: [n_lig_pad] byte offset of the atom's row in vtab
 };
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 constexpr int RING = 64;
 __host__ __device__ inline size_t pair_smem_bytes(int method, int n_lig_pad, int n_lig_tiles, int lig_words,
-                                                  int tiles_per_split) {
+                                                  int tiles_per_split, int vdw_pairs) {
   size_t o = 144;
   if (method == 0) {
     o += (size_t)n_lig_pad * 16 + (size_t)n_lig_tiles * 16 + 16;
   } else {
-    o += (size_t)n_lig_pad * 24 + (size_t)n_lig_tiles * 16 + 16;
-    o += (size_t)n_lig_pad * 24;
+    o += (size_t)n_lig_pad * 32 + (size_t)n_lig_tiles * 16 + 16;
+    o += (size_t)n_lig_pad * 16;
   }
   o += align16((size_t)lig_words * 4);
   o += align16((size_t)tiles_per_split * 8 * (method == 0 ? 1 : 2));
   if (method == 0) o += (size_t)(PAIR_THREADS / 32) * RING * 4;  // work-item rings
+  else o += (size_t)vdw_pairs * 16 + align16((size_t)n_lig_pad * 4);
   return o;
 }
 __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceComplex &cx, const BatchBuffers &bb) {
@@ -243,15 +253,13 @@ __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceCompl
   s.hist = reinterpret_cast<unsigned *>(base + 48);
   unsigned char *o = base + 144;
   s.tma = o;
-  s.l4 = nullptr; s.lx = s.ly = s.lz = nullptr; s.lig_static = nullptr; s.rings = nullptr;
+  s.l4 = nullptr; s.lxyzq = nullptr; s.lig_static = nullptr; s.rings = nullptr; s.vtab = nullptr; s.lig_vt = nullptr;
   if (cx.method == 0) {
     s.l4 = reinterpret_cast<const float4 *>(o);
     o += (size_t)cx.n_lig_pad * 16;
   } else {
-    s.lx = reinterpret_cast<const double *>(o);
-    s.ly = s.lx + cx.n_lig_pad;
-    s.lz = s.ly + cx.n_lig_pad;
-    o += (size_t)cx.n_lig_pad * 24;
+    s.lxyzq = reinterpret_cast<const double *>(o);
+    o += (size_t)cx.n_lig_pad * 32;
   }
   s.lsph = reinterpret_cast<const float4 *>(o);
   o += (size_t)cx.n_lig_tiles * 16;
@@ -259,13 +267,19 @@ __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceCompl
   o += 16;
   if (cx.method != 0) {
     s.lig_static = reinterpret_cast<double *>(o);
-    o += (size_t)cx.n_lig_pad * 24;
+    o += (size_t)cx.n_lig_pad * 16;
   }
   s.iface_lig = reinterpret_cast<unsigned *>(o);
   o += align16((size_t)bb.lig_words * 4);
   s.tile_sum = reinterpret_cast<double *>(o);
   o += align16((size_t)bb.tiles_per_split * 8 * (cx.method == 0 ? 1 : 2));
-  if (cx.method == 0) s.rings = reinterpret_cast<unsigned *>(o);
+  if (cx.method == 0) {
+    s.rings = reinterpret_cast<unsigned *>(o);
+  } else {
+    s.vtab = o;
+    o += (size_t)cx.vdw_nr * cx.vdw_nl * 16;
+    s.lig_vt = reinterpret_cast<const int *>(o);
+  }
   return s;
 }
 
@@ -299,23 +313,22 @@ __device__ __forceinline__ void pair_prologue(const DeviceComplex &cx, const Bat
   }
   __syncthreads();
   if (tid == 0) {
-    const unsigned char *lb = bb.lig_blocks + (size_t)pose * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
-    const uint32_t tail = (uint32_t)(cx.n_lig_tiles * 16 + 16);  // spheres + meta
-    if (METHOD == 0) {
-      const uint32_t bytes = (uint32_t)cx.n_lig_pad * 16 + tail;
-      mbar_expect_tx(s.bar, bytes);
-      bulk_g2s(s.tma, lb + lig_off_f4(cx.n_lig_pad), bytes, s.bar);  // xyzt | spheres | meta are contiguous
-    } else {
-      const uint32_t xyz = (uint32_t)cx.n_lig_pad * 24;
-      mbar_expect_tx(s.bar, xyz + tail);
-      bulk_g2s(s.tma, lb, xyz, s.bar);
-      bulk_g2s(s.tma + xyz, lb + lig_off_sph(cx.n_lig_pad), tail, s.bar);
-    }
+    const unsigned char *lb = bb.lig_blocks + (size_t)pose * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles, cx.method);
+    // xyzt (DFIRE) or xyzq (DNA) | spheres | meta are contiguous: one bulk copy
+    const uint32_t bytes = (uint32_t)cx.n_lig_pad * (uint32_t)lig_wide(METHOD) + (uint32_t)(cx.n_lig_tiles * 16 + 16);
+    mbar_expect_tx(s.bar, bytes);
+    bulk_g2s(s.tma, lb + lig_off_f4(cx.n_lig_pad), bytes, s.bar);
   }
   if (METHOD != 0) {
-    double *lq = s.lig_static, *le = lq + cx.n_lig_pad, *lr = le + cx.n_lig_pad;
+    double *le = s.lig_static, *lr = le + cx.n_lig_pad;
     for (int i = tid; i < cx.n_lig_pad; i += blockDim.x) {
-      lq[i] = cx.lig_q[i]; le[i] = cx.lig_eps[i]; lr[i] = cx.lig_rad[i];
+      le[i] = cx.lig_seps[i]; lr[i] = cx.lig_rad[i];
+    }
+    if (cx.vdw_tab) {
+      double2 *vt = reinterpret_cast<double2 *>(const_cast<unsigned char *>(s.vtab));
+      for (int i = tid; i < cx.vdw_nr * cx.vdw_nl; i += blockDim.x) vt[i] = cx.vdw_tab[i];
+      int *lv = const_cast<int *>(s.lig_vt);
+      for (int i = tid; i < cx.n_lig_pad; i += blockDim.x) lv[i] = cx.lig_vt[i];
     }
   }
   for (int i = tid; i < bb.lig_words; i += blockDim.x) s.iface_lig[i] = 0u;
@@ -474,7 +487,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
 
   const int lane = threadIdx.x & 31;
   unsigned *ring = s.rings + (threadIdx.x >> 5) * RING;
-  const unsigned char *lb = bb.lig_blocks + (size_t)pose * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles);
+  const unsigned char *lb = bb.lig_blocks + (size_t)pose * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles, cx.method);
   const double *glx = reinterpret_cast<const double *>(lb), *gly = glx + cx.n_lig_pad, *glz = gly + cx.n_lig_pad;
   const double *gx = cx.rec_x, *gy = cx.rec_y, *gz = cx.rec_z;
   const float4 *gsph = cx.rec_sphere;
@@ -590,22 +603,226 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
 
 // ---------------------------------------------------------------------------------------------
 // Kernel 2b: DNA / pyDock pair loop, src/dna.rs:471-512 (= src/pydock.rs:486-527).
+//
+// The kernel is FP64-pipe bound (one warp instruction per 2 cycles per scheduler), so everything that does not have
+// to be an FP64 instruction is not one, and the eight pairs of a ligand tile are evaluated branch-free so their
+// dependency chains interleave:
+//   * d2 is evaluated with two FMAs (6 FP64 instructions instead of 8).  It differs from the reference's never-fused
+//     d2 by < 4 ulp, so a cut-off decision taken on it is the reference's unless d2 sits within a few ulp of the
+//     threshold.  The decisions are taken on the HIGH WORD of d2 with integer compares (ALU pipe): 900.0 and 100.0 are
+//     exactly representable in the high word (0x408C2000'00000000, 0x40590000'00000000), so hi < H-1 is surely
+//     inside and hi > H surely outside (4 ulp is 2^-30 of a high-word step); if any pair of the tile has one of the
+//     two high words around a threshold (|d2 - T| < 1e-3, about one pair in 10^6) the whole tile is redone by
+//     dna_tile_exact with the reference's own never-fused arithmetic and IEEE divides.  Same for 3.9*3.9 =
+//     0x402E6B85'1EB851EB with the single ambiguous high word 0x402E6B85.
+//     tests/test_gpu_parity.py::test_dna_decision_thresholds_exact drives pairs whose fused and unfused d2 fall on
+//     different sides of each threshold through this path.
+//   * The two quotients (Coulomb q1*q2/d2, van der Waals (r/d)^6) use the MUFU.RCP64H seed (rel. error < 2^-20) and
+//     ONE Newton step, x1 = x + x*(1 - d2*x): relative error < 1e-12.  They feed only continuous quantities (a sum,
+//     a clamp and a min whose two branches agree at the switch point), never a cut-off decision, so this stays 10^6
+//     below the 1e-6 tolerance.  The receptor charge is factored out of the tile loop: sum_j clamp(q_l/d2, +-C/|q_r|)
+//     is multiplied by q_r once per receptor tile (the clamp of q_r*q_l/d2 to +-C is the same set of pairs).
+//   * sqrt(eps_r*eps_l) (src/dna.rs:496) is sqrt(eps_r)*sqrt(eps_l) with the per-atom roots taken once by ld_create
+//     (continuous; 2 ulp); a complex with a negative eps keeps the reference's form (cx.vdw_sqrt_hoisted == 0).
+//   * the clamp is an integer compare on the bit patterns (order-preserving for same-sign doubles).
+//   * ligand tiles whose sphere is further than 10 A + radii from the receptor tile's cannot hold a van der Waals or
+//     interface pair: they run a loop instance without those tests (1azp: 9 of 10 tile pairs), so the divergent
+//     vdW branch is confined to the tile pairs that can take it.
 // powi(6)/powi(3) follow LLVM's repeated-squaring expansion (x^2, x^4, x^2*x^4 ; x*x^2).
-// Reciprocal for the two energy quotients (Coulomb q1*q2/d2, van der Waals (r/d)^6): MUFU.RCP64H seed + two
-// Newton steps in FMA (relative error < 4e-16).  The quotients feed only continuous quantities (a sum, a clamp and a
-// min whose two branches agree at the switch point), never a cut-off decision, so a last-ulp difference from the
-// reference's IEEE divide stays 1e-10 below the 1e-6 tolerance; the cut-off tests themselves use the exact,
-// never-fused d2.  Saves ~8 FP64-pipe instructions per quotient against __ddiv_rn.
-__device__ __forceinline__ double fast_rcp(double d) {
+__device__ __forceinline__ double rcp_seed(double d) {  // MUFU.RCP64H: relative error < 2^-20
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  x = fma(fma(-d, x, 1.0), x, x);
-  x = fma(fma(-d, x, 1.0), x, x);
   return x;
 }
+#ifndef LDB200_DNA_UNROLL
+#define LDB200_DNA_UNROLL 8
+#endif
+constexpr int DNA_UNROLL = LDB200_DNA_UNROLL;  // pairs of a ligand tile evaluated interleaved (8 or 4)
+constexpr unsigned DNA_HI_ELEC = 0x408C2000u;   // high word of 900.0 (low word 0)
+constexpr unsigned DNA_HI_VDW = 0x40590000u;    // high word of 100.0 (low word 0)
+constexpr unsigned DNA_HI_IFACE = 0x402E6B85u;  // high word of 3.9*3.9 = 15.209999999999999 (src/constants.rs:15)
+static_assert(3.9 * 3.9 == 15.209999999999999, "INTERFACE_CUTOFF2");
 
-template <bool DETAIL>
-__global__ void __launch_bounds__(DNA_THREADS, 1024 / DNA_THREADS)
+struct DnaLane {  // one receptor atom (one lane)
+  double x, y, z, q, se, rad;  // se = sqrt(eps) when hoisted, else eps
+  long long clamp_bits;        // bit pattern of ELEC_MAX_CUTOFF / |q|: the clamp in units of q_l / d2
+  int vt;                      // byte offset of the atom's van der Waals type inside a row of the (A, B) table
+};
+struct DnaAcc {
+  double e_l0, e_l1;  // sum of clamped q_l/d2 (to be multiplied by the lane's q_r)
+  double e_x;         // Coulomb terms of tiles redone exactly (already multiplied by q_r)
+  double v;           // van der Waals
+  unsigned n_e, n_v, n_if;
+  bool iface_r;
+};
+
+// The reference's arithmetic for the eight pairs of one tile: never fused, IEEE divide and square root
+// (src/dna.rs:471-512).  Rare (a pair within 1e-3 A^2 of a cut-off), so deliberately out of line.
+__device__ __noinline__ void dna_tile_exact(const double2 *__restrict__ a2, const double *__restrict__ s_se,
+                                            const double *__restrict__ s_rad, unsigned *iface_lig, bool hoisted,
+                                            const DnaLane *rp, int j0, DnaAcc *accp) {
+  const DnaLane &r = *rp;
+  DnaAcc &acc = *accp;
+  const double ELEC_MAX_CUTOFF = 1.0 * 4.0 / 332.0, ELEC_MIN_CUTOFF = -1.0 * 4.0 / 332.0;  // src/dna.rs:21-22
+  for (int jj = 0; jj < LIG_TILE; ++jj) {
+    const int j = j0 + jj;
+    const double2 xy = a2[2 * jj], zq = a2[2 * jj + 1];
+    const double dx = __dsub_rn(r.x, xy.x), dy = __dsub_rn(r.y, xy.y), dz = __dsub_rn(r.z, zq.x);
+    const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    if (d2 <= 900.0) {  // ELEC_DIST_CUTOFF2
+      double e = __ddiv_rn(__dmul_rn(r.q, zq.y), d2);
+      e = e > ELEC_MAX_CUTOFF ? ELEC_MAX_CUTOFF : e;
+      e = e < ELEC_MIN_CUTOFF ? ELEC_MIN_CUTOFF : e;
+      acc.e_x = __dadd_rn(acc.e_x, e);
+      ++acc.n_e;
+      if (d2 <= 100.0) {  // VDW_DIST_CUTOFF2
+        const double pe = __dmul_rn(r.se, s_se[j]);
+        const double ve = hoisted ? pe : __dsqrt_rn(pe);
+        const double vr = __dadd_rn(r.rad, s_rad[j]);
+        const double vr2 = __dmul_rn(vr, vr), vr4 = __dmul_rn(vr2, vr2), vr6 = __dmul_rn(vr2, vr4);
+        const double p6 = __ddiv_rn(vr6, __dmul_rn(d2, __dmul_rn(d2, d2)));
+        double k = __dmul_rn(ve, __dsub_rn(__dmul_rn(p6, p6), __dmul_rn(2.0, p6)));
+        k = k > 1.0 ? 1.0 : k;
+        acc.v = __dadd_rn(acc.v, k);
+        ++acc.n_v;
+        if (d2 <= 3.9 * 3.9) {  // INTERFACE_CUTOFF2
+          acc.iface_r = true;
+          atomicOr(&iface_lig[j >> 5], 1u << (j & 31));
+          ++acc.n_if;
+        }
+      }
+    }
+  }
+}
+
+// acc += t if hi < bound, as ONE predicated DADD (the compiler's own choice is an unconditional DADD + two selects)
+__device__ __forceinline__ void dadd_if_below(double &acc, double t, unsigned hi, unsigned bound) {
+  asm("{\n.reg .pred p;\nsetp.lt.u32 p, %2, %3;\n@p add.rn.f64 %0, %0, %1;\n}" : "+d"(acc) : "d"(t), "r"(hi), "r"(bound));
+}
+__device__ __forceinline__ void dfma_if_below(double &acc, double a, double b, unsigned hi, unsigned bound) {
+  asm("{\n.reg .pred p;\nsetp.lt.u32 p, %3, %4;\n@p fma.rn.f64 %0, %1, %2, %0;\n}" : "+d"(acc) : "d"(a), "d"(b), "r"(hi), "r"(bound));
+}
+
+// One ligand tile (8 atoms) against the lane's receptor atom.
+//   CLOSE == false: the tile pair is further apart than cx.dna_close_reach (>= 10 A) + radii: no van der Waals pair,
+//                   no interface pair, and no Coulomb term can reach the clamp (|q_r q_l| / d2 <= C there): the loop
+//                   is 9 FP64 instructions per pair and has no branch.
+//   CLOSE == true : clamp applied per term, and the van der Waals term
+//        TAB == true : evaluated branch-free for all eight pairs from a shared-memory table indexed by the pair's
+//                      (receptor, ligand) van der Waals types: with A = sqrt(e_r e_l) (r_r + r_l)^12 and
+//                      B = 2 sqrt(e_r e_l) (r_r + r_l)^6 (f64, ld_create), k = ve (p6^2 - 2 p6) = x6 (A x6 - B),
+//                      x6 = (1/d2)^3 from the reciprocal the Coulomb term already has: 5 FP64 instructions, no second
+//                      reciprocal, no divergence (the per-lane candidate loop ran max-over-lanes trips with a third of
+//                      the lanes active and cost more than the Coulomb part);
+//        TAB == false: (more than 1024 type pairs) candidates collected in a mask and evaluated by their own lane.
+template <bool CLOSE, bool DETAIL, bool TAB>
+__device__ __forceinline__ void dna_tile(const PairSmem &s, const double *__restrict__ s_se,
+                                         const double *__restrict__ s_rad, bool hoisted, const DnaLane &r, int j0,
+                                         DnaAcc &acc) {
+  const double2 *a2 = reinterpret_cast<const double2 *>(s.lxyzq) + 2 * j0;  // {x, y} {z, q} per ligand atom
+  double t0 = 0.0, t1 = 0.0, v0 = 0.0, v1 = 0.0;
+  unsigned kmin = 0xffffffffu, cnt = 0, cnt_v = 0;
+  unsigned vmask = 0u, imask = 0u, near_v = 0u;  // CLOSE: pairs inside 100.0 / inside 3.9^2 by their high word; any
+                                                 // pair with an ambiguous high word
+  const unsigned c_hi = (unsigned)(r.clamp_bits >> 32), c_lo = (unsigned)r.clamp_bits;
+#pragma unroll 1
+  for (int j4 = 0; j4 < LIG_TILE; j4 += DNA_UNROLL) {
+#pragma unroll
+  for (int ju = 0; ju < DNA_UNROLL; ++ju) {
+    const int jj = j4 + ju;
+    const double2 xy = a2[2 * jj], zq = a2[2 * jj + 1];
+    const double dx = __dsub_rn(r.x, xy.x), dy = __dsub_rn(r.y, xy.y), dz = __dsub_rn(r.z, zq.x);
+    const double d2 = fma(dz, dz, fma(dy, dy, __dmul_rn(dx, dx)));
+    const unsigned hi = (unsigned)__double2hiint(d2);
+    kmin = min(kmin, hi - (DNA_HI_ELEC - 1u));  // <= 1 iff hi is one of the two words around 900.0
+    const double x = rcp_seed(d2);
+    const double e1 = fma(-d2, x, 1.0);
+    const double x1 = fma(x, e1, x);
+    if (!CLOSE) {
+      dfma_if_below((ju & 1) ? t1 : t0, zq.y, x1, hi, DNA_HI_ELEC - 1u);
+    } else {
+      double t = __dmul_rn(zq.y, x1);
+      {  // clamp q_l/d2 to +-C/|q_r| (src/dna.rs:484-489 divided by |q_r|) on the bit patterns
+        const unsigned th = (unsigned)__double2hiint(t), ta = th & 0x7fffffffu, tl = (unsigned)__double2loint(t);
+        if (ta > c_hi || (ta == c_hi && tl > c_lo)) t = __hiloint2double((int)(c_hi | (th & 0x80000000u)), (int)c_lo);
+      }
+      dadd_if_below((ju & 1) ? t1 : t0, t, hi, DNA_HI_ELEC - 1u);
+      // the vdW / interface decisions are ambiguous on the high words around 100.0 and on the one holding 3.9*3.9
+      near_v |= (hi - (DNA_HI_VDW - 1u) <= 1u) | (hi == DNA_HI_IFACE);
+      if (TAB) {
+        const double2 ab = *reinterpret_cast<const double2 *>(s.vtab + r.vt + s.lig_vt[j0 + jj]);
+        const double x6 = __dmul_rn(__dmul_rn(x1, x1), x1);
+        double k = __dmul_rn(fma(ab.x, x6, -ab.y), x6);
+        if (__double2hiint(k) >= 0x3FF00000) k = 1.0;  // min(k, 1.0) (src/dna.rs:500-502) on the high word: k >= 1
+        dadd_if_below((ju & 1) ? v1 : v0, k, hi, DNA_HI_VDW - 1u);
+        imask |= (hi < DNA_HI_IFACE ? 1u : 0u) << jj;
+        if (DETAIL) cnt_v += hi < DNA_HI_VDW - 1u;
+      } else {
+        vmask |= (hi <= DNA_HI_VDW ? 1u : 0u) << jj;
+      }
+    }
+    if (DETAIL) cnt += hi < DNA_HI_ELEC - 1u;
+  }
+  }
+  if (kmin <= 1u || (CLOSE && near_v)) {  // ~1e-6 of the tiles: the reference's own arithmetic decides
+    DnaLane rc = r;  // copies: only this rare branch takes addresses, so r and acc stay in registers
+    DnaAcc ac = acc;
+    dna_tile_exact(a2, s_se, s_rad, s.iface_lig, hoisted, &rc, j0, &ac);
+    acc = ac;
+    vmask = 0u;
+    imask = 0u;
+  } else {
+    acc.e_l0 = __dadd_rn(acc.e_l0, t0);
+    acc.e_l1 = __dadd_rn(acc.e_l1, t1);
+    if (DETAIL) acc.n_e += cnt;
+    if (CLOSE && TAB) {
+      acc.v = __dadd_rn(acc.v, __dadd_rn(v0, v1));
+      if (DETAIL) acc.n_v += cnt_v;
+    }
+  }
+  if (CLOSE && TAB && imask) {  // rare: a contact inside 3.9 A (src/dna.rs:507-510)
+    acc.iface_r = true;
+    for (unsigned m = imask; m; m &= m - 1u) {
+      const int j = j0 + __ffs(m) - 1;
+      atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
+      if (DETAIL) ++acc.n_if;
+    }
+  }
+  if (CLOSE && !TAB) {
+    // the few pairs inside 10 A (no ambiguous high word among them: near_v == 0): src/dna.rs:494-510
+    for (unsigned m = vmask; m; m &= m - 1u) {
+      const int jj = __ffs(m) - 1, j = j0 + jj;
+      const double2 xy = a2[2 * jj], zq = a2[2 * jj + 1];
+      const double dx = __dsub_rn(r.x, xy.x), dy = __dsub_rn(r.y, xy.y), dz = __dsub_rn(r.z, zq.x);
+      const double d2 = fma(dz, dz, fma(dy, dy, __dmul_rn(dx, dx)));  // the same operations as above: the same bits
+      const double pe = __dmul_rn(r.se, s_se[j]);
+      const double ve = hoisted ? pe : __dsqrt_rn(pe);
+      const double vr = __dadd_rn(r.rad, s_rad[j]);
+      const double vr2 = __dmul_rn(vr, vr), vr4 = __dmul_rn(vr2, vr2);
+      const double vr6 = __dmul_rn(vr2, vr4);
+      const double d6 = __dmul_rn(d2, __dmul_rn(d2, d2));
+      const double x6 = rcp_seed(d6);
+      const double e6 = fma(-d6, x6, 1.0);
+      const double t6 = __dmul_rn(vr6, x6);
+      const double p6 = fma(t6, e6, t6);
+      double k = __dmul_rn(ve, __dsub_rn(__dmul_rn(p6, p6), __dmul_rn(2.0, p6)));
+      k = k > 1.0 ? 1.0 : k;
+      acc.v = __dadd_rn(acc.v, k);
+      if (DETAIL) ++acc.n_v;
+      if ((unsigned)__double2hiint(d2) < DNA_HI_IFACE) {
+        acc.iface_r = true;
+        atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
+        if (DETAIL) ++acc.n_if;
+      }
+    }
+  }
+  // Lanes leave the branches above after different trip counts; without an explicit reconvergence point the warp
+  // stays split over the following tiles (measured: 12 active threads per instruction on average).
+  __syncwarp();
+}
+
+template <bool DETAIL, bool TAB>
+__global__ void __launch_bounds__(DNA_THREADS, DNA_CTAS_PER_SM)
     dna_pair_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int pose = blockIdx.x / bb.rec_splits, split = blockIdx.x % bb.rec_splits;
@@ -614,8 +831,8 @@ __global__ void __launch_bounds__(DNA_THREADS, 1024 / DNA_THREADS)
   const int t1 = min(t0 + bb.tiles_per_split, cx.n_rec_tiles);
   const PairSmem s = carve(smem_raw, cx, bb);
   pair_prologue<1>(cx, bb, s, pose, t1 - t0);
-  const double *s_q = s.lig_static;
-  const double *s_eps = s_q + cx.n_lig_pad, *s_rad = s_eps + cx.n_lig_pad;
+  const double *s_se = s.lig_static, *s_rad = s_se + cx.n_lig_pad;
+  const bool hoisted = cx.vdw_sqrt_hoisted != 0;
 
   const int lane = threadIdx.x & 31;
   const double *gx = cx.rec_x, *gy = cx.rec_y, *gz = cx.rec_z;
@@ -626,10 +843,6 @@ __global__ void __launch_bounds__(DNA_THREADS, 1024 / DNA_THREADS)
     gsph = reinterpret_cast<const float4 *>(gz + cx.n_rec_pad);
   }
   unsigned *iface_rec_out = bb.iface_rec + (size_t)pose * cx.n_rec_tiles;
-  // src/dna.rs:15-25 — the constants are f64 products/quotients evaluated at compile time
-  const double ELEC_DIST_CUTOFF2 = 30.0 * 30.0, VDW_DIST_CUTOFF2 = 10.0 * 10.0;
-  const double ELEC_MAX_CUTOFF = 1.0 * 4.0 / 332.0, ELEC_MIN_CUTOFF = -1.0 * 4.0 / 332.0;
-  const double INTERFACE_CUTOFF2 = 3.9 * 3.9;  // src/constants.rs:15
 
   for (;;) {
     int t = 0;
@@ -637,72 +850,46 @@ __global__ void __launch_bounds__(DNA_THREADS, 1024 / DNA_THREADS)
     t = __shfl_sync(0xffffffffu, t, 0) + t0;
     if (t >= t1) break;
     const int ia = t * REC_TILE + lane;
-    const double rx = gx[ia], ry = gy[ia], rz = gz[ia];
-    const double rq = cx.rec_q[ia], reps = cx.rec_eps[ia], rrad = cx.rec_rad[ia];
+    DnaLane r = {gx[ia], gy[ia], gz[ia], cx.rec_q[ia], cx.rec_seps[ia], cx.rec_rad[ia], 0, TAB ? cx.rec_vt[ia] : 0};
+    // ELEC_MAX_CUTOFF / |q_r| (src/dna.rs:21); q_r == 0 gives +inf: no clamp, and every term is 0 * q_l/d2 = 0
+    r.clamp_bits = __double_as_longlong(__ddiv_rn(1.0 * 4.0 / 332.0, fabs(r.q)));
     const float4 rs = gsph[t];
-    double acc_e = 0.0, acc_v = 0.0;
-    bool iface_r = false;
-    unsigned n_e = 0, n_v = 0, n_if = 0, n_tested = 0;
+    DnaAcc acc = {0.0, 0.0, 0.0, 0.0, 0u, 0u, 0u, false};
+    unsigned n_tested = 0;
 
     for (int lt0 = 0; lt0 < cx.n_lig_tiles; lt0 += 32) {
       const int lt = lt0 + lane;
-      bool pass = false;
+      bool pass = false, close = false;
       if (lt < cx.n_lig_tiles) {
         const float4 ls = s.lsph[lt];
         const float dx = rs.x - ls.x, dy = rs.y - ls.y, dz = rs.z - ls.z;
         const float d2 = dx * dx + dy * dy + dz * dz;
         const float reach = 30.0f + rs.w + ls.w;  // ELEC_DIST_CUTOFF, the widest of the three
         pass = d2 <= reach * reach * 1.00001f;
+        const float reach_v = cx.dna_close_reach + rs.w + ls.w;  // >= VDW_DIST_CUTOFF and the widest clamp distance
+        close = d2 <= reach_v * reach_v * 1.00001f;
       }
       unsigned m = __ballot_sync(0xffffffffu, pass);
+      const unsigned mv = __ballot_sync(0xffffffffu, close);
       while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
         const int j0 = (lt0 + b) * LIG_TILE;
         if (DETAIL && ia < cx.n_rec) n_tested += min(LIG_TILE, cx.n_lig - j0);
-#pragma unroll
-        for (int jj = 0; jj < LIG_TILE; ++jj) {
-          const int j = j0 + jj;
-          const double dx = __dsub_rn(rx, s.lx[j]);
-          const double dy = __dsub_rn(ry, s.ly[j]);
-          const double dz = __dsub_rn(rz, s.lz[j]);
-          const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-          if (d2 <= ELEC_DIST_CUTOFF2) {  // src/dna.rs:481-491
-            double e = __dmul_rn(__dmul_rn(rq, s_q[j]), fast_rcp(d2));
-            e = e > ELEC_MAX_CUTOFF ? ELEC_MAX_CUTOFF : e;
-            e = e < ELEC_MIN_CUTOFF ? ELEC_MIN_CUTOFF : e;
-            acc_e = __dadd_rn(acc_e, e);
-            if (DETAIL) ++n_e;
-            if (d2 <= VDW_DIST_CUTOFF2) {  // src/dna.rs:494-504
-              const double ve = __dsqrt_rn(__dmul_rn(reps, s_eps[j]));
-              const double vr = __dadd_rn(rrad, s_rad[j]);
-              const double vr2 = __dmul_rn(vr, vr), vr4 = __dmul_rn(vr2, vr2);
-              const double vr6 = __dmul_rn(vr2, vr4);
-              const double d6 = __dmul_rn(d2, __dmul_rn(d2, d2));
-              const double p6 = __dmul_rn(vr6, fast_rcp(d6));
-              double k = __dmul_rn(ve, __dsub_rn(__dmul_rn(p6, p6), __dmul_rn(2.0, p6)));
-              k = k > 1.0 ? 1.0 : k;
-              acc_v = __dadd_rn(acc_v, k);
-              if (DETAIL) ++n_v;
-              if (d2 <= INTERFACE_CUTOFF2) {  // src/dna.rs:507-510
-                iface_r = true;
-                atomicOr(&s.iface_lig[j >> 5], 1u << (j & 31));
-                if (DETAIL) ++n_if;
-              }
-            }
-          }
-        }
+        if ((mv >> b) & 1u) dna_tile<true, DETAIL, TAB>(s, s_se, s_rad, hoisted, r, j0, acc);
+        else dna_tile<false, DETAIL, TAB>(s, s_se, s_rad, hoisted, r, j0, acc);
       }
     }
-    const double esum = warp_sum(acc_e), vsum = warp_sum(acc_v);
-    const unsigned rbits = __ballot_sync(0xffffffffu, iface_r);
+    const double e_lane = __dadd_rn(__dmul_rn(r.q, __dadd_rn(acc.e_l0, acc.e_l1)), acc.e_x);
+    const double esum = warp_sum(e_lane), vsum = warp_sum(acc.v);
+    const unsigned rbits = __ballot_sync(0xffffffffu, acc.iface_r);
     if (lane == 0) {
       s.tile_sum[2 * (t - t0)] = esum;
       s.tile_sum[2 * (t - t0) + 1] = vsum;
       iface_rec_out[t] = rbits;
     }
     if (DETAIL) {
-      n_e = warp_sum_u32(n_e); n_v = warp_sum_u32(n_v); n_if = warp_sum_u32(n_if);
+      const unsigned n_e = warp_sum_u32(acc.n_e), n_v = warp_sum_u32(acc.n_v), n_if = warp_sum_u32(acc.n_if);
       n_tested = warp_sum_u32(n_tested);
       if (lane == 0) {
         atomicAdd(&s.counters[0], (unsigned long long)n_e);

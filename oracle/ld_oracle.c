@@ -512,9 +512,11 @@ static int write_swarm(const gw_t *g, int n, int plen, int use_anm, int step, co
 /* Runs `steps` GSO steps with the oracle energy.  out_dir may be NULL (no files).  If `trace` is
  * non-NULL it receives, per step and glowworm, [luciferin, scoring, n_neighbors, vision, moved]
  * (5 doubles) followed by the pose row, i.e. steps*n*(5+pose_len) doubles. */
-ORACLE_API int oracle_gso_run(const oracle_complex_t *c, int n, const double *positions, uint64_t seed, int steps,
-                              const char *out_dir, double *final_poses, double *trace,
-                              oracle_gso_stats_t *stats) {
+/* n_threads > 1 only changes WHO evaluates a step's energies (the step's batch of moved glowworms is scored by
+ * oracle_score_batch_mt, each pose by the same energy_one): every number is bit-identical to the scalar run. */
+ORACLE_API int oracle_gso_run_mt(const oracle_complex_t *c, int n, const double *positions, uint64_t seed, int steps,
+                                 const char *out_dir, double *final_poses, double *trace, oracle_gso_stats_t *stats,
+                                 int n_threads) {
   const int plen = pose_len(c);
   const int nrm = c->use_anm ? c->rec.n_modes : 0, nlm = c->use_anm ? c->lig.n_modes : 0;
   scratch_t s;
@@ -522,6 +524,8 @@ ORACLE_API int oracle_gso_run(const oracle_complex_t *c, int n, const double *po
   gw_t *g = (gw_t *)calloc(n, sizeof(gw_t));
   double *snap = (double *)malloc(sizeof(double) * n * plen);
   double *lucs = (double *)malloc(sizeof(double) * n);
+  double *batch = (double *)malloc(sizeof(double) * n * plen), *batch_e = (double *)malloc(sizeof(double) * n);
+  int *batch_i = (int *)malloc(sizeof(int) * n);
   for (int i = 0; i < n; ++i) { /* src/glowworm.rs:29-59 */
     g[i].pose = (double *)malloc(sizeof(double) * plen);
     memcpy(g[i].pose, positions + (size_t)i * plen, sizeof(double) * plen);
@@ -537,8 +541,19 @@ ORACLE_API int oracle_gso_run(const oracle_complex_t *c, int n, const double *po
   const int max_neighbors = 5;
   for (int step = 1; step <= steps; ++step) {
     /* update_luciferin: src/swarm.rs:66-70, src/glowworm.rs:61-72 */
+    if (n_threads > 1) {
+      int nb = 0;
+      for (int i = 0; i < n; ++i)
+        if (g[i].moved || g[i].step == 0) {
+          memcpy(batch + (size_t)nb * plen, g[i].pose, sizeof(double) * plen);
+          batch_i[nb++] = i;
+        }
+      if (nb > 0 && oracle_score_batch_mt(c, nb, batch, batch_e, n_threads) != 0) return -1;
+      for (int k = 0; k < nb; ++k) g[batch_i[k]].scoring = batch_e[k];
+      calls += nb;
+    }
     for (int i = 0; i < n; ++i) {
-      if (g[i].moved || g[i].step == 0) {
+      if (n_threads <= 1 && (g[i].moved || g[i].step == 0)) {
         g[i].scoring = energy_one(c, g[i].pose, &s, NULL);
         ++calls;
       }
@@ -637,9 +652,15 @@ ORACLE_API int oracle_gso_run(const oracle_complex_t *c, int n, const double *po
     for (int i = 0; i < n; ++i) memcpy(final_poses + (size_t)i * plen, g[i].pose, sizeof(double) * plen);
   if (stats) stats->n_energy_calls = calls;
   for (int i = 0; i < n; ++i) { free(g[i].pose); free(g[i].neighbors); free(g[i].probabilities); }
-  free(g); free(snap); free(lucs);
+  free(g); free(snap); free(lucs); free(batch); free(batch_e); free(batch_i);
   scratch_free(&s);
   return 0;
+}
+
+ORACLE_API int oracle_gso_run(const oracle_complex_t *c, int n, const double *positions, uint64_t seed, int steps,
+                              const char *out_dir, double *final_poses, double *trace,
+                              oracle_gso_stats_t *stats) {
+  return oracle_gso_run_mt(c, n, positions, seed, steps, out_dir, final_poses, trace, stats, 1);
 }
 
 ORACLE_API int oracle_sizeof_complex(void) { return (int)sizeof(oracle_complex_t); }

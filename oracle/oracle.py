@@ -279,15 +279,17 @@ class Complex:
         assert rc == 0
         return e
 
-    def gso_run(self, positions, seed, steps, out_dir=None, trace=False):
+    def gso_run(self, positions, seed, steps, out_dir=None, trace=False, threads=1):
+        """The reference's GSO loop.  threads > 1 scores each step's batch of moved glowworms on that many threads
+        (same per-pose function: bit-identical results), so that a 100-step 1k4c trajectory takes seconds."""
         pos = self._poses(positions)
         n = pos.shape[0]
         final = np.zeros_like(pos)
         tr = np.zeros((steps, n, 5 + self.pose_len), dtype=np.float64) if trace else None
         st = GsoStats()
-        rc = self.lib.oracle_gso_run(C.byref(self.c), n, C.c_void_p(pos.ctypes.data), C.c_uint64(seed), int(steps),
-                                     out_dir.encode() if out_dir else None, C.c_void_p(final.ctypes.data),
-                                     C.c_void_p(tr.ctypes.data) if trace else None, C.byref(st))
+        rc = self.lib.oracle_gso_run_mt(C.byref(self.c), n, C.c_void_p(pos.ctypes.data), C.c_uint64(seed), int(steps),
+                                        out_dir.encode() if out_dir else None, C.c_void_p(final.ctypes.data),
+                                        C.c_void_p(tr.ctypes.data) if trace else None, C.byref(st), int(threads))
         assert rc == 0, rc
         return final, tr, int(st.n_energy_calls)
 

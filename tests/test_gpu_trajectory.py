@@ -72,11 +72,22 @@ def test_host_gso_matches_oracle_gso_dfire_anm(name, steps, tmp_path, monkeypatc
     assert (np.abs(state[:, 1] - last[:, 1]) <= ENERGY_RTOL * np.abs(last[:, 1])).all()  # scoring
 
 
-@pytest.mark.parametrize("name,steps", [("1ppe", 40), ("1k4c", 6)])
-def test_host_gso_matches_oracle_gso_rigid_path(name, steps, tmp_path, monkeypatch):
-    """BASELINE configs 1ppe (shipped set-up: no ANM, active restraint) and 1k4c (membrane beads) run on the
-    rigid-ligand DFIRE kernel: product host + GPU against the oracle's GSO, same seed; every discrete field
-    of the final state exact, poses to 1e-9, scores to the north-star tolerance."""
+def oracle_threads():
+    try:
+        return max(1, min(32, len(os.sched_getaffinity(0))))
+    except AttributeError:
+        return max(1, min(32, os.cpu_count() or 1))
+
+
+@pytest.mark.timeout(1500)
+@pytest.mark.parametrize("name", ["1ppe", "1k4c"])
+def test_host_gso_matches_oracle_gso_rigid_path(name, tmp_path, monkeypatch):
+    """BASELINE configs 1ppe (shipped set-up: no ANM, active restraint) and 1k4c (membrane beads) for the reference's
+    full 100 steps on the rigid-ligand DFIRE kernel: product host + GPU against the oracle's GSO, same seed.
+    Every saved step (1, 10, 20, ..., 100) is compared through the gso_<step>.out files both sides write
+    (neighbour counts and vision ranges exact, poses / luciferin / scoring to print precision + 1e-6 relative), and the
+    final state at full precision: discrete fields exact, poses to 1e-9, scores to the north-star tolerance.
+    The oracle scores each step's batch on all host cores (bit-identical to its scalar run)."""
     from ldb200 import host
     cx, pos, seed = case(name, O.DFIRE)
     g = os.path.join(GOLDEN, name)
@@ -84,14 +95,18 @@ def test_host_gso_matches_oracle_gso_rigid_path(name, steps, tmp_path, monkeypat
     monkeypatch.setenv("LIGHTDOCK_DATA", str(tmp_path))
     c = host.Case(os.path.join(g, "setup.json"), "dfire", anm_dir=g)
     assert c.path_info().startswith("rigid path on"), c.path_info()
-    state, calls = c.gso(os.path.join(g, "initial_positions_0.dat"), steps)
-    final, tr, ocalls = cx.gso_run(pos, seed, steps, trace=True)
+    os.makedirs(tmp_path / "gpu"); os.makedirs(tmp_path / "cpu")
+    state, calls = c.gso(os.path.join(g, "initial_positions_0.dat"), 100, out_dir=str(tmp_path / "gpu"))
+    final, tr, ocalls = cx.gso_run(pos, seed, 100, out_dir=str(tmp_path / "cpu"), trace=True, threads=oracle_threads())
+    for s in STEPS:
+        compare_gso_files(str(tmp_path / "gpu" / f"gso_{s}.out"), str(tmp_path / "cpu" / f"gso_{s}.out"))
     last = tr[-1]
     assert calls == ocalls
     np.testing.assert_array_equal(state[:, 2], last[:, 2])            # neighbour counts
     np.testing.assert_array_equal(state[:, 3], last[:, 3])            # vision range
     assert np.abs(state[:, 4:] - last[:, 5:]).max() <= 1e-9            # poses
     assert (np.abs(state[:, 1] - last[:, 1]) <= ENERGY_RTOL * np.abs(last[:, 1])).all()  # scoring
+    assert tr[:, :, 4].sum() > 5000, "the swarm must actually move over the 100 steps"
 
 
 def test_multi_gso_equals_single_swarm_runs():
