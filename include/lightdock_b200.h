@@ -130,7 +130,11 @@ int ld_score_batch_begin(ld_handle *h, int32_t slot, int64_t n_poses, const doub
 int ld_score_batch_end(ld_handle *h, int32_t slot, double *energies);
 
 /* Same, with device-resident poses/energies on a caller-provided CUDA stream (cudaStream_t passed
- * as void*; NULL = the handle's own stream).  Asynchronous with respect to the host. */
+ * as void*; NULL = the handle's own stream).  Asynchronous with respect to the host.  The call works in the
+ * handle's slot-0 work buffers; the library orders successive users of those buffers itself (an event recorded
+ * after the call's last kernel is waited on by the next call, on whatever stream that one launches), so calls on
+ * different streams serialise on the device instead of racing.  The caller still owns the ordering of ITS buffers
+ * (d_poses must be ready on `stream`; d_energies is complete when `stream` reaches the end of the call). */
 int ld_score_batch_device(ld_handle *h, int64_t n_poses, const double *d_poses, double *d_energies,
                           void *stream);
 
@@ -144,7 +148,9 @@ int ld_score_batch_detail(ld_handle *h, int64_t n_poses, const double *poses, do
 int ld_transform_batch(ld_handle *h, int64_t n_poses, const double *poses, double *rec_coords,
                        double *lig_coords);
 
+/* Counters of the last scoring call on the handle (whatever slot it used) / of the last call on one slot. */
 int ld_get_stats(ld_handle *h, ld_batch_stats *out);
+int ld_get_stats_slot(ld_handle *h, int32_t slot, ld_batch_stats *out);
 
 /* Tuning knob for benchmarks/tests: force the number of receptor splits (0 = automatic). */
 int ld_set_rec_splits(ld_handle *h, int32_t splits);
@@ -170,6 +176,11 @@ int ld_set_profiling(ld_handle *h, int32_t on);
  * window in G loads/s. */
 int ld_probe_peaks(int32_t device, double *fp64_nonfma_tflops, double *fp32_nonfma_tflops,
                    double *l2_gather_gloads);
+
+/* Process-wide tuning defaults for handles created afterwards (benchmark / experiment aid; the library never reads
+ * the environment): "rigid_rows" 1..4 table rows per receptor group, "cell_size" ligand-frame cell edge in A
+ * (0.5..8), "units_per_sm" rigid-kernel work units per SM, "default_path" LD_PATH_AUTO | LD_PATH_GENERIC. */
+int ld_set_option(const char *key, double value);
 
 /* Number of CUDA devices visible to the process (0 if none / no driver): the multi-swarm driver shards swarms
  * over them (swarm s -> device s mod count). */

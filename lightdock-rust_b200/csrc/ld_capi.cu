@@ -15,6 +15,15 @@
 #include "ld_kernels.cuh"
 #include "ld_rigid.cuh"
 
+// NVTX ranges around the phases of a host-buffer call (staging + H2D, kernel launches, D2H + wait): visible in an
+// Nsight Systems timeline, free otherwise.
+#if __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+namespace { struct Nvtx { explicit Nvtx(const char *n) { nvtxRangePushA(n); } ~Nvtx() { nvtxRangePop(); } }; }
+#else
+namespace { struct Nvtx { explicit Nvtx(const char *) {} }; }
+#endif
+
 using namespace ldb200;
 
 // ---------------------------------------------------------------------------------------------
@@ -36,7 +45,32 @@ extern "C" int ld_device_count(void) {
   int n = 0;
   return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
-extern "C" const char *ld_version(void) { return "lightdock_b200 0.1 (sm_100a)"; }
+extern "C" const char *ld_version(void) { return "lightdock_b200 0.2 (sm_100a)"; }
+
+// Process-wide tuning defaults read by ld_create / the launch code (ld_set_option); the library itself never looks
+// at the environment.
+namespace {
+struct Options {
+  int rigid_rows = RG_MAX_ROWS;   // table rows a receptor group may span (1..RG_MAX_ROWS)
+  double cell_size = 1.0;         // ligand-frame cell size in A
+  int units_per_sm = 16;          // rigid kernel: work units per SM
+  int default_path = LD_PATH_AUTO;
+};
+Options g_opt;
+}  // namespace
+
+extern "C" int ld_set_option(const char *key, double value) {
+  if (!key) return fail(LD_EINVAL, "ld_set_option: NULL key");
+  const std::string k(key);
+  if (k == "rigid_rows") g_opt.rigid_rows = std::max(1, std::min(RG_MAX_ROWS, (int)value));
+  else if (k == "cell_size") g_opt.cell_size = std::max(0.5, std::min(8.0, value));
+  else if (k == "units_per_sm") g_opt.units_per_sm = std::max(1, (int)value);
+  else if (k == "default_path") {
+    if (value != LD_PATH_AUTO && value != LD_PATH_GENERIC) return fail(LD_EINVAL, "ld_set_option: default_path is AUTO or GENERIC");
+    g_opt.default_path = (int)value;
+  } else return fail(LD_EINVAL, "ld_set_option: unknown key " + k);
+  return LD_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Everything one batch in flight needs: a stream, pinned staging, device pose/energy buffers and the kernels'
@@ -64,6 +98,10 @@ struct Workspace {
   std::vector<cudaEvent_t> prof_events;
   size_t prof_used = 0;
   cudaStream_t last_stream = nullptr;
+  // Orders the work buffers of this workspace across streams: recorded after the last kernel that touches them,
+  // waited on by the next user whatever stream it launches on (ld_score_batch_device takes the caller's stream).
+  cudaEvent_t done = nullptr;
+  bool done_recorded = false;
   int64_t pending = -1;                 // poses of the batch begun on this slot and not yet ended (-1 = none)
 };
 
@@ -71,6 +109,7 @@ struct ld_handle {
   int device = 0;
   Workspace ws[LD_SLOTS];
   Workspace *w = &ws[0];                // the slot the current call works on (one host thread per handle)
+  Workspace *last_w = &ws[0];           // the slot of the last scoring call (ld_get_stats)
   DeviceComplex cx{};
   std::vector<void *> owned;  // device allocations of the complex
   std::vector<int> rec_perm, lig_perm;  // sorted position -> original atom index
@@ -226,6 +265,7 @@ extern "C" int ld_destroy(ld_handle *h) {
     for (cudaEvent_t e : w.prof_events) cudaEventDestroy(e);
     if (w.ev0) cudaEventDestroy(w.ev0);
     if (w.ev1) cudaEventDestroy(w.ev1);
+    if (w.done) cudaEventDestroy(w.done);
     if (w.stream) cudaStreamDestroy(w.stream);
   }
   for (void *p : h->owned) cudaFree(p);
@@ -282,7 +322,7 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   if (cx.n_lig_tiles > 65535) { h->rigid_info = "rigid path off: ligand tile ids exceed 16 bits"; return LD_OK; }
   const long avail = (long)h->max_smem_optin - (long)rigid_smem_bytes(cx.n_lig_pad, 0);
   int rows_max = (int)std::min<long>(RG_MAX_ROWS, avail / RG_ROW_BYTES);
-  if (const char *e = getenv("LDB200_ROWS")) rows_max = std::max(1, std::min(rows_max, atoi(e)));  // tuning aid
+  rows_max = std::max(1, std::min(rows_max, g_opt.rigid_rows));
   if (rows_max < 1) { h->rigid_info = "rigid path off: ligand + one table row exceed shared memory"; return LD_OK; }
 
   RigidComplex &rc = h->rc;
@@ -336,8 +376,7 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
 
   // cell grid over the ligand's bounding box grown by the cut-off; a cell lists every tile with an atom
   // within 15 A + slack of the cell's box (slack: f32 cell assignment + the classification margin delta)
-  double cell = 1.0;
-  if (const char *e = getenv("LDB200_CELL")) cell = std::max(0.5, std::min(8.0, atof(e)));
+  double cell = g_opt.cell_size;
   const double reach = 15.0 + 0.01;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   const std::vector<double> *LC[3] = {&L.x, &L.y, &L.z};
@@ -484,6 +523,7 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
     CU(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&w.ev0));
     CU(cudaEventCreate(&w.ev1));
+    CU(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
   }
 
   const int nrm = h->use_anm ? desc->receptor.n_modes : 0, nlm = h->use_anm ? desc->ligand.n_modes : 0;
@@ -610,9 +650,7 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
   CU(cudaFuncSetAttribute(dna_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CU(cudaFuncSetAttribute(dna_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CU(cudaFuncSetAttribute(dna_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  if (const char *e = getenv("LDB200_PATH")) {  // benchmarking aid; ld_set_path() is the API
-    if (!strcmp(e, "generic")) h->path_mode = LD_PATH_GENERIC;
-  }
+  h->path_mode = g_opt.default_path;
   return build_rigid(desc, h, L);
 }
 
@@ -662,25 +700,33 @@ extern "C" int ld_set_profiling(ld_handle *h, int32_t on) {
   return LD_OK;
 }
 
-extern "C" int ld_get_stats(ld_handle *h, ld_batch_stats *out) {
-  if (!h || !out) return fail(LD_EINVAL, "ld_get_stats: NULL argument");
-  h->w = &h->ws[0];
-  if (h->profiling && h->w->prof_used >= 4) {
+static int get_stats(ld_handle *h, Workspace *w, ld_batch_stats *out) {
+  if (h->profiling && w->prof_used >= 4) {
     CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->w->last_stream));
+    CU(cudaStreamSynchronize(w->last_stream));
     double t[3] = {0, 0, 0};
-    for (size_t c = 0; c + 4 <= h->w->prof_used; c += 4)
+    for (size_t c = 0; c + 4 <= w->prof_used; c += 4)
       for (int k = 0; k < 3; ++k) {
         float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, h->w->prof_events[c + k], h->w->prof_events[c + k + 1]));
+        CU(cudaEventElapsedTime(&ms, w->prof_events[c + k], w->prof_events[c + k + 1]));
         t[k] += ms;
       }
-    h->w->stats.transform_ms = t[0];
-    h->w->stats.pair_ms = t[1];
-    h->w->stats.finalize_ms = t[2];
+    w->stats.transform_ms = t[0];
+    w->stats.pair_ms = t[1];
+    w->stats.finalize_ms = t[2];
   }
-  *out = h->w->stats;
+  *out = w->stats;
   return LD_OK;
+}
+
+extern "C" int ld_get_stats(ld_handle *h, ld_batch_stats *out) {
+  if (!h || !out) return fail(LD_EINVAL, "ld_get_stats: NULL argument");
+  return get_stats(h, h->last_w, out);
+}
+
+extern "C" int ld_get_stats_slot(ld_handle *h, int32_t slot, ld_batch_stats *out) {
+  if (!h || !out || slot < 0 || slot >= LD_SLOTS) return fail(LD_EINVAL, "ld_get_stats_slot: bad argument");
+  return get_stats(h, &h->ws[slot], out);
 }
 
 static int prof_mark(ld_handle *h, cudaStream_t st) {
@@ -787,12 +833,16 @@ static int ensure_poses(ld_handle *h, int64_t n, bool detail) {
 // If host_iface_* are given (detail mode) the bitmaps of each chunk are copied back as they are produced.
 static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_energies, cudaStream_t st,
                       ld_pose_detail *d_detail, std::vector<unsigned> *host_ifr, std::vector<unsigned> *host_ifl) {
+  Nvtx range_launch("ld: kernel launches (prep/transform, pair, finalize)");
   const DeviceComplex &cx = h->cx;
   h->w->stats = ld_batch_stats{};
   h->w->stats.n_poses = n;
   h->w->stats.pair_evals_bruteforce = n * (int64_t)cx.n_rec * (int64_t)cx.n_lig;
   if (!h->prof_continue) h->w->prof_used = 0;
+  // the previous user of this workspace's buffers may have launched on another stream
+  if (h->w->done_recorded && h->w->last_stream != st) CU(cudaStreamWaitEvent(st, h->w->done, 0));
   h->w->last_stream = st;
+  h->last_w = h->w;
   if (n == 0) return LD_OK;
   const int64_t climit = chunk_limit(h, use_rigid(h));
   const int lig_words = (cx.n_lig_pad + 31) / 32;
@@ -831,7 +881,7 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       CU(cudaMemsetAsync(h->w->d_iface_lig, 0, (size_t)nc * lig_words * sizeof(unsigned), st));
       CU(cudaMemsetAsync(h->w->d_unit_counter, 0, sizeof(unsigned), st));
       // work units: (group, range of poses); ~16 units per SM and group changes kept rare
-      static const int units_per_sm = [] { const char *e = getenv("LDB200_UNITS_PER_SM"); return e ? std::max(1, atoi(e)) : 16; }();
+      const int units_per_sm = g_opt.units_per_sm;
       int64_t ppu = (nc * rg.n_groups + (int64_t)h->sm_count * units_per_sm - 1) / ((int64_t)h->sm_count * units_per_sm);
       ppu = std::max<int64_t>(RG_WARPS, std::min<int64_t>(ppu, 1024));
       const int n_chunks = (int)((nc + ppu - 1) / ppu);
@@ -922,6 +972,8 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
   }
   h->w->stats.kernel_launches = launches;
   h->w->stats.pair_launches = pair_launches;
+  CU(cudaEventRecord(h->w->done, st));
+  h->w->done_recorded = true;
   return LD_OK;
 }
 
@@ -957,6 +1009,7 @@ static int score_host(ld_handle *h, int64_t n, const double *poses, double *ener
   const int64_t n_head = (!want_detail && n >= 65536) ? n / 8 : 0;  // smaller batches: a second launch costs more
   ld_batch_stats head_stats{};
   CU(cudaEventRecord(h->w->ev0, h->w->stream));
+  Nvtx range_call("ld_score_batch");
   if (n_head > 0) {
     const size_t head_bytes = (size_t)n_head * cx.pose_len * sizeof(double);
     std::memcpy(h->w->h_poses, poses, head_bytes);
@@ -998,7 +1051,10 @@ static int score_host(ld_handle *h, int64_t n, const double *poses, double *ener
   if (want_detail)
     CU(cudaMemcpyAsync(detail, h->w->d_detail, (size_t)n * sizeof(ld_pose_detail), cudaMemcpyDeviceToHost, h->w->stream));
   CU(cudaEventRecord(h->w->ev1, h->w->stream));
-  CU(cudaStreamSynchronize(h->w->stream));
+  {
+    Nvtx range_wait("ld_score_batch: wait for the device + D2H");
+    CU(cudaStreamSynchronize(h->w->stream));
+  }
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, h->w->ev0, h->w->ev1));
   h->w->stats.device_ms = ms;
@@ -1081,6 +1137,7 @@ extern "C" int ld_transform_batch(ld_handle *h, int64_t n, const double *poses, 
   const DeviceComplex &cx = h->cx;
   int rc;
   if ((rc = ensure_poses(h, n, false)) != LD_OK) return rc;
+  if (h->w->done_recorded && h->w->last_stream != h->w->stream) CU(cudaStreamWaitEvent(h->w->stream, h->w->done, 0));
   CU(cudaMemcpyAsync(h->w->d_poses, poses, (size_t)n * cx.pose_len * sizeof(double), cudaMemcpyHostToDevice, h->w->stream));
   const int64_t climit = chunk_limit(h, false);
   std::vector<unsigned char> lb, rb;

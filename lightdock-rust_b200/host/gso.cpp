@@ -1,4 +1,5 @@
 #include "gso.hpp"
+#include "log.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -140,10 +141,19 @@ size_t Swarm::gather_poses(std::vector<double> &rows, std::vector<uint32_t> &who
   size_t n = 0;
   for (const Glowworm &g : glowworms)
     if (g.needs_scoring()) {
-      if (7 + g.rec_nmodes.size() + g.lig_nmodes.size() != pl)
-        throw std::runtime_error("start position width does not match the scoring function's pose length");
+      // The reference's energy() reads exactly num_anm extents per partner (src/dfire.rs:290-320) and ignores trailing
+      // columns a start file may carry (they end up at the tail of lig_nmodes, src/swarm.rs:47-50); too few is an
+      // out-of-bounds panic there.
+      const size_t have = 7 + g.rec_nmodes.size() + g.lig_nmodes.size();
+      if (have < pl) throw std::runtime_error("index out of bounds: start position has fewer columns than the pose");
       rows.resize(rows.size() + pl);
-      g.write_pose(rows.data() + rows.size() - pl);
+      if (have == pl) {
+        g.write_pose(rows.data() + rows.size() - pl);
+      } else {
+        std::vector<double> full(have);
+        g.write_pose(full.data());
+        std::copy(full.begin(), full.begin() + pl, rows.end() - pl);
+      }
       who.push_back(g.id);
       ++n;
     }
@@ -261,19 +271,31 @@ void Swarm::movement_phase(StdRng &rng) {
   }
 }
 
+// `{:.N}` of an f64 as Rust prints it: NaN, inf, -inf for the non-finite values (C prints nan / -nan).
+static void print_f(FILE *f, const char *prefix, double v, int prec) {
+  if (std::isnan(v)) std::fprintf(f, "%sNaN", prefix);
+  else if (std::isinf(v)) std::fprintf(f, "%s%s", prefix, v > 0 ? "inf" : "-inf");
+  else std::fprintf(f, "%s%.*f", prefix, prec, v);
+}
+
 void Swarm::save(uint32_t step, const std::string &output_directory) const {
   const std::string path = output_directory + "/gso_" + std::to_string(step) + ".out";
   FILE *f = std::fopen(path.c_str(), "w");
   if (!f) throw std::runtime_error("Error saving GSO output: cannot create " + path);
   std::fprintf(f, "#Coordinates  RecID  LigID  Luciferin  Neighbor's number  Vision Range  Scoring\n");
   for (const Glowworm &g : glowworms) {
-    std::fprintf(f, "(%.7f, %.7f, %.7f, %.7f, %.7f, %.7f, %.7f", g.translation[0], g.translation[1],
-                 g.translation[2], g.rotation.w, g.rotation.x, g.rotation.y, g.rotation.z);
+    const double head[7] = {g.translation[0], g.translation[1], g.translation[2], g.rotation.w, g.rotation.x,
+                            g.rotation.y, g.rotation.z};
+    for (int k = 0; k < 7; ++k) print_f(f, k == 0 ? "(" : ", ", head[k], 7);
     if (g.use_anm && !g.rec_nmodes.empty())
-      for (double v : g.rec_nmodes) std::fprintf(f, ", %.7f", v);
+      for (double v : g.rec_nmodes) print_f(f, ", ", v, 7);
     if (g.use_anm && !g.lig_nmodes.empty())
-      for (double v : g.lig_nmodes) std::fprintf(f, ", %.7f", v);
-    std::fprintf(f, ")    0    0   %.8f  %zu %.3f %.8f\n", g.luciferin, g.neighbors.size(), g.vision_range, g.scoring);
+      for (double v : g.lig_nmodes) print_f(f, ", ", v, 7);
+    print_f(f, ")    0    0   ", g.luciferin, 8);
+    std::fprintf(f, "  %zu ", g.neighbors.size());
+    print_f(f, "", g.vision_range, 3);
+    print_f(f, " ", g.scoring, 8);
+    std::fputc('\n', f);
   }
   std::fclose(f);
 }
@@ -286,9 +308,19 @@ GSO::GSO(const std::vector<std::vector<double>> &positions, uint64_t seed, const
 
 void GSO::run(uint32_t steps) {
   for (uint32_t step = 1; step <= steps; ++step) {
-    swarm.update_luciferin();
-    swarm.movement_phase(rng);
-    if ((step % 10 == 0 || step == 1) && !output_directory.empty()) swarm.save(step, output_directory);
+    log_line(LogLevel::Info, "lightdock", "Step " + std::to_string(step));  // src/lib.rs:48
+    {
+      NvtxRange r("update_luciferin (gather + ld_score_batch + scatter)");
+      swarm.update_luciferin();
+    }
+    {
+      NvtxRange r("movement_phase");
+      swarm.movement_phase(rng);
+    }
+    if ((step % 10 == 0 || step == 1) && !output_directory.empty()) {
+      NvtxRange r("save");
+      swarm.save(step, output_directory);
+    }
   }
 }
 
@@ -403,12 +435,22 @@ void MultiGSO::run_lane(const std::vector<size_t> &mine, const Score *sc, uint32
   std::vector<std::vector<uint32_t>> who(ns);
   std::vector<std::vector<double>> swarm_rows(ns);
   auto gather_and_begin = [&](int k) {
+    NvtxRange range(k == 0 ? "gather + begin (set 0)" : "gather + begin (set 1)");
     Half &h = half[k];
     workers.for_each(h.hi - h.lo, [&](size_t i) {  // which glowworms must be rescored, and their pose rows
       const size_t s = h.lo + i;
       who[s].clear();
       swarm_rows[s].clear();
-      runs[mine[s]].swarm.gather_poses(swarm_rows[s], who[s]);
+      GSO &r = runs[mine[s]];
+      if (r.failed) return;
+      try {
+        r.swarm.gather_poses(swarm_rows[s], who[s]);
+      } catch (const std::exception &e) {  // what would be a panic of that swarm's own process in the reference
+        r.failed = true;
+        r.error = e.what();
+        who[s].clear();
+        swarm_rows[s].clear();
+      }
     });
     for (size_t i = 0; i < h.hi - h.lo; ++i) h.first[i + 1] = h.first[i] + swarm_rows[h.lo + i].size();
     h.rows.resize(h.first.back());
@@ -419,21 +461,57 @@ void MultiGSO::run_lane(const std::vector<size_t> &mine, const Score *sc, uint32
     sc->energy_batch_begin(k, h.scores.size(), h.rows.data());  // ONE batched launch for all swarms of the set
   };
   auto end_and_move = [&](int k, uint32_t step) {
+    NvtxRange range(k == 0 ? "end + scatter + movement (set 0)" : "end + scatter + movement (set 1)");
     Half &h = half[k];
-    sc->energy_batch_end(k, h.scores.data());
+    {
+      NvtxRange wait("ld_score_batch_end (device wait)");
+      sc->energy_batch_end(k, h.scores.data());
+    }
     workers.for_each(h.hi - h.lo, [&](size_t i) {
       GSO &r = runs[mine[h.lo + i]];
-      r.swarm.scatter_scores(who[h.lo + i], h.scores.data() + h.first[i] / pl);
-      r.swarm.movement_phase(r.rng);
-      if ((step % 10 == 0 || step == 1) && !r.output_directory.empty()) r.swarm.save(step, r.output_directory);
+      if (r.failed) return;
+      // One process per swarm in the reference (example/1czy/execution.sh:21-25): a panic there ends that swarm
+      // only.  Same here: the swarm is marked failed and dropped from the following steps, the others go on.
+      try {
+        r.swarm.scatter_scores(who[h.lo + i], h.scores.data() + h.first[i] / pl);
+        r.swarm.movement_phase(r.rng);
+        if ((step % 10 == 0 || step == 1) && !r.output_directory.empty()) r.swarm.save(step, r.output_directory);
+      } catch (const std::exception &e) {
+        r.failed = true;
+        r.error = std::string("step ") + std::to_string(step) + ": " + e.what();
+      }
     });
   };
-  for (int k = 0; k < nh; ++k) gather_and_begin(k);
-  for (uint32_t step = 1; step <= steps; ++step)
-    for (int k = 0; k < nh; ++k) {
-      end_and_move(k, step);
-      if (step < steps) gather_and_begin(k);
-    }
+  // A failure of the scoring call itself (CUDA error, bad argument) is not a per-swarm event: it ends the lane, but
+  // not before every slot with a batch in flight has been collected, so the handle stays usable.
+  bool in_flight[2] = {false, false};
+  try {
+    for (int k = 0; k < nh; ++k) { gather_and_begin(k); in_flight[k] = true; }
+    for (uint32_t step = 1; step <= steps; ++step)
+      for (int k = 0; k < nh; ++k) {
+        if (k == 0) log_line(LogLevel::Info, "lightdock", "Step " + std::to_string(step));  // src/lib.rs:48
+        in_flight[k] = false;
+        end_and_move(k, step);
+        if (step < steps) { gather_and_begin(k); in_flight[k] = true; }
+      }
+  } catch (...) {
+    for (int k = 0; k < nh; ++k)
+      if (in_flight[k]) {
+        try {
+          half[k].scores.resize(half[k].rows.size() / pl);
+          sc->energy_batch_end(k, half[k].scores.data());
+        } catch (...) {
+        }
+      }
+    throw;
+  }
+}
+
+std::vector<std::pair<size_t, std::string>> MultiGSO::failures() const {
+  std::vector<std::pair<size_t, std::string>> out;
+  for (size_t s = 0; s < runs.size(); ++s)
+    if (runs[s].failed) out.emplace_back(s, runs[s].error);
+  return out;
 }
 
 void MultiGSO::run(uint32_t steps, int host_threads) {

@@ -6,6 +6,7 @@
 #pragma once
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "quaternion.hpp"
@@ -76,6 +77,10 @@ struct GSO {  // src/lib.rs:20-59
   Swarm swarm;
   StdRng rng;
   std::string output_directory;
+  // MultiGSO only: this swarm hit what is a panic in the reference (roulette overrun, unwritable output file, ...);
+  // it stops there, like the reference's one-process-per-swarm model, and the other swarms go on
+  bool failed = false;
+  std::string error;
 
   GSO(const std::vector<std::vector<double>> &positions, uint64_t seed, const Score *scoring, bool use_anm,
       size_t rec_num_anm, size_t lig_num_anm, std::string output_directory);
@@ -98,6 +103,8 @@ struct MultiGSO {
   // other set's device scoring.
   void run(uint32_t steps, int host_threads = 1);
   uint64_t energy_calls() const;
+  // (index into `runs`, message) of every swarm that stopped early
+  std::vector<std::pair<size_t, std::string>> failures() const;
 
  private:
   void run_lane(const std::vector<size_t> &mine, const Score *sc, uint32_t steps, int host_threads);

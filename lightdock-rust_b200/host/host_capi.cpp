@@ -1,6 +1,7 @@
 // host_capi.cpp — small C entry points over the C++ host layer so the Python tests / bench can drive
 // exactly the code the CLI runs (model building, batched scoring, GSO).  Not part of the drop-in ABI.
 #include <cstring>
+#include <stdexcept>
 #include <string>
 
 #include "gso.hpp"
@@ -161,6 +162,7 @@ int ldh_case_multi_gso(ldh_case *c, int n_swarms, int n_glowworms, const double 
   }
   multi.run(steps, host_threads);
   if (energy_calls) *energy_calls = multi.energy_calls();
+  const auto failures = multi.failures();
   if (final_state)
     for (int w = 0; w < n_swarms; ++w)
       for (int i = 0; i < n_glowworms; ++i) {
@@ -169,6 +171,11 @@ int ldh_case_multi_gso(ldh_case *c, int n_swarms, int n_glowworms, const double 
         r[0] = g.luciferin; r[1] = g.scoring; r[2] = (double)g.neighbors.size(); r[3] = g.vision_range;
         g.write_pose(r + 4);
       }
+  if (!failures.empty()) {  // the other swarms ran to the end; their state is in final_state
+    std::string msg = std::to_string(failures.size()) + " swarm(s) stopped early:";
+    for (const auto &f : failures) msg += " [" + std::to_string(f.first) + "] " + f.second + ";";
+    throw std::runtime_error(msg);
+  }
   return 0;
   LDH_CATCH(-1)
 }
@@ -194,6 +201,35 @@ int ldh_find_neighbors(int n, const double *xyz, const double *luciferin, const 
   }
   out_offsets[n] = k;
   return k;
+  LDH_CATCH(-1)
+}
+
+// Host-only test hooks for the text I/O either side of the path -----------------------------------
+// 1 if `token.parse::<f64>()` succeeds in Rust (value in *out), 0 if it is a ParseFloatError there.
+int ldh_parse_f64(const char *token, double *out) {
+  double v = 0.0;
+  const bool ok = parse_f64_like_rust(token, v);
+  if (ok && out) *out = v;
+  return ok ? 1 : 0;
+}
+// Writes a swarm state with Swarm::save (src/swarm.rs:128-167): rows [n][4 + pose_len] = luciferin, scoring,
+// vision range, n_neighbors, pose...
+int ldh_save_swarm(int n, int n_rec_anm, int n_lig_anm, const double *rows, unsigned step, const char *dir) {
+  LDH_TRY
+  const int pl = 7 + n_rec_anm + n_lig_anm;
+  Swarm sw;
+  std::vector<std::vector<double>> pos(n);
+  for (int i = 0; i < n; ++i) pos[i].assign(rows + (size_t)i * (4 + pl) + 4, rows + (size_t)(i + 1) * (4 + pl));
+  sw.add_glowworms(pos, nullptr, n_rec_anm + n_lig_anm > 0, n_rec_anm, n_lig_anm);
+  for (int i = 0; i < n; ++i) {
+    const double *r = rows + (size_t)i * (4 + pl);
+    sw.glowworms[i].luciferin = r[0];
+    sw.glowworms[i].scoring = r[1];
+    sw.glowworms[i].vision_range = r[2];
+    sw.glowworms[i].neighbors.assign((size_t)r[3], 0u);
+  }
+  sw.save(step, dir);
+  return 0;
   LDH_CATCH(-1)
 }
 

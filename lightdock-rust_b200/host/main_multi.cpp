@@ -138,6 +138,7 @@ int main(int argc, char **argv) {
     std::fflush(stdout);
     std::vector<std::exception_ptr> errors(G);
     std::vector<uint64_t> calls(G, 0);
+    std::vector<std::vector<std::pair<std::string, std::string>>> failed(G);  // (swarm dir, message) per GPU
     std::vector<std::thread> drivers;
     for (size_t g = 0; g < G; ++g)
       drivers.emplace_back([&, g] {
@@ -148,6 +149,7 @@ int main(int argc, char **argv) {
             multi.add(positions[s], lc.seed, setup.use_anm, setup.anm_rec, setup.anm_lig, dirs[s]);
           multi.run((uint32_t)job.steps, host_threads);
           calls[g] = multi.energy_calls();
+          for (const auto &f : multi.failures()) failed[g].emplace_back(dirs[g + f.first * G], f.second);
         } catch (...) {
           errors[g] = std::current_exception();
         }
@@ -158,7 +160,14 @@ int main(int argc, char **argv) {
     uint64_t total = 0;
     for (uint64_t c : calls) total += c;
     std::printf("Done: %llu poses scored\n", (unsigned long long)total);
-    return 0;
+    // a swarm that hit what is a panic in the reference stopped alone (one process per swarm there); report and fail
+    size_t n_failed = 0;
+    for (const auto &fg : failed)
+      for (const auto &f : fg) {
+        std::fprintf(stderr, "lightdock-rust-multi: %s failed: %s\n", f.first.c_str(), f.second.c_str());
+        ++n_failed;
+      }
+    return n_failed ? 1 : 0;
   } catch (const std::exception &e) {
     std::fprintf(stderr, "lightdock-rust-multi: %s\n", e.what());
     return 1;

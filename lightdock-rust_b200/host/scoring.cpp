@@ -1,4 +1,5 @@
 #include "scoring.hpp"
+#include "log.hpp"
 
 #include <algorithm>
 #include <cstdio>
@@ -62,7 +63,8 @@ DockingModel DockingModel::build(Method method, const PDB &structure, const std:
           if (at == amber.end())
             throw std::runtime_error(std::string(tag) + " Error: Atom [\"" + atom_id + "\"] not supported");
         } else if (method == Method::PYDOCK) {
-          std::fprintf(stderr, "PYDOCK Warning: Atom [\"%s\"] not supported, trying generic\n", atom_id.c_str());
+          // warn!(..) of src/pydock.rs:332-335: shown at RUST_LOG=warn and above, silent by default (env_logger)
+          log_line(LogLevel::Warn, "lightdock::pydock", "PYDOCK Warning: Atom [\"" + atom_id + "\"] not supported, trying generic");
           if (atom.name.empty())
             throw std::runtime_error("PYDOCK Error: Atom element could not be guessed from [\"\"]");
           atom_id = std::string("*-") + atom.name[0];
@@ -95,6 +97,8 @@ DockingModel DockingModel::build(Method method, const PDB &structure, const std:
     model.coordinates.push_back(atom.z);
     ++atom_index;
   }
+  if (method == Method::PYDOCK)  // info!("Atoms read: {}", atom_index), src/pydock.rs:379
+    log_line(LogLevel::Info, "lightdock::pydock", "Atoms read: " + std::to_string(atom_index));
   return model;
 }
 

@@ -186,6 +186,43 @@ SetupFile read_setup_from_file(const std::string &path) {
   return s;
 }
 
+// `str::parse::<f64>()` (Rust core, dec2flt): an optional sign, then either decimal digits with an optional fraction and
+// an optional exponent (at least one digit overall), or "inf" / "infinity" / "nan" in any case.  No surrounding white
+// space, no hexadecimal floats, no "nan(...)", no digit separators: everything strtod accepts beyond that is refused
+// here so that a start file the reference would panic on is not silently read.
+bool parse_f64_like_rust(const std::string &tok, double &out) {
+  size_t i = 0;
+  const size_t n = tok.size();
+  if (i < n && (tok[i] == '+' || tok[i] == '-')) ++i;
+  if (i == n) return false;
+  auto ieq = [&](const char *w) {
+    size_t k = 0;
+    for (; w[k]; ++k)
+      if (i + k >= n || std::tolower((unsigned char)tok[i + k]) != w[k]) return false;
+    return i + k == n;
+  };
+  if (!(ieq("inf") || ieq("infinity") || ieq("nan"))) {
+    size_t digits = 0, j = i;
+    while (j < n && std::isdigit((unsigned char)tok[j])) { ++j; ++digits; }
+    if (j < n && tok[j] == '.') {
+      ++j;
+      while (j < n && std::isdigit((unsigned char)tok[j])) { ++j; ++digits; }
+    }
+    if (digits == 0) return false;
+    if (j < n && (tok[j] == 'e' || tok[j] == 'E')) {
+      ++j;
+      if (j < n && (tok[j] == '+' || tok[j] == '-')) ++j;
+      size_t ed = 0;
+      while (j < n && std::isdigit((unsigned char)tok[j])) { ++j; ++ed; }
+      if (ed == 0) return false;
+    }
+    if (j != n) return false;
+  }
+  char *end = nullptr;
+  out = std::strtod(tok.c_str(), &end);  // correctly rounded, like dec2flt
+  return *end == '\0';
+}
+
 std::vector<std::vector<double>> parse_input_coordinates(const std::string &swarm_filename) {
   std::ifstream in(swarm_filename);
   if (!in) throw std::runtime_error("Error reading the input file");
@@ -201,9 +238,8 @@ std::vector<std::vector<double>> parse_input_coordinates(const std::string &swar
       size_t a = tok.find_first_not_of(" \t");
       size_t b = tok.find_last_not_of(" \t");
       tok = a == std::string::npos ? "" : tok.substr(a, b - a + 1);
-      char *end = nullptr;
-      const double v = std::strtod(tok.c_str(), &end);
-      if (tok.empty() || *end != '\0')
+      double v = 0.0;
+      if (!parse_f64_like_rust(tok, v))
         throw std::runtime_error("called `Result::unwrap()` on an `Err` value: ParseFloatError (start positions)");
       position.push_back(v);
       if (sp == std::string::npos) break;

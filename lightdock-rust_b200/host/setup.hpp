@@ -24,6 +24,8 @@ struct SetupFile {
 // Throws std::runtime_error with a serde-like message on malformed input or a missing required key.
 SetupFile read_setup_from_file(const std::string &path);
 std::vector<std::vector<double>> parse_input_coordinates(const std::string &swarm_filename);
+// `token.parse::<f64>()` as Rust accepts it (no hex floats, no nan(...), no white space); false = ParseFloatError.
+bool parse_f64_like_rust(const std::string &token, double &out);
 // 1-D (or any C-order) little-endian f64 .npy -> flat vector
 std::vector<double> read_npy_f64(const std::string &path);
 std::optional<int> parse_swarm_id(const std::string &path);  // :150-156

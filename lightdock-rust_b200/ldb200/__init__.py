@@ -17,7 +17,8 @@ DFIRE_TABLE_LEN = 169 * 169 * 20
 
 EXPORTS = ["ld_create", "ld_destroy", "ld_pose_len", "ld_score_batch", "ld_score_batch_device",
            "ld_score_batch_detail", "ld_transform_batch", "ld_get_stats", "ld_set_rec_splits",
-           "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version", "ld_set_path", "ld_path_info", "ld_device_count", "ld_score_batch_begin", "ld_score_batch_end"]
+           "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version", "ld_set_path", "ld_path_info", "ld_device_count", "ld_score_batch_begin", "ld_score_batch_end", "ld_get_stats_slot",
+           "ld_set_option"]
 
 PATH_AUTO, PATH_GENERIC, PATH_RIGID = 0, 1, 2
 
@@ -84,6 +85,16 @@ def load_library():
         lib.ld_path_info.argtypes = [C.c_void_p]
         lib.ld_path_info.restype = C.c_char_p
         lib.ld_probe_peaks.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ld_get_stats_slot.argtypes = [C.c_void_p, C.c_int32, C.POINTER(BatchStats)]
+        lib.ld_set_option.argtypes = [C.c_char_p, C.c_double]
+        # experiment knobs of the tools (tools/units_sweep.py, ...): forwarded through the API, the library itself
+        # never reads the environment
+        for env, key in (("LDB200_ROWS", "rigid_rows"), ("LDB200_CELL", "cell_size"),
+                         ("LDB200_UNITS_PER_SM", "units_per_sm")):
+            if os.environ.get(env):
+                _check(lib, lib.ld_set_option(key.encode(), float(os.environ[env])))
+        if os.environ.get("LDB200_PATH") == "generic":
+            _check(lib, lib.ld_set_option(b"default_path", float(PATH_GENERIC)))
         _lib = lib
     return _lib
 
@@ -231,13 +242,16 @@ class Scorer:
     def set_profiling(self, on):
         _check(self.lib, self.lib.ld_set_profiling(self.h, int(bool(on))))
 
-    def stats(self):
-        return handle_stats(self.lib, self.h)
+    def stats(self, slot=None):
+        return handle_stats(self.lib, self.h, slot)
 
 
-def handle_stats(lib, h):
+def handle_stats(lib, h, slot=None):
     s = BatchStats()
-    _check(lib, lib.ld_get_stats(h, C.byref(s)))
+    if slot is None:
+        _check(lib, lib.ld_get_stats(h, C.byref(s)))
+    else:
+        _check(lib, lib.ld_get_stats_slot(h, int(slot), C.byref(s)))
     return dict(n_poses=s.n_poses, pair_evals_bruteforce=s.pair_evals_bruteforce,
                 kernel_launches=s.kernel_launches, rec_splits=s.rec_splits, device_ms=s.device_ms,
                 transform_ms=s.transform_ms, pair_ms=s.pair_ms, finalize_ms=s.finalize_ms, path=s.path,

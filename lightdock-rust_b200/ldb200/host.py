@@ -39,6 +39,8 @@ def load_host_library():
         lib.ldh_slerp.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         lib.ldh_rotate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ldh_find_neighbors.argtypes = [C.c_int] + [C.c_void_p] * 5
+        lib.ldh_parse_f64.argtypes = [C.c_char_p, C.c_void_p]
+        lib.ldh_save_swarm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_char_p]
         lib.ldh_build_model.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p] + [C.c_void_p] * 10
         _lib = lib
     return _lib
@@ -64,6 +66,21 @@ def rotate(q, v):
     q, v, out = np.asarray(q, np.float64), np.asarray(v, np.float64), np.empty(3)
     load_host_library().ldh_rotate(q.ctypes.data, v.ctypes.data, out.ctypes.data)
     return out
+
+
+def parse_f64(token):
+    """Host-only: `token.parse::<f64>()` as the start-position reader applies it; None = ParseFloatError."""
+    v = C.c_double()
+    return v.value if load_host_library().ldh_parse_f64(token.encode(), C.addressof(v)) else None
+
+
+def save_swarm(rows, n_rec_anm, n_lig_anm, step, out_dir):
+    """Host-only: Swarm::save on a given state; rows [n][4 + pose_len] = luciferin, scoring, vision range,
+    neighbour count, pose."""
+    lib = load_host_library()
+    rows = np.ascontiguousarray(rows, np.float64)
+    if lib.ldh_save_swarm(rows.shape[0], n_rec_anm, n_lig_anm, rows.ctypes.data, step, out_dir.encode()):
+        raise _err(lib)
 
 
 def find_neighbors(xyz, luciferin, vision_range):

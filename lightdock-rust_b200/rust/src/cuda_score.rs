@@ -108,15 +108,6 @@ impl CudaScore {
         Box::new(CudaScore { handle, pose_len })
     }
 
-    /// All poses of a step in one launch: rows of `pose_len` f64 (tx,ty,tz,qw,qx,qy,qz, rec extents, lig extents).
-    pub fn energy_batch(&self, poses: &[f64]) -> Vec<f64> {
-        let n = poses.len() / self.pose_len;
-        let mut out = vec![0.0f64; n];
-        if unsafe { ld_score_batch(self.handle, n as i64, poses.as_ptr(), out.as_mut_ptr()) } != 0 {
-            panic!("lightdock_b200: {}", last_error());
-        }
-        out
-    }
 }
 
 impl Score for CudaScore {
@@ -127,7 +118,19 @@ impl Score for CudaScore {
         row.extend_from_slice(rec_nmodes);
         row.extend_from_slice(lig_nmodes);
         assert_eq!(row.len(), self.pose_len);
-        self.energy_batch(&row)[0]
+        self.energy_batch(&row, self.pose_len, rec_nmodes.len())[0]
+    }
+
+    /// Overrides the trait's provided method (scoring_trait.patch.rs): all poses of a step in ONE launch sequence.
+    /// Rows of `pose_len` f64 (tx,ty,tz,qw,qx,qy,qz, rec extents, lig extents); the library knows the split.
+    fn energy_batch(&self, poses: &[f64], pose_len: usize, _rec_num_anm: usize) -> Vec<f64> {
+        assert_eq!(pose_len, self.pose_len, "pose rows do not match the scoring object's pose length");
+        let n = poses.len() / self.pose_len;
+        let mut out = vec![0.0f64; n];
+        if unsafe { ld_score_batch(self.handle, n as i64, poses.as_ptr(), out.as_mut_ptr()) } != 0 {
+            panic!("lightdock_b200: {}", last_error());
+        }
+        out
     }
 }
 

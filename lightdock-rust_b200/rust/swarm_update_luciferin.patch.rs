@@ -1,7 +1,8 @@
-// Replacement body for Swarm::update_luciferin (src/swarm.rs:66-70).  `Score` gains a provided method
-//     fn energy_batch(&self, poses: &[f64], pose_len: usize) -> Vec<f64>   (default: loop over energy())
-// which CudaScore overrides with one ld_score_batch call.  Everything else in swarm.rs / glowworm.rs / lib.rs,
-// including the StdRng stream and the order of the `moved` bookkeeping, is untouched.
+// Replacement body for Swarm::update_luciferin (src/swarm.rs:66-70).  `Score` gains the provided method
+//     fn energy_batch(&self, poses: &[f64], pose_len: usize, rec_num_anm: usize) -> Vec<f64>
+// (scoring_trait.patch.rs; default: loop over energy()), which CudaScore overrides with one ld_score_batch call.
+// Every Glowworm field used here is `pub` upstream (src/glowworm.rs:6-26).  Everything else in swarm.rs /
+// glowworm.rs / lib.rs, including the StdRng stream and the order of the `moved` bookkeeping, is untouched.
 pub fn update_luciferin(&mut self) {
     if self.glowworms.is_empty() {
         return;
@@ -19,7 +20,8 @@ pub fn update_luciferin(&mut self) {
         }
     }
     let pose_len = if who.is_empty() { 7 } else { rows.len() / who.len() };
-    let scores = scoring.energy_batch(&rows, pose_len);
+    let rec_num_anm = self.glowworms[0].rec_nmodes.len();
+    let scores = scoring.energy_batch(&rows, pose_len, rec_num_anm);
     for (k, &i) in who.iter().enumerate() {
         self.glowworms[i].scoring = scores[k];
     }

@@ -70,3 +70,29 @@ def test_product_never_imports_the_oracle():
                         continue
                     assert "ld_oracle" not in s and "import oracle" not in s and "oracle/" not in s.replace("never imports oracle/", "").replace("never touches oracle/", ""), \
                         f"{os.path.join(dirpath, f)}: {s}"
+
+
+def test_rust_shim_sources_are_self_consistent():
+    """The Rust shim cannot be compiled in this image (no cargo/rustc); what can be checked is that it agrees with
+    itself and with the C header: one `energy_batch` signature in the trait patch, the impl and the call site, and
+    every `extern "C"` function it binds is exported by the library with the same number of arguments."""
+    import re
+    rust = os.path.join(ROOT, "lightdock-rust_b200", "rust")
+    trait = open(os.path.join(rust, "scoring_trait.patch.rs")).read()
+    impl = open(os.path.join(rust, "src", "cuda_score.rs")).read()
+    call = open(os.path.join(rust, "swarm_update_luciferin.patch.rs")).read()
+    sig = re.compile(r"fn energy_batch\(&self, poses: &\[f64\], pose_len: usize, _?rec_num_anm: usize\) -> Vec<f64>")
+    assert len(sig.findall(trait)) == 1 and len(sig.findall(impl)) == 1
+    assert "impl Score for CudaScore" in impl and impl.index("impl Score for CudaScore") < impl.index("fn energy_batch")
+    assert re.search(r"scoring\.energy_batch\(&rows, pose_len, rec_num_anm\)", call)
+    assert re.search(r"self\.energy_batch\(&row, self\.pose_len, rec_nmodes\.len\(\)\)", impl)
+    header = open(os.path.join(ROOT, "include", "lightdock_b200.h")).read()
+    block = impl[impl.index('extern "C" {'):]
+    block = block[:block.index("}\n")]
+    for name, args in re.findall(r"fn (ld_\w+)\(([^)]*)\)", block):
+        m = re.search(r"\b" + name + r"\(([^;]*)\);", header)
+        assert m, f"{name} is not declared in include/lightdock_b200.h"
+        n_rust = 0 if not args.strip() else args.count(":")
+        c_args = m.group(1).strip()
+        n_c = 0 if c_args in ("", "void") else c_args.count(",") + 1
+        assert n_rust == n_c, (name, args, c_args)

@@ -282,3 +282,43 @@ def test_rigid_huge_sparse_ligand_coarsens_the_grid():
     e_ref, d_ref = cx2.energy(poses, detail=True)
     assert_parity(e_gpu, d_gpu, e_ref, d_ref, O.DFIRE)
     assert d_ref["n_in_cutoff"].max() > 0
+
+
+@pytest.mark.parametrize("name,method", [("1k4c", O.DFIRE), ("1azp", O.DNA)])
+def test_device_calls_on_different_streams_do_not_race(name, method):
+    """ld_score_batch_device launches on the caller's stream but works in the handle's slot-0 buffers: the library
+    must order successive calls itself (two calls on different streams used to be free to overlap and
+    corrupt each other's partial sums / interface bitmaps)."""
+    import torch
+    from ldb200 import workload
+    cx, pos, _ = case(name, method)
+    sc = scorer_from_oracle(cx)
+    rng = np.random.default_rng(9)
+    if name == "1k4c":
+        a = np.ascontiguousarray(workload.synthetic_1k4c_swarms(12, 200).reshape(-1, 7))
+        b = a[::-1].copy()
+        b[:, :3] += rng.normal(0, 0.5, size=(len(b), 3))
+    else:
+        a = np.tile(pos, (6, 1)); a[:, :3] += rng.normal(0, 1.0, size=(len(a), 3))
+        b = np.tile(pos, (6, 1)); b[:, :3] += rng.normal(0, 1.0, size=(len(b), 3))
+    want_a, want_b = sc.energy(a), sc.energy(b)
+    dev = torch.device("cuda", 0)
+    da, db = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
+    ea = torch.zeros(len(a), dtype=torch.float64, device=dev)
+    eb = torch.zeros(len(b), dtype=torch.float64, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    for rep in range(3):
+        ea.zero_(); eb.zero_()
+        torch.cuda.synchronize()
+        sc.energy_device(len(a), da.data_ptr(), ea.data_ptr(), s1.cuda_stream)
+        sc.energy_device(len(b), db.data_ptr(), eb.data_ptr(), s2.cuda_stream)
+        sc.energy_device(len(a), da.data_ptr(), ea.data_ptr(), s1.cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(ea.cpu().numpy(), want_a), f"rep {rep}: stream 1 result corrupted"
+        assert np.array_equal(eb.cpu().numpy(), want_b), f"rep {rep}: stream 2 result corrupted"
+    # and a host-buffer call on the handle's own stream right after an asynchronous device call
+    sc.energy_device(len(a), da.data_ptr(), ea.data_ptr(), s1.cuda_stream)
+    assert np.array_equal(sc.energy(b), want_b)
+    torch.cuda.synchronize()
+    assert np.array_equal(ea.cpu().numpy(), want_a)

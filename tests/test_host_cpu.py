@@ -158,3 +158,30 @@ def test_neighbour_search_equals_the_reference_expression():
             xyz[17] = [0.0, 0.0, 0.0]; xyz[18] = [3.0, 4.0, 0.0]; vr[17] = 5.0; lum[17], lum[18] = 1.0, 2.0   # exactly 5
             xyz[19] = [0.0, 0.0, 0.0]; xyz[20] = [3.0, 4.0, 0.0]; vr[19] = np.nextafter(5.0, 6); lum[19], lum[20] = 1.0, 2.0
         assert host.find_neighbors(xyz, lum, vr) == literal(xyz, lum, vr), f"trial {trial}"
+
+
+def test_start_position_tokens_parse_like_rust():
+    """parse_input_coordinates (src/bin/lightdock-rust.rs:60-75) is `pos.trim().parse::<f64>().unwrap()`: the host
+    reader must accept exactly what Rust's f64::from_str accepts, not everything strtod does."""
+    ok = {"1.5": 1.5, "-2e3": -2000.0, "+.5": 0.5, "5.": 5.0, "1E-2": 0.01, "007": 7.0, "inf": float("inf"),
+          "-Infinity": float("-inf"), "-0": -0.0, "1e400": float("inf"), "4.9e-324": 5e-324}
+    for tok, want in ok.items():
+        got = host.parse_f64(tok)
+        assert got is not None and (got == want), (tok, got)
+    assert np.isnan(host.parse_f64("NaN")) and np.isnan(host.parse_f64("nan"))
+    for tok in ["", ".", "e5", "1e", "1e+", "0x10", "0x1p3", "nan(1)", "1_000", " 1", "1 ", "1,5", "--1", "infinit", "1.5f", "1d3"]:
+        assert host.parse_f64(tok) is None, tok
+
+
+def test_gso_out_prints_non_finite_values_like_rust(tmp_path):
+    """Swarm::save (src/swarm.rs:128-167) formats with {:.7} / {:.8} / {:.3}: Rust prints NaN, inf, -inf where C's
+    printf would print nan / -nan."""
+    rows = np.zeros((2, 4 + 7))
+    rows[0] = [float("nan"), float("inf"), 0.2, 3, 1.0, -2.5, float("-inf"), 1, 0, 0, float("nan")]
+    rows[1] = [5.0, -12.345678912, 5.0, 0, 1.23456789, 2, 3, 0.5, 0.5, 0.5, 0.5]
+    host.save_swarm(rows, 0, 0, 10, str(tmp_path))
+    lines = open(tmp_path / "gso_10.out").read().splitlines()
+    assert lines[0] == "#Coordinates  RecID  LigID  Luciferin  Neighbor's number  Vision Range  Scoring"
+    assert lines[1] == "(1.0000000, -2.5000000, -inf, 1.0000000, 0.0000000, 0.0000000, NaN)    0    0   NaN  3 0.200 inf"
+    assert lines[2] == ("(1.2345679, 2.0000000, 3.0000000, 0.5000000, 0.5000000, 0.5000000, 0.5000000)    0    0   "
+                        "5.00000000  0 5.000 -12.34567891")
