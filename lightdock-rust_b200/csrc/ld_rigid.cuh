@@ -1,5 +1,6 @@
-// ld_rigid.cuh — DFIRE pair loop (src/dfire.rs:325-345) for a RIGID ligand (no ligand ANM modes):
-// the fast path of the library, used by the 1k4c-class workloads.
+// ld_rigid.cuh — DFIRE pair loop (src/dfire.rs:325-345) in the LIGAND's frame: the fast path of the library.
+// Written for a rigid ligand (no ligand ANM modes: the 1k4c-class workloads); a ligand WITH ANM modes takes the
+// same kernel in its FLEX instantiation (end of this comment).
 //
 // Idea.  |r - (R l + t)| = |R^-1 (r - t) - l|: instead of moving the 3,268 ligand atoms of every pose
 // into the lab frame, each receptor atom is moved into the ligand's LOCAL frame (one 3x3 f64 product
@@ -26,6 +27,18 @@
 // is accepted only when it is PROVABLY the reference's FP64 decision; everything else (and every pair
 // in the thin 2.4-2.5 A shell around the 2.45 A interface edge) is re-evaluated with the reference's own
 // lab-frame FP64 arithmetic (rigid_exact_pair).  See the bound next to rigid_row().
+//
+// FLEX (ligand with ANM modes, src/dfire.rs:290-301).  In the ligand's frame atom j of pose p sits at
+// l_j + R^T D_j(p), D_j = sum_k mode_k[j] * extent_k(p): the ligand is no longer the same for every pose, but it moves
+// little.  flex_prep_kernel writes, per pose, the f32 ligand block (same layout as lig4) and the largest displacement
+// of every ligand tile; the cell lists are built with a per-tile SLACK added to the 15 A reach, so a list still holds
+// every tile that can be in range as long as the pose's tile displacements stay below the slacks.  A pose that exceeds
+// one (the first batch of a fresh handle, before the slacks have been learnt) is scored in the same launch by brute
+// force over all ligand tiles -- still exact -- and the host then grows the slacks and rebuilds the lists for the
+// following calls.  Each warp stages the block of the pose it is working on into its own slice of shared memory.
+// Because the lists now depend on the history of the handle, the per-lane summation order would too; the FLEX
+// instance therefore accumulates the table values in 64-bit FIXED POINT (table * 2^k rounded once, at ld_create):
+// integer sums are exact, so a pose's energy is bit-identical whatever the lists, the batch or the warp that took it.
 #pragma once
 #include "ld_kernels.cuh"
 
@@ -61,16 +74,25 @@ struct RigidComplex {
   float thr_out;                        // 225 + delta
   float half_minus_eps;                 // 0.5 - 2.5e-5 (the f32 evaluation error of t)
   float delta;                          // 1.02 * delta: eps_t = 1.02 * delta / sqrt(d2f) + 2.5e-5
+  // FLEX (ligand with ANM modes)
+  int flex;                             // 1: per-pose ligand blocks + slack lists + fixed-point sums
+  int n_lig_modes;
+  const double *lig_modes;              // [k][3][n_lig_pad] (exact path)
+  const long long *potx_fx;             // potx * fx_scale rounded to nearest: same layout
+  double fx_scale;                      // 2^k
+  const float *tile_slack;              // [n_lig_tiles] slack the current lists were built with
 };
 
-__host__ __device__ inline size_t rigid_smem_bytes(int n_lig_pad, int rows) {
-  return 128 + (size_t)n_lig_pad * 16 + (size_t)rows * RG_ROW_BYTES;
+// ligand copies: 1 (rigid: shared by the CTA) or one per warp (FLEX: each warp works on its own pose)
+__host__ __device__ inline size_t rigid_smem_bytes(int n_lig_pad, int rows, int lig_copies = 1) {
+  return 128 + (size_t)lig_copies * n_lig_pad * 16 + (size_t)rows * RG_ROW_BYTES;
 }
 
 extern __shared__ __align__(128) unsigned char smem_rigid[];
 // Loads at byte offsets of the kernel's dynamic shared memory (plain C++ so the scheduler may interleave the
 // eight pairs of an item; the array is known to live in shared memory, so these are LDS with 32-bit addresses).
 __device__ __forceinline__ double lds_f64(uint32_t off) { return *reinterpret_cast<const double *>(smem_rigid + off); }
+__device__ __forceinline__ long long lds_i64(uint32_t off) { return *reinterpret_cast<const long long *>(smem_rigid + off); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Per-pose quantities shared by the 100+ (group, pose) work items of a pose, computed once per batch:
@@ -102,6 +124,107 @@ __global__ void __launch_bounds__(256) rigid_prep_kernel(const double *poses, in
   o[12] = __ddiv_rn(qw, n2); o[13] = __ddiv_rn(-qx, n2); o[14] = __ddiv_rn(-qy, n2); o[15] = __ddiv_rn(-qz, n2);
 }
 
+// FLEX per-pose preparation: FLEX_PP poses per CTA so that a ligand atom's mode vectors are read once for all of them
+// (one pose per CTA re-read every mode of the ligand per pose from L2: that is what bounds transform_kernel).
+//   prep[p]        as rigid_prep_kernel
+//   lig4p[p][j]    ligand-frame position l_j + R^T D_j, D_j = sum_k mode_k[j] * extent_k (src/dfire.rs:290-301 gives
+//                  the lab-frame R l_j + t + D_j; the same point seen from the ligand's frame), rounded to f32, with
+//                  the table column offset in .w (copied from the static lig4)
+//   pose_flag[p]   1 if some ligand tile moved further than the slack its cell lists were built with
+//   need[t]        running maximum (over every pose ever prepared) of tile t's displacement, for the host to grow
+//                  the slacks; non-negative floats compared as integers
+// The displacements only feed the f32 coordinates and the (conservative, inflated) slack test; every decision that
+// could depend on their last bits is re-derived by rigid_exact_pair with the reference's own arithmetic.
+constexpr int FLEX_PP = 8;
+constexpr int FLEX_THREADS = 128;
+__global__ void __launch_bounds__(FLEX_THREADS)
+    flex_prep_kernel(const RigidComplex rc, const double *__restrict__ poses, int n_poses, double *__restrict__ prep,
+                     float4 *__restrict__ lig4p, unsigned char *__restrict__ pose_flag, int *__restrict__ need) {
+  extern __shared__ __align__(16) unsigned char smem_flex[];
+  double *sM = reinterpret_cast<double *>(smem_flex);                       // [FLEX_PP][16]
+  double *sE = sM + FLEX_PP * RG_PREP;                                      // [FLEX_PP][n_lig_modes]
+  int *sD = reinterpret_cast<int *>(sE + FLEX_PP * max(rc.n_lig_modes, 1)); // [FLEX_PP][n_lig_tiles] max |D|^2 (float bits)
+  __shared__ int s_flag[FLEX_PP];
+  const int p0 = blockIdx.x * FLEX_PP, np = min(FLEX_PP, n_poses - p0);
+  const int tid = threadIdx.x;
+  if (tid < np) {
+    const double *pose = poses + (size_t)(p0 + tid) * rc.pose_len;
+    const double tx = pose[0], ty = pose[1], tz = pose[2];
+    const double qw = pose[3], qx = pose[4], qy = pose[5], qz = pose[6];
+    const double n2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(qw, qw), __dmul_rn(qx, qx)), __dmul_rn(qy, qy)),
+                                __dmul_rn(qz, qz));
+    const double s2 = 2.0 / n2;
+    const double xx = qx * qx * s2, yy = qy * qy * s2, zz = qz * qz * s2;
+    const double xy = qx * qy * s2, xz = qx * qz * s2, yz = qy * qz * s2;
+    const double wx = qw * qx * s2, wy = qw * qy * s2, wz = qw * qz * s2;
+    const double m[9] = {1.0 - (yy + zz), xy + wz, xz - wy, xy - wz, 1.0 - (xx + zz), yz + wx, xz + wy, yz - wx,
+                         1.0 - (xx + yy)};
+    double *o = sM + tid * RG_PREP;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) o[i] = m[i];
+    o[9] = fma(m[0], tx, fma(m[1], ty, m[2] * tz));
+    o[10] = fma(m[3], tx, fma(m[4], ty, m[5] * tz));
+    o[11] = fma(m[6], tx, fma(m[7], ty, m[8] * tz));
+    o[12] = __ddiv_rn(qw, n2); o[13] = __ddiv_rn(-qx, n2); o[14] = __ddiv_rn(-qy, n2); o[15] = __ddiv_rn(-qz, n2);
+    double *g = prep + (size_t)(p0 + tid) * RG_PREP;
+#pragma unroll
+    for (int i = 0; i < RG_PREP; ++i) g[i] = o[i];
+    s_flag[tid] = 0;
+  }
+  for (int i = tid; i < np * rc.n_lig_modes; i += FLEX_THREADS) {
+    const int p = i / rc.n_lig_modes, k = i % rc.n_lig_modes;
+    sE[p * rc.n_lig_modes + k] = poses[(size_t)(p0 + p) * rc.pose_len + 7 + rc.n_rec_modes + k];
+  }
+  for (int i = tid; i < FLEX_PP * rc.n_lig_tiles; i += FLEX_THREADS) sD[i] = 0;
+  __syncthreads();
+  for (int j = tid; j < rc.n_lig_pad; j += FLEX_THREADS) {
+    const float4 st = rc.lig4[j];  // static block: pads at 1e6, .w = (float)(type * RG_SLOTS)
+    if (j >= rc.n_lig) {
+      for (int p = 0; p < np; ++p) lig4p[(size_t)(p0 + p) * rc.n_lig_pad + j] = st;
+      continue;
+    }
+    double dx[FLEX_PP], dy[FLEX_PP], dz[FLEX_PP];
+#pragma unroll
+    for (int p = 0; p < FLEX_PP; ++p) dx[p] = dy[p] = dz[p] = 0.0;
+    for (int k = 0; k < rc.n_lig_modes; ++k) {
+      const double *m = rc.lig_modes + (size_t)k * 3 * rc.n_lig_pad;
+      const double mx = m[j], my = m[rc.n_lig_pad + j], mz = m[2 * rc.n_lig_pad + j];
+#pragma unroll
+      for (int p = 0; p < FLEX_PP; ++p) {
+        const double e = sE[p * rc.n_lig_modes + k];
+        dx[p] = fma(mx, e, dx[p]); dy[p] = fma(my, e, dy[p]); dz[p] = fma(mz, e, dz[p]);
+      }
+    }
+    const double lx = rc.lig_x[j], ly = rc.lig_y[j], lz = rc.lig_z[j];
+#pragma unroll
+    for (int p = 0; p < FLEX_PP; ++p) {
+      if (p >= np) break;
+      const double *M = sM + p * RG_PREP;
+      const double x = lx + fma(M[0], dx[p], fma(M[1], dy[p], M[2] * dz[p]));
+      const double y = ly + fma(M[3], dx[p], fma(M[4], dy[p], M[5] * dz[p]));
+      const double z = lz + fma(M[6], dx[p], fma(M[7], dy[p], M[8] * dz[p]));
+      lig4p[(size_t)(p0 + p) * rc.n_lig_pad + j] = make_float4((float)x, (float)y, (float)z, st.w);
+      // |R^T D| = |D|; rounded up so the f32 value never understates it
+      const float d2 = __double2float_ru(fma(dz[p], dz[p], fma(dy[p], dy[p], dx[p] * dx[p])));
+      atomicMax(&sD[p * rc.n_lig_tiles + j / LIG_TILE], __float_as_int(d2));
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < np * rc.n_lig_tiles; i += FLEX_THREADS) {
+    const int p = i / rc.n_lig_tiles, t = i % rc.n_lig_tiles;
+    // displacement of the tile, inflated (f32 square root rounded up, plus the f32 rounding of the coordinates)
+    const float d = __fsqrt_ru(__int_as_float(sD[p * rc.n_lig_tiles + t])) * 1.000001f + 1.0e-5f;
+    if (d > rc.tile_slack[t]) s_flag[p] = 1;
+    if (__float_as_int(d) > need[t]) atomicMax(&need[t], __float_as_int(d));
+  }
+  __syncthreads();
+  if (tid < np) pose_flag[p0 + tid] = (unsigned char)s_flag[tid];
+}
+__host__ __device__ inline size_t flex_prep_smem(int n_lig_modes, int n_lig_tiles) {
+  return (size_t)FLEX_PP * RG_PREP * 8 + (size_t)FLEX_PP * (n_lig_modes > 1 ? n_lig_modes : 1) * 8 +
+         (size_t)FLEX_PP * n_lig_tiles * 4;
+}
+
 // The reference's arithmetic for ONE pair, lab frame, never fused: src/qt.rs:57-61,174-185 (rotate),
 // src/dfire.rs:286-288 (translate), :304-320 (receptor ANM), :331-342 (distance, bin, interface).
 // Returns -1 if the pair is outside the cut-off, else bin | (interface ? 32 : 0).
@@ -113,7 +236,14 @@ __device__ __noinline__ int rigid_exact_pair(const RigidComplex *__restrict__ rc
   const Quat qi = {prep[12], prep[13], prep[14], prep[15]};
   const Quat v = {0.0, rc.lig_x[j], rc.lig_y[j], rc.lig_z[j]};
   const Quat r = qmul(qmul(q, v), qi);
-  const double lx = __dadd_rn(r.x, tx), ly = __dadd_rn(r.y, ty), lz = __dadd_rn(r.z, tz);
+  double lx = __dadd_rn(r.x, tx), ly = __dadd_rn(r.y, ty), lz = __dadd_rn(r.z, tz);
+  for (int k = 0; k < rc.n_lig_modes; ++k) {  // src/dfire.rs:290-301
+    const double e = pose[7 + rc.n_rec_modes + k];
+    const double *m = rc.lig_modes + (size_t)k * 3 * rc.n_lig_pad;
+    lx = __dadd_rn(lx, __dmul_rn(m[j], e));
+    ly = __dadd_rn(ly, __dmul_rn(m[rc.n_lig_pad + j], e));
+    lz = __dadd_rn(lz, __dmul_rn(m[2 * rc.n_lig_pad + j], e));
+  }
   double x = rc.rec_x[ia], y = rc.rec_y[ia], z = rc.rec_z[ia];
   for (int k = 0; k < rc.n_rec_modes; ++k) {
     const double e = pose[7 + k];
@@ -149,12 +279,21 @@ __device__ __noinline__ int rigid_exact_pair(const RigidComplex *__restrict__ rc
 // that decides it in FP32 outside 6.0025 +- delta and with rigid_exact_pair inside.
 __device__ __forceinline__ float4 lds_f4(uint32_t off) { return *reinterpret_cast<const float4 *>(smem_rigid + off); }
 
-template <bool DETAIL>
+// Accumulator of the table values: f64 (rigid ligand: lists are static, so the order of a pose's additions is a
+// function of the pose alone) or 64-bit fixed point (FLEX: exact whatever the order).
+template <bool FLEX> struct RgAcc { typedef double type; };
+template <> struct RgAcc<true> { typedef long long type; };
+__device__ __forceinline__ void rg_add(double &acc, uint32_t addr) { acc = __dadd_rn(acc, lds_f64(addr)); }
+__device__ __forceinline__ void rg_add(long long &acc, uint32_t addr) { acc += lds_i64(addr); }
+__device__ __forceinline__ void rg_add_exact(double &acc, double v, double) { acc = __dadd_rn(acc, v); }
+__device__ __forceinline__ void rg_add_exact(long long &acc, double v, double scale) { acc += __double2ll_rn(v * scale); }
+
+template <bool DETAIL, bool FLEX>
 __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuffers &bb, uint32_t l4_addr,
                                           uint32_t lane_sw, bool active, int o, int lt, float rxf, float ryf,
-                                          float rzf, unsigned rowoff, int p, int pos_base, double &acc0,
-                                          double &acc1, unsigned &ifr_mask, const RigidComplex *rc_dev,
-                                          const double *prep) {
+                                          float rzf, unsigned rowoff, int p, int pos_base,
+                                          typename RgAcc<FLEX>::type &acc0, typename RgAcc<FLEX>::type &acc1,
+                                          unsigned &ifr_mask, const RigidComplex *rc_dev, const double *prep) {
   ld_pose_detail *dt = DETAIL ? reinterpret_cast<ld_pose_detail *>(bb.detail) + p : nullptr;
   const int lane = threadIdx.x & 31;
   const float ax = __shfl_sync(0xffffffffu, rxf, o), ay = __shfl_sync(0xffffffffu, ryf, o),
@@ -187,9 +326,8 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
     // MAGIC_BITS + type*RG_SLOTS + index in the mantissa -> one shift-add gives the byte address
     const uint32_t addr = ((uint32_t)__float_as_int(__fadd_rn(m, a.w)) << 3) + rb;
     if (fast) {
-      const double v = lds_f64(addr);
-      if (k & 1) acc1 = __dadd_rn(acc1, v);
-      else acc0 = __dadd_rn(acc0, v);
+      if (k & 1) rg_add(acc1, addr);
+      else rg_add(acc0, addr);
       if (DETAIL) {
         ++n_fast;
         atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[dfire_bin_fast(__float_as_int(m) - (int)RG_MAGIC_BITS)]),
@@ -221,7 +359,8 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
     if (n_fast) atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_in_cutoff), (unsigned long long)n_fast);
   }
   if (slow_bits) {  // rare: near a decision threshold, or closer than 2.5 A
-    double extra = 0.0;
+    typename RgAcc<FLEX>::type extra = 0;
+    const double fx_scale = FLEX ? rc_dev->fx_scale : 0.0;
     const int toff = rc_dev->rec_toff[pos_base + o];
     const double *pose = bb.poses + (size_t)p * rc_dev->pose_len;
     for (unsigned b = slow_bits; b; b &= b - 1) {
@@ -229,7 +368,7 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
       const int r = rigid_exact_pair(rc_dev, pose, prep, pos_base + o, j);
       if (DETAIL) atomicAdd(reinterpret_cast<unsigned long long *>(&dt->n_exact_fallback), 1ull);
       if (r >= 0) {
-        extra = __dadd_rn(extra, __ldg(rc_dev->pot + toff + rc_dev->lig_tb20[j] + (r & 31)));
+        rg_add_exact(extra, __ldg(rc_dev->pot + toff + rc_dev->lig_tb20[j] + (r & 31)), fx_scale);
         if (r & 32) {
           ifr_mask |= 1u << o;
           atomicOr(&bb.iface_lig[(size_t)p * bb.lig_words + (j >> 5)], 1u << (j & 31));
@@ -241,23 +380,42 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
         }
       }
     }
-    acc0 = __dadd_rn(acc0, extra);
+    if (FLEX) acc0 += extra;
+    else rg_add_exact(acc0, (double)extra, 0.0);
   }
 }
 
-template <bool DETAIL>
+__device__ __forceinline__ double rg_join(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ long long rg_join(long long a, long long b) { return a + b; }
+// Sum of a lane value over the warp in a fixed order (f64) / exactly (fixed point).
+__device__ __forceinline__ long long warp_sum(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// lig4p / pose_flag: FLEX only -- per-pose ligand blocks [n_poses][n_lig_pad] and 1 = "a tile moved further than its
+// slack: score this pose against every ligand tile" (both written by flex_prep_kernel).
+template <bool DETAIL, bool FLEX>
 __global__ void __launch_bounds__(RG_THREADS, 1)
     dfire_rigid_kernel(const RigidComplex rc, const BatchBuffers bb, int n_poses, int poses_per_unit, int n_chunks,
-                       unsigned *unit_counter, const RigidComplex *rc_dev, const double *prep_all) {
+                       unsigned *unit_counter, const RigidComplex *rc_dev, const double *prep_all,
+                       const float4 *__restrict__ lig4p, const unsigned char *__restrict__ pose_flag) {
+  typedef typename RgAcc<FLEX>::type acc_t;
   unsigned char *smem_raw = smem_rigid;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
   int *s_unit = reinterpret_cast<int *>(smem_raw + 8);
   int *s_pose_next = reinterpret_cast<int *>(smem_raw + 12);
-  float4 *l4 = reinterpret_cast<float4 *>(smem_raw + 128);
-  unsigned char *rows = smem_raw + 128 + (size_t)rc.n_lig_pad * 16;
   const int lane = threadIdx.x & 31;
-  const uint32_t l4_addr = 128u /* byte offset of l4 in smem_rigid */, lane_sw = (uint32_t)(lane & 7) << 4;
+  const int n_warps = blockDim.x >> 5;
+  // rigid: one ligand block for the CTA; FLEX: one per warp (the pose it is working on)
+  const uint32_t l4_addr = 128u + (FLEX ? (uint32_t)(threadIdx.x >> 5) * (uint32_t)rc.n_lig_pad * 16u : 0u);
+  float4 *l4 = reinterpret_cast<float4 *>(smem_raw + l4_addr);
+  unsigned char *rows = smem_raw + 128 + (size_t)(FLEX ? n_warps : 1) * rc.n_lig_pad * 16;
+  const uint32_t lane_sw = (uint32_t)(lane & 7) << 4;
   const int n_units = rc.n_groups * n_chunks;
+  const unsigned char *rows_src = FLEX ? reinterpret_cast<const unsigned char *>(rc.potx_fx)
+                                       : reinterpret_cast<const unsigned char *>(rc.potx);
 
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
@@ -265,7 +423,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
   }
   __syncthreads();
   uint32_t phase = 0;
-  bool lig_loaded = false;
+  bool lig_loaded = FLEX;  // FLEX: nothing static to load, every warp stages its pose's block itself
   int cur_g = -1;
   unsigned rowoff = 0u;
 
@@ -293,7 +451,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
         for (int r = 0; r < rc.rows_max; ++r) {
           const int ty = rc.group_types[g * RG_MAX_ROWS + r];
           if (ty >= 0)
-            bulk_g2s(rows + (size_t)r * RG_ROW_BYTES, rc.potx + (size_t)ty * (RG_ROW_BYTES / 8), RG_ROW_BYTES, bar);
+            bulk_g2s(rows + (size_t)r * RG_ROW_BYTES, rows_src + (size_t)ty * RG_ROW_BYTES, RG_ROW_BYTES, bar);
         }
       }
       const int ia = g * 32 + lane;
@@ -314,6 +472,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
       p = __shfl_sync(0xffffffffu, p, 0) + p0;
       if (p >= p1) break;
       const double *prep = prep_all + (size_t)p * RG_PREP;
+      bool brute = false;
+      if (FLEX) {
+        // this pose's ligand block (ligand frame, f32) into the warp's slice of shared memory
+        const float4 *src = lig4p + (size_t)p * rc.n_lig_pad;
+        for (int i = lane; i < rc.n_lig_pad; i += 32) l4[i] = __ldg(src + i);
+        brute = pose_flag[p] != 0;
+        __syncwarp();
+      }
       float fx, fy, fz;
       unsigned my_off;
       int my_n;
@@ -340,9 +506,16 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
           ce = __ldg(rc.cells + ((size_t)czi * rc.ny + cyi) * rc.nx + cxi);
         my_off = ce.x;
         my_n = (int)rowoff == -1 ? 0 : (int)ce.y;  // pad lanes own nothing
+        if (FLEX && brute) {  // every ligand tile, whatever the lists say: entry k of the "list" is tile k
+          my_off = 0u;
+          my_n = (int)rowoff == -1 ? 0 : rc.n_lig_tiles;
+        }
       }
+      auto tile_at = [&](unsigned idx) -> unsigned {
+        return (FLEX && brute) ? idx : (unsigned)__ldg(rc.cell_tiles + idx);
+      };
 
-      double acc0 = 0.0, acc1 = 0.0;
+      acc_t acc0 = 0, acc1 = 0;
       unsigned ifr_mask = 0u;
       // Work items = (owner lane, ligand tile) for every entry of the 32 lanes' cell lists, scored 32 at a time.
       //  (1) an owner with >= 32 entries fills whole rows on its own: lane i takes entry r*32 + i of its list;
@@ -375,7 +548,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
         }
         if (big_left > 0) {
           o_nxt = big_o;
-          lt_nxt = __ldg(rc.cell_tiles + big_off + lane);
+          lt_nxt = tile_at(big_off + lane);
           act_nxt = true;
           big_off += 32u;
           big_left -= 32;
@@ -394,7 +567,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
           o_nxt = oo;
           act_nxt = k < total;
           lt_nxt = 0u;
-          if (act_nxt) lt_nxt = __ldg(rc.cell_tiles + off + (unsigned)(k - (oo > 0 ? prev : 0)));
+          if (act_nxt) lt_nxt = tile_at(off + (unsigned)(k - (oo > 0 ? prev : 0)));
           k0 += 32;
           return true;
         }
@@ -404,14 +577,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
       while (have) {
         act = act_nxt; o = o_nxt; lt = lt_nxt;
         have = produce();
-        rigid_row<DETAIL>(rc, bb, l4_addr, lane_sw, act, o, (int)lt, fx, fy, fz, rowoff, p, pos_base, acc0, acc1,
-                          ifr_mask, rc_dev, prep);
+        rigid_row<DETAIL, FLEX>(rc, bb, l4_addr, lane_sw, act, o, (int)lt, fx, fy, fz, rowoff, p, pos_base, acc0,
+                                acc1, ifr_mask, rc_dev, prep);
       }
-      __syncwarp();
-      const double tsum = warp_sum(__dadd_rn(acc0, acc1));
+      __syncwarp();  // FLEX: also "every lane is done with this pose's ligand block"
+      const acc_t tsum = warp_sum(rg_join(acc0, acc1));
       const unsigned rbits = __reduce_or_sync(0xffffffffu, ifr_mask);
       if (lane == 0) {
-        bb.partials[(size_t)p * rc.n_groups + g] = tsum;
+        reinterpret_cast<acc_t *>(bb.partials)[(size_t)p * rc.n_groups + g] = tsum;  // both are 8 bytes
         bb.iface_rec[(size_t)p * rc.n_groups + g] = rbits;
       }
     }

@@ -89,7 +89,9 @@ def test_1azp_gso1_golden(golden_dir):
     # half a unit of the 8-decimal print precision + 1e-11 relative (the kernel's reciprocals carry 1e-12; the
     # north-star tolerance is 1e-6)
     assert (np.abs(e - score) <= 5.0e-9 + 1e-11 * np.abs(score)).all()
-    assert np.abs(np.round(e, 8) - score).max() <= 1e-8
+    # printed to 8 decimals: a value within 1e-10 of a rounding boundary may print one unit away
+    assert (np.abs(np.round(e, 8) - score) <= 1.0e-8 * (1 + 1e-6)).all()
+    assert (np.round(e, 8) == score).mean() >= 0.9
 
 
 def test_rec_splits_same_result():
