@@ -182,6 +182,13 @@ int ld_probe_peaks(int32_t device, double *fp64_nonfma_tflops, double *fp32_nonf
  * (0.5..8), "units_per_sm" rigid-kernel work units per SM, "default_path" LD_PATH_AUTO | LD_PATH_GENERIC. */
 int ld_set_option(const char *key, double value);
 
+/* Creates the CUDA context of `device` (cudaSetDevice + first runtime call).  Optional: ld_create does it too; a
+ * driver can call this from a helper thread at start-up so the 0.2-0.4 s of context creation overlap its file parsing. */
+int ld_init_device(int32_t device);
+/* Milliseconds ld_create spent: [0] CUDA context, [1] sorting + uploading the complex, [2] receptor groups of the
+ * ligand-frame path, [3] ligand-frame cell lists ([3] is refreshed by every FLEX rebuild). */
+int ld_get_create_ms(const ld_handle *h, double *out4);
+
 /* Number of CUDA devices visible to the process (0 if none / no driver): the multi-swarm driver shards swarms
  * over them (swarm s -> device s mod count). */
 int ld_device_count(void);

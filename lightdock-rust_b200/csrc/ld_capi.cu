@@ -3,6 +3,7 @@
 // There is no CPU fallback anywhere in this file: every entry point either runs the CUDA kernels
 // or returns an error.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -12,6 +13,7 @@
 #include <thread>
 #include <vector>
 
+#include "ld_cells.cuh"
 #include "ld_kernels.cuh"
 #include "ld_rigid.cuh"
 
@@ -55,6 +57,7 @@ struct Options {
   double cell_size = 1.0;         // ligand-frame cell size in A
   int units_per_sm = 16;          // rigid kernel: work units per SM
   int default_path = LD_PATH_AUTO;
+  int cells_on_host = 0;          // 1: build the ligand-frame cell lists with host threads (the round-1 builder; cross-check)
 };
 Options g_opt;
 }  // namespace
@@ -65,6 +68,7 @@ extern "C" int ld_set_option(const char *key, double value) {
   if (k == "rigid_rows") g_opt.rigid_rows = std::max(1, std::min(RG_MAX_ROWS, (int)value));
   else if (k == "cell_size") g_opt.cell_size = std::max(0.5, std::min(8.0, value));
   else if (k == "units_per_sm") g_opt.units_per_sm = std::max(1, (int)value);
+  else if (k == "cells_on_host") g_opt.cells_on_host = value != 0.0;
   else if (k == "default_path") {
     if (value != LD_PATH_AUTO && value != LD_PATH_GENERIC) return fail(LD_EINVAL, "ld_set_option: default_path is AUTO or GENERIC");
     g_opt.default_path = (int)value;
@@ -93,6 +97,9 @@ struct Workspace {
   unsigned *d_unit_counter = nullptr;   // rigid path: work-unit counter
   double *d_prep = nullptr;             // rigid path: [cap_prep][RG_PREP] per-pose rotation data
   int64_t cap_prep = 0;
+  float4 *d_lig4p = nullptr;            // FLEX: [cap_flex][n_lig_pad] per-pose ligand blocks (ligand frame, f32)
+  unsigned char *d_flag = nullptr;      // FLEX: [cap_flex] 1 = pose scored by brute force
+  int64_t cap_flex = 0;
   ld_batch_stats stats{};
   // profiling: events bracketing every kernel of the last call (4 per chunk)
   std::vector<cudaEvent_t> prof_events;
@@ -125,11 +132,25 @@ struct ld_handle {
   std::vector<int> rec_perm_r;          // grouped position -> original atom index, -1 = pad lane
   RigidComplex *d_rc = nullptr;         // device copy of rc for the rare exact path
   std::string rigid_info;
+  uint2 *d_cells = nullptr;             // ligand-frame cell lists (replaced when the FLEX slacks grow)
+  unsigned short *d_cell_tiles = nullptr;
+  std::vector<double> lig_sx, lig_sy, lig_sz;  // sorted ligand coordinates (cell-list rebuilds)
+  // FLEX: ligand with ANM modes on the ligand-frame path
+  bool flex = false;
+  int flex_warps = 0, flex_rebuilds = 0;
+  std::vector<float> tile_slack;        // per ligand tile: slack the current lists were built with
+  float *d_tile_slack = nullptr;
+  int *d_need = nullptr, *h_need = nullptr;  // running max of the tile displacements seen (float bits), device / pinned
   int max_smem_optin = 0;
   int sm_count = 0;
+  double create_ms[4] = {0, 0, 0, 0};   // ld_create: CUDA context, complex (sort + upload), rigid groups, cell lists
   bool profiling = false;
   bool prof_continue = false;  // second part of a two-part call: keep the first part's profiling events
 };
+
+static double ms_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
 
 template <typename T>
 static int upload(ld_handle *h, const std::vector<T> &v, const T **out) {
@@ -261,6 +282,7 @@ extern "C" int ld_destroy(ld_handle *h) {
     cudaFree(w.d_poses); cudaFree(w.d_energies); cudaFree(w.d_detail);
     cudaFree(w.d_lig_blocks); cudaFree(w.d_rec_blocks); cudaFree(w.d_partials);
     cudaFree(w.d_iface_rec); cudaFree(w.d_iface_lig); cudaFree(w.d_unit_counter); cudaFree(w.d_prep);
+    cudaFree(w.d_lig4p); cudaFree(w.d_flag);
     cudaFreeHost(w.h_poses); cudaFreeHost(w.h_energies);
     for (cudaEvent_t e : w.prof_events) cudaEventDestroy(e);
     if (w.ev0) cudaEventDestroy(w.ev0);
@@ -270,6 +292,8 @@ extern "C" int ld_destroy(ld_handle *h) {
   }
   for (void *p : h->owned) cudaFree(p);
   cudaFree(h->d_rc);
+  cudaFree(h->d_cells); cudaFree(h->d_cell_tiles); cudaFree(h->d_tile_slack); cudaFree(h->d_need);
+  cudaFreeHost(h->h_need);
   delete h;
   return LD_OK;
 }
@@ -312,18 +336,231 @@ static std::vector<RigidGroup> pack_groups(const ld_molecule_desc &m, int rows_m
   return groups;
 }
 
+// Ligand-frame cell lists: uniform grid over the ligand's bounding box grown by the cut-off (+ the largest tile slack);
+// a cell lists every ligand tile with an atom within 15 A + the tile's slack + 0.01 of the cell's box (0.01: f32 cell
+// assignment + the classification margin delta).  Slack is 0 for a rigid ligand; for a ligand with ANM modes it is how
+// far the tile's atoms may move in the ligand frame before a pose must be scored by brute force (ld_rigid.cuh, FLEX),
+// learnt from the poses the handle has seen.  Called by ld_create and again whenever the slacks grow.
+static int build_cells(ld_handle *h) {
+  const auto t_cells = std::chrono::steady_clock::now();
+  struct Stamp { ld_handle *h; std::chrono::steady_clock::time_point t; ~Stamp() { h->create_ms[3] = ms_since(t); } } stamp_{h, t_cells};
+  const DeviceComplex &cx = h->cx;
+  RigidComplex &rc = h->rc;
+  const std::vector<double> &LX = h->lig_sx, &LY = h->lig_sy, &LZ = h->lig_sz;
+  double cell = g_opt.cell_size;
+  double max_slack = 0.0;
+  for (float v : h->tile_slack) max_slack = std::max(max_slack, (double)v);
+  const double base_reach = 15.0 + 0.01, reach_max = base_reach + max_slack;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  const std::vector<double> *LC[3] = {&LX, &LY, &LZ};
+  for (int j = 0; j < cx.n_lig; ++j)
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = std::min(lo[d], (*LC[d])[j]);
+      hi[d] = std::max(hi[d], (*LC[d])[j]);
+    }
+  float g0[3];
+  int nc[3];
+  float inv_h = 0.f;
+  double hh = 0.0, maxabs = 0.0;
+  size_t ncell = 0;
+  // 1 A cells by default; a ligand so large that the grid would pass 2^24 cells (~270 MB of host scratch, ~130 MB
+  // of offsets on the device) gets proportionally coarser cells instead of losing the fast path
+  for (;; cell *= 1.25) {
+    inv_h = (float)(1.0 / cell);
+    hh = 1.0 / (double)inv_h;  // the cell size the device's (f - g0) * inv_h implies
+    maxabs = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      g0[d] = (float)(lo[d] - reach_max - 0.05);
+      nc[d] = (int)std::floor((hi[d] + reach_max + 0.05 - (double)g0[d]) / hh) + 1;
+      maxabs = std::max(maxabs, std::max(std::fabs((double)g0[d]), std::fabs((double)g0[d] + nc[d] * hh)));
+    }
+    ncell = (size_t)nc[0] * nc[1] * nc[2];
+    if (ncell <= ((size_t)1 << 24) || cell > 16.0) break;
+  }
+  if (ncell > ((size_t)1 << 24)) { h->rigid_info = "rigid path off: cell grid too large"; h->rigid_ok = false; return LD_OK; }
+  const double delta = 2.0e-4 + 1.3e-5 * maxabs;  // 2x the |d2f - dist_ref| bound derived at rigid_row()
+  if (!(delta < 0.01)) {
+    h->rigid_info = "rigid path off: ligand extent makes the FP32 margin too wide";
+    h->rigid_ok = false;
+    return LD_OK;
+  }
+  size_t total = 0, longest = 0, nonempty = 0;
+  std::vector<uint2> cells;
+  std::vector<unsigned short> flat;
+  uint2 *d_cells_new = nullptr;
+  unsigned short *d_flat_new = nullptr;
+  if (!g_opt.cells_on_host) {
+    // ---- device builder (ld_cells.cuh): count, scan, fill ----
+    CellGrid grid{};
+    for (int d = 0; d < 3; ++d) { grid.g0[d] = g0[d]; grid.nc[d] = nc[d]; }
+    grid.hh = hh;
+    grid.base_reach = base_reach;
+    std::vector<TileBox> boxes(cx.n_lig_tiles);
+    for (int t = 0; t < cx.n_lig_tiles; ++t) {
+      TileBox &b = boxes[t];
+      for (int d = 0; d < 3; ++d) { b.lo[d] = 3.0e38f; b.hi[d] = -3.0e38f; }
+      for (int j = t * LIG_TILE; j < std::min((t + 1) * LIG_TILE, cx.n_lig); ++j)
+        for (int d = 0; d < 3; ++d) {
+          const double v = (*LC[d])[j];
+          b.lo[d] = std::min(b.lo[d], std::nextafter((float)v, -3.0e38f));
+          b.hi[d] = std::max(b.hi[d], std::nextafter((float)v, 3.0e38f));
+        }
+    }
+    struct Tmp {  // scratch freed on every exit path
+      TileBox *boxes = nullptr; float *slack = nullptr; unsigned *counts = nullptr, *stats = nullptr;
+      unsigned long long *sums = nullptr;
+      ~Tmp() { cudaFree(boxes); cudaFree(slack); cudaFree(counts); cudaFree(stats); cudaFree(sums); }
+    } tmp;
+    const int n_blocks = (int)((ncell + (size_t)SCAN_THREADS * SCAN_ITEMS - 1) / ((size_t)SCAN_THREADS * SCAN_ITEMS));
+    CU(cudaMalloc(reinterpret_cast<void **>(&tmp.boxes), boxes.size() * sizeof(TileBox)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&tmp.slack), h->tile_slack.size() * sizeof(float)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&tmp.counts), ncell * sizeof(unsigned)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&tmp.stats), 2 * sizeof(unsigned)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&tmp.sums), ((size_t)n_blocks + 1) * sizeof(unsigned long long)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&d_cells_new), ncell * sizeof(uint2)));
+    CU(cudaMemcpy(tmp.boxes, boxes.data(), boxes.size() * sizeof(TileBox), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(tmp.slack, h->tile_slack.data(), h->tile_slack.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemset(tmp.stats, 0, 2 * sizeof(unsigned)));
+    const unsigned wgrid = (unsigned)((ncell + 127) / 128);
+    cells_walk_kernel<false><<<wgrid, 128>>>(grid, cx.lig_x, cx.lig_y, cx.lig_z, cx.n_lig, cx.n_lig_tiles, tmp.boxes,
+                                             tmp.slack, tmp.counts, nullptr, nullptr);
+    cells_scan_blocks_kernel<<<n_blocks, SCAN_THREADS>>>(tmp.counts, ncell, tmp.sums);
+    cells_scan_sums_kernel<<<1, 1024>>>(tmp.sums, n_blocks);
+    cells_scan_write_kernel<<<n_blocks, SCAN_THREADS>>>(tmp.counts, ncell, tmp.sums, d_cells_new, tmp.stats);
+    unsigned long long tot = 0;
+    unsigned st[2] = {0, 0};
+    CU(cudaMemcpy(&tot, tmp.sums + n_blocks, sizeof tot, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(st, tmp.stats, sizeof st, cudaMemcpyDeviceToHost));
+    total = (size_t)tot; nonempty = st[0]; longest = st[1];
+    if (total >= ((size_t)1 << 31)) {
+      cudaFree(d_cells_new);
+      h->rigid_info = "rigid path off: cell lists too large"; h->rigid_ok = false; return LD_OK;
+    }
+    CU(cudaMalloc(reinterpret_cast<void **>(&d_flat_new), std::max<size_t>(total, 1) * sizeof(unsigned short)));
+    cells_walk_kernel<true><<<wgrid, 128>>>(grid, cx.lig_x, cx.lig_y, cx.lig_z, cx.n_lig, cx.n_lig_tiles, tmp.boxes,
+                                            tmp.slack, nullptr, d_cells_new, d_flat_new);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+  } else {
+  // Two passes (count, fill) over z-slabs of the grid, one host thread per slab: a slab owns its cells, so
+  // the passes need no synchronisation, and tiles are visited in ascending order, so every list is sorted.
+  std::vector<unsigned> count(ncell, 0u);
+  std::vector<int> stamp(ncell, -1);
+  cells.assign(ncell, make_uint2(0u, 0u));
+  auto sweep = [&](int z_lo, int z_hi, bool fill) {
+    for (int t = 0; t < cx.n_lig_tiles; ++t) {
+      const double reach = base_reach + (double)h->tile_slack[t], reach2 = reach * reach;
+      for (int j = t * LIG_TILE; j < std::min((t + 1) * LIG_TILE, cx.n_lig); ++j) {
+        // the f32 value the kernel uses and the f64 one differ by < 1e-5: inside the slack
+        const double a[3] = {LX[j], LY[j], LZ[j]};
+        int c0[3], c1[3];
+        for (int d = 0; d < 3; ++d) {
+          c0[d] = std::max(0, (int)std::floor((a[d] - reach - (double)g0[d]) / hh));
+          c1[d] = std::min(nc[d] - 1, (int)std::floor((a[d] + reach - (double)g0[d]) / hh));
+        }
+        for (int cz = std::max(c0[2], z_lo); cz <= std::min(c1[2], z_hi - 1); ++cz) {
+          const double bz0 = (double)g0[2] + cz * hh, ez = std::max(0.0, std::max(bz0 - a[2], a[2] - (bz0 + hh)));
+          for (int cy = c0[1]; cy <= c1[1]; ++cy) {
+            const double by0 = (double)g0[1] + cy * hh, ey = std::max(0.0, std::max(by0 - a[1], a[1] - (by0 + hh)));
+            const double eyz = ez * ez + ey * ey;
+            if (eyz > reach2) continue;
+            size_t c = ((size_t)cz * nc[1] + cy) * nc[0] + c0[0];
+            for (int cxx = c0[0]; cxx <= c1[0]; ++cxx, ++c) {
+              const double bx0 = (double)g0[0] + cxx * hh, ex = std::max(0.0, std::max(bx0 - a[0], a[0] - (bx0 + hh)));
+              if (ex * ex + eyz > reach2 || stamp[c] == t) continue;
+              stamp[c] = t;
+              if (fill) flat[cells[c].x + count[c]] = (unsigned short)t;
+              ++count[c];
+            }
+          }
+        }
+      }
+    }
+  };
+  const int n_thr = std::max(1, std::min(std::min(16, nc[2]), (int)std::thread::hardware_concurrency()));
+  auto run_pass = [&](bool fill) {
+    std::vector<std::thread> pool;
+    for (int w = 0; w < n_thr; ++w)
+      pool.emplace_back(sweep, (int)((long)nc[2] * w / n_thr), (int)((long)nc[2] * (w + 1) / n_thr), fill);
+    for (auto &th : pool) th.join();
+  };
+  run_pass(false);
+  for (size_t c = 0; c < ncell; ++c) {
+    cells[c] = make_uint2((unsigned)total, count[c]);
+    total += count[c];
+    longest = std::max<size_t>(longest, count[c]);
+    nonempty += count[c] != 0;
+  }
+  if (total >= ((size_t)1 << 31)) { h->rigid_info = "rigid path off: cell lists too large"; h->rigid_ok = false; return LD_OK; }
+  flat.assign(std::max<size_t>(total, 1), 0);
+  std::fill(count.begin(), count.end(), 0u);
+  std::fill(stamp.begin(), stamp.end(), -1);
+  run_pass(true);
+    CU(cudaMalloc(reinterpret_cast<void **>(&d_cells_new), cells.size() * sizeof(uint2)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&d_flat_new), flat.size() * sizeof(unsigned short)));
+    CU(cudaMemcpy(d_cells_new, cells.data(), cells.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_flat_new, flat.data(), flat.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+  }
+
+  // replace the device copies (a rebuild happens only with every stream of the handle idle: grow_flex_slack)
+  cudaFree(h->d_cells); cudaFree(h->d_cell_tiles);
+  h->d_cells = d_cells_new; h->d_cell_tiles = d_flat_new;
+  if (h->d_tile_slack)
+    CU(cudaMemcpy(h->d_tile_slack, h->tile_slack.data(), h->tile_slack.size() * sizeof(float), cudaMemcpyHostToDevice));
+  rc.cells = h->d_cells; rc.cell_tiles = h->d_cell_tiles;
+  rc.gx0 = g0[0]; rc.gy0 = g0[1]; rc.gz0 = g0[2]; rc.inv_h = inv_h;
+  rc.nx = nc[0]; rc.ny = nc[1]; rc.nz = nc[2];
+  rc.thr_out = (float)(225.0 + delta);
+  rc.half_minus_eps = (float)(0.5 - 2.5e-5);
+  rc.delta = (float)(1.02 * delta);
+  if (h->d_rc) CU(cudaMemcpy(h->d_rc, &rc, sizeof(RigidComplex), cudaMemcpyHostToDevice));
+  char buf[640];
+  snprintf(buf, sizeof buf,
+           "rigid path on%s: %d receptor groups (%.1f atoms/group, <=%d table rows each), cell %.2f A, grid %dx%dx%d, "
+           "%zu non-empty cells, %zu list entries (longest %zu), delta %.2e, smem %zu B",
+           h->flex ? " (flexible ligand: per-pose ligand blocks, slack lists, fixed-point sums)" : "", rc.n_groups,
+           (double)cx.n_rec / rc.n_groups, rc.rows_max, hh, nc[0], nc[1], nc[2], nonempty, total, longest, delta,
+           rigid_smem_bytes(cx.n_lig_pad, rc.rows_max, h->flex ? h->flex_warps : 1));
+  h->rigid_info = buf;
+  if (h->flex) {
+    snprintf(buf, sizeof buf, ", %d warps per CTA, tile slack max %.2f A (rebuilt %d times)", h->flex_warps, max_slack,
+             h->flex_rebuilds);
+    h->rigid_info += buf;
+  }
+  return LD_OK;
+}
+
 static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMol &L) {
   const DeviceComplex &cx = h->cx;
   const ld_molecule_desc &R = desc->receptor;
   h->rigid_ok = false;
+  h->flex = false;
   if (cx.method != 0) { h->rigid_info = "rigid path off: not DFIRE"; return LD_OK; }
-  if (cx.n_lig_modes > 0) { h->rigid_info = "rigid path off: the ligand has ANM modes"; return LD_OK; }
   if (cx.n_rec == 0 || cx.n_lig == 0) { h->rigid_info = "rigid path off: empty partner"; return LD_OK; }
   if (cx.n_lig_tiles > 65535) { h->rigid_info = "rigid path off: ligand tile ids exceed 16 bits"; return LD_OK; }
-  const long avail = (long)h->max_smem_optin - (long)rigid_smem_bytes(cx.n_lig_pad, 0);
-  int rows_max = (int)std::min<long>(RG_MAX_ROWS, avail / RG_ROW_BYTES);
-  rows_max = std::max(1, std::min(rows_max, g_opt.rigid_rows));
-  if (rows_max < 1) { h->rigid_info = "rigid path off: ligand + one table row exceed shared memory"; return LD_OK; }
+  int rows_max = 0;
+  if (cx.n_lig_modes == 0) {
+    const long avail = (long)h->max_smem_optin - (long)rigid_smem_bytes(cx.n_lig_pad, 0);
+    rows_max = (int)std::min<long>(RG_MAX_ROWS, avail / RG_ROW_BYTES);
+    rows_max = std::min(rows_max, g_opt.rigid_rows);
+    if (rows_max < 1) { h->rigid_info = "rigid path off: ligand + one table row exceed shared memory"; return LD_OK; }
+  } else {
+    // FLEX: one ligand block per warp next to the table rows; prefer many rows (fewer, fuller receptor groups) as
+    // long as enough warps fit to keep the SM busy
+    const long lig_bytes = (long)cx.n_lig_pad * 16;
+    int best_w = 0;
+    for (int r = std::min(RG_MAX_ROWS, g_opt.rigid_rows); r >= 1 && rows_max == 0; --r) {
+      const long avail = (long)h->max_smem_optin - 128 - (long)r * RG_ROW_BYTES;
+      const int w = (int)std::min<long>(RG_WARPS, avail / lig_bytes);
+      if (w >= 12 || (r <= 2 && w >= 8)) { rows_max = r; best_w = w; }
+    }
+    if (rows_max == 0) {
+      h->rigid_info = "rigid path off: the ligand has ANM modes and its per-warp blocks do not fit in shared memory";
+      return LD_OK;
+    }
+    h->flex = true;
+    h->flex_warps = best_w;
+  }
 
   RigidComplex &rc = h->rc;
   rc = RigidComplex{};
@@ -373,112 +610,23 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
       l4[j] = make_float4(1.0e6f, 1.0e6f, 1.0e6f, 0.f);
     }
   }
-
-  // cell grid over the ligand's bounding box grown by the cut-off; a cell lists every tile with an atom
-  // within 15 A + slack of the cell's box (slack: f32 cell assignment + the classification margin delta)
-  double cell = g_opt.cell_size;
-  const double reach = 15.0 + 0.01;
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-  const std::vector<double> *LC[3] = {&L.x, &L.y, &L.z};
-  for (int j = 0; j < cx.n_lig; ++j)
-    for (int d = 0; d < 3; ++d) {
-      lo[d] = std::min(lo[d], (*LC[d])[j]);
-      hi[d] = std::max(hi[d], (*LC[d])[j]);
-    }
-  float g0[3];
-  int nc[3];
-  float inv_h = 0.f;
-  double hh = 0.0, maxabs = 0.0;
-  size_t ncell = 0;
-  // 1 A cells by default; a ligand so large that the grid would pass 2^24 cells (~270 MB of host scratch, ~130 MB
-  // of offsets on the device) gets proportionally coarser cells instead of losing the fast path
-  for (;; cell *= 1.25) {
-    inv_h = (float)(1.0 / cell);
-    hh = 1.0 / (double)inv_h;  // the cell size the device's (f - g0) * inv_h implies
-    maxabs = 0.0;
-    for (int d = 0; d < 3; ++d) {
-      g0[d] = (float)(lo[d] - reach - 0.05);
-      nc[d] = (int)std::floor((hi[d] + reach + 0.05 - (double)g0[d]) / hh) + 1;
-      maxabs = std::max(maxabs, std::max(std::fabs((double)g0[d]), std::fabs((double)g0[d] + nc[d] * hh)));
-    }
-    ncell = (size_t)nc[0] * nc[1] * nc[2];
-    if (ncell <= ((size_t)1 << 24) || cell > 16.0) break;
-  }
-  if (ncell > ((size_t)1 << 24)) { h->rigid_info = "rigid path off: cell grid too large"; return LD_OK; }
-  // Two passes (count, fill) over z-slabs of the grid, one host thread per slab: a slab owns its cells, so
-  // the passes need no synchronisation, and tiles are visited in ascending order, so every list is sorted.
-  std::vector<unsigned> count(ncell, 0u);
-  std::vector<int> stamp(ncell, -1);
-  std::vector<uint2> cells(ncell);
-  std::vector<unsigned short> flat;
-  const double reach2 = reach * reach;
-  auto sweep = [&](int z_lo, int z_hi, bool fill) {
-    for (int t = 0; t < cx.n_lig_tiles; ++t)
-      for (int j = t * LIG_TILE; j < std::min((t + 1) * LIG_TILE, cx.n_lig); ++j) {
-        // the f32 value the kernel uses and the f64 one differ by < 1e-5: inside the slack
-        const double a[3] = {L.x[j], L.y[j], L.z[j]};
-        int c0[3], c1[3];
-        for (int d = 0; d < 3; ++d) {
-          c0[d] = std::max(0, (int)std::floor((a[d] - reach - (double)g0[d]) / hh));
-          c1[d] = std::min(nc[d] - 1, (int)std::floor((a[d] + reach - (double)g0[d]) / hh));
-        }
-        for (int cz = std::max(c0[2], z_lo); cz <= std::min(c1[2], z_hi - 1); ++cz) {
-          const double bz0 = (double)g0[2] + cz * hh, ez = std::max(0.0, std::max(bz0 - a[2], a[2] - (bz0 + hh)));
-          for (int cy = c0[1]; cy <= c1[1]; ++cy) {
-            const double by0 = (double)g0[1] + cy * hh, ey = std::max(0.0, std::max(by0 - a[1], a[1] - (by0 + hh)));
-            const double eyz = ez * ez + ey * ey;
-            if (eyz > reach2) continue;
-            size_t c = ((size_t)cz * nc[1] + cy) * nc[0] + c0[0];
-            for (int cxx = c0[0]; cxx <= c1[0]; ++cxx, ++c) {
-              const double bx0 = (double)g0[0] + cxx * hh, ex = std::max(0.0, std::max(bx0 - a[0], a[0] - (bx0 + hh)));
-              if (ex * ex + eyz > reach2 || stamp[c] == t) continue;
-              stamp[c] = t;
-              if (fill) flat[cells[c].x + count[c]] = (unsigned short)t;
-              ++count[c];
-            }
-          }
-        }
-      }
-  };
-  const int n_thr = std::max(1, std::min(std::min(16, nc[2]), (int)std::thread::hardware_concurrency()));
-  auto run_pass = [&](bool fill) {
-    std::vector<std::thread> pool;
-    for (int w = 0; w < n_thr; ++w)
-      pool.emplace_back(sweep, (int)((long)nc[2] * w / n_thr), (int)((long)nc[2] * (w + 1) / n_thr), fill);
-    for (auto &th : pool) th.join();
-  };
-  run_pass(false);
-  size_t total = 0, longest = 0, nonempty = 0;
-  for (size_t c = 0; c < ncell; ++c) {
-    cells[c] = make_uint2((unsigned)total, count[c]);
-    total += count[c];
-    longest = std::max<size_t>(longest, count[c]);
-    nonempty += count[c] != 0;
-  }
-  if (total >= ((size_t)1 << 31)) { h->rigid_info = "rigid path off: cell lists too large"; return LD_OK; }
-  flat.assign(std::max<size_t>(total, 1), 0);
-  std::fill(count.begin(), count.end(), 0u);
-  std::fill(stamp.begin(), stamp.end(), -1);
-  run_pass(true);
+  h->lig_sx = L.x; h->lig_sy = L.y; h->lig_sz = L.z;
+  h->tile_slack.assign(cx.n_lig_tiles, 0.f);
 
   int rcode;
 #define UPR(vec, field) \
   if ((rcode = upload(h, vec, &rc.field)) != LD_OK) return rcode
   UPR(x, rec_x); UPR(y, rec_y); UPR(z, rec_z); UPR(slot, rec_slot); UPR(toff, rec_toff);
   UPR(gtypes, group_types); UPR(order, group_order); UPR(modes, rec_modes);
-  UPR(l4, lig4); UPR(cells, cells); UPR(flat, cell_tiles);
+  UPR(l4, lig4);
 #undef UPR
   rc.n_groups = ng; rc.n_rec_pos = npos;
   rc.n_lig = cx.n_lig; rc.n_lig_pad = cx.n_lig_pad; rc.n_lig_tiles = cx.n_lig_tiles;
   rc.n_rec_modes = nrm; rc.pose_len = cx.pose_len; rc.rows_max = rows_max;
   rc.lig_x = cx.lig_x; rc.lig_y = cx.lig_y; rc.lig_z = cx.lig_z; rc.lig_tb20 = cx.lig_tb20; rc.pot = cx.pot; rc.potx = cx.potx;
-  rc.gx0 = g0[0]; rc.gy0 = g0[1]; rc.gz0 = g0[2]; rc.inv_h = inv_h;
-  rc.nx = nc[0]; rc.ny = nc[1]; rc.nz = nc[2];
-  const double delta = 2.0e-4 + 1.3e-5 * maxabs;  // 2x the |d2f - dist_ref| bound derived at rigid_row()
-  rc.thr_out = (float)(225.0 + delta);
-  rc.half_minus_eps = (float)(0.5 - 2.5e-5);
-  rc.delta = (float)(1.02 * delta);
-  if (!(delta < 0.01)) { h->rigid_info = "rigid path off: ligand extent makes the FP32 margin too wide"; return LD_OK; }
+  rc.flex = h->flex ? 1 : 0;
+  rc.n_lig_modes = cx.n_lig_modes;
+  rc.lig_modes = cx.lig_modes;
 
   // what finalize_kernel sees: groups play the role of receptor tiles
   h->cxr = cx;
@@ -486,22 +634,83 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   h->cxr.n_rec_pad = npos;
   if ((rcode = upload(h, rst_idx, &h->cxr.rec_rst_idx)) != LD_OK) return rcode;
   if ((rcode = upload(h, mem_idx, &h->cxr.membrane_idx)) != LD_OK) return rcode;
+  if (h->flex) {
+    // fixed-point copy of the re-indexed table: scale 2^k with 32 atoms x n_lig_pad pairs x max|value| x 2^k < 2^61, so
+    // that the sum over one (receptor group, pose) cannot overflow; finalize_kernel converts each group's sum back
+    // and adds the groups in order
+    const size_t n_potx = 169 * (size_t)(RG_ROW_BYTES / 8);
+    std::vector<double> potx(n_potx);
+    CU(cudaMemcpy(potx.data(), cx.potx, n_potx * sizeof(double), cudaMemcpyDeviceToHost));
+    double vmax = 1.0;
+    for (double v : potx) vmax = std::max(vmax, std::fabs(v));
+    const int k = 61 - (int)std::ceil(std::log2(32.0 * cx.n_lig_pad * vmax));
+    if (k < 20) { h->rigid_info = "rigid path off: table values too large for the fixed-point sums"; h->flex = false; return LD_OK; }
+    rc.fx_scale = std::ldexp(1.0, k);
+    std::vector<long long> fx(n_potx);
+    for (size_t i = 0; i < n_potx; ++i) fx[i] = std::llrint(potx[i] * rc.fx_scale);
+    if ((rcode = upload(h, fx, &rc.potx_fx)) != LD_OK) return rcode;
+    h->cxr.fx_inv_scale = 1.0 / rc.fx_scale;
+    CU(cudaMalloc(reinterpret_cast<void **>(&h->d_tile_slack), cx.n_lig_tiles * sizeof(float)));
+    CU(cudaMalloc(reinterpret_cast<void **>(&h->d_need), cx.n_lig_tiles * sizeof(int)));
+    CU(cudaMemset(h->d_need, 0, cx.n_lig_tiles * sizeof(int)));
+    CU(cudaHostAlloc(reinterpret_cast<void **>(&h->h_need), cx.n_lig_tiles * sizeof(int), cudaHostAllocDefault));
+    rc.tile_slack = h->d_tile_slack;
+    CU(cudaFuncSetAttribute(dfire_rigid_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+    CU(cudaFuncSetAttribute(dfire_rigid_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  } else {
+    CU(cudaFuncSetAttribute(dfire_rigid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+    CU(cudaFuncSetAttribute(dfire_rigid_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
+  }
   CU(cudaMalloc(reinterpret_cast<void **>(&h->d_rc), sizeof(RigidComplex)));
-  CU(cudaMemcpy(h->d_rc, &rc, sizeof(RigidComplex), cudaMemcpyHostToDevice));
-  CU(cudaFuncSetAttribute(dfire_rigid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  CU(cudaFuncSetAttribute(dfire_rigid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  char buf[512];
-  snprintf(buf, sizeof buf,
-           "rigid path on: %d receptor groups (%.1f atoms/group, <=%d table rows each), cell %.2f A, grid %dx%dx%d, "
-           "%zu non-empty cells, %zu list entries (longest %zu), delta %.2e, smem %zu B",
-           ng, (double)cx.n_rec / ng, rows_max, hh, nc[0], nc[1], nc[2], nonempty, total, longest, delta,
-           rigid_smem_bytes(cx.n_lig_pad, rows_max));
-  h->rigid_info = buf;
   h->rigid_ok = true;
+  return build_cells(h);  // fills the grid fields of rc, uploads d_rc, clears rigid_ok if the grid cannot be built
+}
+
+// FLEX: after a call has completed, grow the tile slacks to what the poses seen so far need (with head-room, so a
+// drifting swarm does not trigger a rebuild per step) and rebuild the cell lists.  Every stream of the handle must be
+// idle: the lists are replaced in place.  Results never depend on this: a pose whose tiles exceed the slacks is scored
+// by brute force in the same launch, and FLEX sums are exact integers.
+static int grow_flex_slack(ld_handle *h) {
+  if (!h->flex || !h->rigid_ok) return LD_OK;
+  bool grow = false;
+  for (int t = 0; t < h->cx.n_lig_tiles; ++t) {
+    float need;
+    std::memcpy(&need, &h->h_need[t], sizeof need);
+    if (need > h->tile_slack[t]) grow = true;
+  }
+  if (!grow) return LD_OK;
+  for (Workspace &w : h->ws)
+    if (w.stream) CU(cudaStreamSynchronize(w.stream));
+  CU(cudaDeviceSynchronize());  // device-API calls may sit on caller streams
+  for (int t = 0; t < h->cx.n_lig_tiles; ++t) {
+    float need;
+    std::memcpy(&need, &h->h_need[t], sizeof need);
+    if (need > h->tile_slack[t]) h->tile_slack[t] = need * 1.25f + 0.25f;
+  }
+  ++h->flex_rebuilds;
+  return build_cells(h);
+}
+
+extern "C" int ld_init_device(int32_t device) {
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(LD_ECUDA, std::string("no CUDA device available (there is no CPU fallback): ") +
+                              (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+  if (device < 0 || device >= ndev) return fail(LD_EINVAL, "device ordinal out of range");
+  CU(cudaSetDevice(device));
+  CU(cudaFree(nullptr));  // forces the primary context into existence
+  return LD_OK;
+}
+
+extern "C" int ld_get_create_ms(const ld_handle *h, double *out4) {
+  if (!h || !out4) return fail(LD_EINVAL, "ld_get_create_ms: NULL argument");
+  for (int i = 0; i < 4; ++i) out4[i] = h->create_ms[i];
   return LD_OK;
 }
 
 static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
+  const auto t_start = std::chrono::steady_clock::now();
   const int method = desc->method == LD_METHOD_DFIRE ? 0 : 1;
   h->device = desc->device;
   h->use_anm = desc->use_anm ? 1 : 0;
@@ -512,6 +721,9 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
   if (desc->device < 0 || desc->device >= ndev) return fail(LD_EINVAL, "device ordinal out of range");
   CU(cudaSetDevice(desc->device));
+  CU(cudaFree(nullptr));
+  h->create_ms[0] = ms_since(t_start);
+  const auto t_complex = std::chrono::steady_clock::now();
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, desc->device));
   if (prop.major < 10)
@@ -651,7 +863,11 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
   CU(cudaFuncSetAttribute(dna_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CU(cudaFuncSetAttribute(dna_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   h->path_mode = g_opt.default_path;
-  return build_rigid(desc, h, L);
+  h->create_ms[1] = ms_since(t_complex);
+  const auto t_rigid = std::chrono::steady_clock::now();
+  const int rrc = build_rigid(desc, h, L);
+  h->create_ms[2] = ms_since(t_rigid) - h->create_ms[3];
+  return rrc;
 }
 
 extern "C" int ld_create(const ld_complex_desc *desc, ld_handle **out) {
@@ -780,6 +996,8 @@ static int choose_splits(const ld_handle *h, int64_t n) {
 static bool use_rigid(const ld_handle *h) { return h->rigid_ok && h->path_mode != LD_PATH_GENERIC; }
 
 static int64_t chunk_limit(const ld_handle *h, bool rigid) {
+  if (rigid && h->flex)  // per-pose f32 ligand blocks, read once per receptor group: keep a chunk's worth L2-resident
+    return std::max<int64_t>(256, std::min<int64_t>((int64_t)1 << 20, ((int64_t)64 << 20) / ((int64_t)h->cx.n_lig_pad * 16)));
   if (rigid) return (int64_t)1 << 20;  // no per-pose coordinate blocks on this path (~2 KB per pose)
   const size_t per_pose = h->lig_block + h->rec_block + 64;
   int64_t c = (int64_t)((size_t)1 << 30) / (int64_t)per_pose;  // <= 1 GiB of coordinate blocks in flight
@@ -873,27 +1091,48 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
         if ((rc = regrow(&h->w->d_prep, (size_t)nc * RG_PREP)) != LD_OK) return rc;
         h->w->cap_prep = nc;
       }
+      if (h->flex && nc > h->w->cap_flex) {
+        if ((rc = regrow(&h->w->d_lig4p, (size_t)nc * cx.n_lig_pad)) != LD_OK) return rc;
+        if ((rc = regrow(&h->w->d_flag, (size_t)nc)) != LD_OK) return rc;
+        h->w->cap_flex = nc;
+      }
       if ((rc = prof_mark(h, st)) != LD_OK) return rc;
-      // per-pose rotation data (the only "transform" on this path: nothing is moved per atom)
-      rigid_prep_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(bb.poses, (int)nc, cx.pose_len, h->w->d_prep);
+      // per-pose rotation data (the only "transform" on this path for a rigid ligand: nothing is moved per atom);
+      // FLEX adds the per-pose f32 ligand block and the slack test
+      if (h->flex)
+        flex_prep_kernel<<<(unsigned)((nc + FLEX_PP - 1) / FLEX_PP), FLEX_THREADS,
+                           flex_prep_smem(cx.n_lig_modes, cx.n_lig_tiles), st>>>(rg, bb.poses, (int)nc, h->w->d_prep,
+                                                                                 h->w->d_lig4p, h->w->d_flag, h->d_need);
+      else
+        rigid_prep_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(bb.poses, (int)nc, cx.pose_len, h->w->d_prep);
       ++launches;
       if ((rc = prof_mark(h, st)) != LD_OK) return rc;
       CU(cudaMemsetAsync(h->w->d_iface_lig, 0, (size_t)nc * lig_words * sizeof(unsigned), st));
       CU(cudaMemsetAsync(h->w->d_unit_counter, 0, sizeof(unsigned), st));
       // work units: (group, range of poses); ~16 units per SM and group changes kept rare
       const int units_per_sm = g_opt.units_per_sm;
+      const int cta_warps = h->flex ? h->flex_warps : RG_WARPS;
       int64_t ppu = (nc * rg.n_groups + (int64_t)h->sm_count * units_per_sm - 1) / ((int64_t)h->sm_count * units_per_sm);
-      ppu = std::max<int64_t>(RG_WARPS, std::min<int64_t>(ppu, 1024));
+      ppu = std::max<int64_t>(cta_warps, std::min<int64_t>(ppu, 1024));
       const int n_chunks = (int)((nc + ppu - 1) / ppu);
       const int64_t n_units = (int64_t)n_chunks * rg.n_groups;
       const unsigned grid = (unsigned)std::min<int64_t>(h->sm_count, n_units);
-      const size_t smem = rigid_smem_bytes(rg.n_lig_pad, rg.rows_max);
-      if (detail)
-        dfire_rigid_kernel<true><<<grid, RG_THREADS, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->w->d_unit_counter,
-                                                             h->d_rc, h->w->d_prep);
-      else
-        dfire_rigid_kernel<false><<<grid, RG_THREADS, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->w->d_unit_counter,
-                                                             h->d_rc, h->w->d_prep);
+      const size_t smem = rigid_smem_bytes(rg.n_lig_pad, rg.rows_max, h->flex ? cta_warps : 1);
+      const unsigned threads = (unsigned)cta_warps * 32u;
+      if (h->flex) {
+        if (detail)
+          dfire_rigid_kernel<true, true><<<grid, threads, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->w->d_unit_counter,
+                                                                      h->d_rc, h->w->d_prep, h->w->d_lig4p, h->w->d_flag);
+        else
+          dfire_rigid_kernel<false, true><<<grid, threads, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->w->d_unit_counter,
+                                                                       h->d_rc, h->w->d_prep, h->w->d_lig4p, h->w->d_flag);
+      } else if (detail) {
+        dfire_rigid_kernel<true, false><<<grid, threads, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->w->d_unit_counter,
+                                                                     h->d_rc, h->w->d_prep, nullptr, nullptr);
+      } else {
+        dfire_rigid_kernel<false, false><<<grid, threads, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->w->d_unit_counter,
+                                                                      h->d_rc, h->w->d_prep, nullptr, nullptr);
+      }
       ++launches;
       ++pair_launches;
       if ((rc = prof_mark(h, st)) != LD_OK) return rc;
@@ -1051,10 +1290,13 @@ static int score_host(ld_handle *h, int64_t n, const double *poses, double *ener
   if (want_detail)
     CU(cudaMemcpyAsync(detail, h->w->d_detail, (size_t)n * sizeof(ld_pose_detail), cudaMemcpyDeviceToHost, h->w->stream));
   CU(cudaEventRecord(h->w->ev1, h->w->stream));
+  if (h->flex && use_rigid(h))
+    CU(cudaMemcpyAsync(h->h_need, h->d_need, (size_t)cx.n_lig_tiles * sizeof(int), cudaMemcpyDeviceToHost, h->w->stream));
   {
     Nvtx range_wait("ld_score_batch: wait for the device + D2H");
     CU(cudaStreamSynchronize(h->w->stream));
   }
+  if (h->flex && use_rigid(h) && (rc = grow_flex_slack(h)) != LD_OK) return rc;
   float ms = 0.f;
   CU(cudaEventElapsedTime(&ms, h->w->ev0, h->w->ev1));
   h->w->stats.device_ms = ms;
@@ -1097,6 +1339,8 @@ extern "C" int ld_score_batch_begin(ld_handle *h, int32_t slot, int64_t n, const
     if ((rc = run_device(h, n, w->d_poses, w->d_energies, w->stream, nullptr, nullptr, nullptr)) != LD_OK) return rc;
     CU(cudaMemcpyAsync(w->h_energies, w->d_energies, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, w->stream));
     CU(cudaEventRecord(w->ev1, w->stream));
+    if (h->flex && use_rigid(h))
+      CU(cudaMemcpyAsync(h->h_need, h->d_need, (size_t)h->cx.n_lig_tiles * sizeof(int), cudaMemcpyDeviceToHost, w->stream));
   } else {
     w->stats = ld_batch_stats{};
   }
@@ -1118,6 +1362,8 @@ extern "C" int ld_score_batch_end(ld_handle *h, int32_t slot, double *energies) 
   CU(cudaEventElapsedTime(&ms, w->ev0, w->ev1));
   w->stats.device_ms = ms;
   std::memcpy(energies, w->h_energies, (size_t)n * sizeof(double));
+  // FLEX: the other slot may still be in flight; grow_flex_slack waits for it before it replaces the lists
+  if (h->flex && use_rigid(h)) return grow_flex_slack(h);
   return LD_OK;
 }
 

@@ -85,6 +85,7 @@ struct DeviceComplex {
   const double *lig_modes;                  // [k][3][n_lig_pad]
   const double *pot;                        // DFIRE table as the reference indexes it
   const double *potx;                       // [169][RG_ROW_BYTES/8]: row ta = [tb][RG_SLOTS], slot s <-> idx s + RG_SLOT0
+  double fx_inv_scale;                      // DFIRE ligand-frame FLEX path: per-group sums are 64-bit fixed point, value = sum * this; 0 = f64 sums
   // restraints (sorted atom positions) and membrane beads
   int n_rec_rst, n_lig_rst, n_membrane;
   const int *rec_rst_off, *rec_rst_idx, *lig_rst_off, *lig_rst_idx, *membrane_idx;

@@ -949,7 +949,12 @@ __global__ void __launch_bounds__(128) finalize_kernel(const DeviceComplex cx, c
   hr = warp_sum_u32(hr); hl = warp_sum_u32(hl); hm = warp_sum_u32(hm);
   if (lane != 0) return;
   double s0 = 0.0, s1 = 0.0;
-  if (cx.method == 0) {
+  if (cx.method == 0 && cx.fx_inv_scale != 0.0) {
+    // FLEX: each group's sum is an exact 64-bit fixed-point integer (ld_rigid.cuh); converted (one rounding, a power-
+    // of-two scale) and added in group order
+    const long long *part = reinterpret_cast<const long long *>(bb.partials) + (size_t)pose * cx.n_rec_tiles;
+    for (int t = 0; t < cx.n_rec_tiles; ++t) s0 = __dadd_rn(s0, __dmul_rn((double)part[t], cx.fx_inv_scale));
+  } else if (cx.method == 0) {
     const double *part = bb.partials + (size_t)pose * cx.n_rec_tiles;
     for (int t = 0; t < cx.n_rec_tiles; ++t) s0 = __dadd_rn(s0, part[t]);
   } else {

@@ -5,6 +5,7 @@
 #include <string>
 
 #include "gso.hpp"
+#include "sharding.hpp"
 #include "simulate.hpp"
 
 using namespace lightdock;
@@ -201,6 +202,24 @@ int ldh_find_neighbors(int n, const double *xyz, const double *luciferin, const 
   }
   out_offsets[n] = k;
   return k;
+  LDH_CATCH(-1)
+}
+
+// Cost-aware swarm -> GPU map (host/sharding.hpp).  centres [n_swarms][3]: mean translation of each swarm's glowworms.
+// out_cost [n_swarms] (may be NULL), out_gpu [n_swarms].  Host-only: needs no device.
+int ldh_shard_swarms(int n_rec, const double *rec_xyz, int n_lig, const double *lig_xyz, int n_swarms,
+                     const double *centres, int n_gpus, double *out_cost, int *out_gpu) {
+  LDH_TRY
+  const SwarmCostModel model(std::vector<double>(rec_xyz, rec_xyz + (size_t)3 * n_rec),
+                             std::vector<double>(lig_xyz, lig_xyz + (size_t)3 * n_lig));
+  std::vector<double> cost(n_swarms);
+  for (int s = 0; s < n_swarms; ++s) cost[s] = model.cost(centres + (size_t)3 * s);
+  const std::vector<int> gpu = assign_swarms_lpt(cost, n_gpus);
+  for (int s = 0; s < n_swarms; ++s) {
+    if (out_cost) out_cost[s] = cost[s];
+    out_gpu[s] = gpu[s];
+  }
+  return 0;
   LDH_CATCH(-1)
 }
 

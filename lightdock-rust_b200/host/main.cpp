@@ -6,19 +6,28 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <exception>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
+#include "../../include/lightdock_b200.h"
 #include "gso.hpp"
+#include "scoring.hpp"
 #include "simulate.hpp"
 
 using namespace lightdock;
 
+// LDB200_TIMING=1: one line on stderr with where the wall clock of the run went (bench.py's single_swarm_runs reads
+// it).  stdout stays byte-identical to the reference's.
+static const auto g_t0 = std::chrono::steady_clock::now();
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_t0).count(); }
+
 static int simulate(const std::string &simulation_path, const SetupFile &setup, const std::string &swarm_filename,
-                    uint32_t steps, Method method) {
+                    uint32_t steps, Method method, int device) {
   std::printf("Reading starting positions from %s\n", rust_debug_str(swarm_filename).c_str());
   const std::optional<int> swarm_id = parse_swarm_id(swarm_filename);
   if (!swarm_id) throw std::runtime_error("Could not parse swarm from swarm filename");
@@ -31,13 +40,24 @@ static int simulate(const std::string &simulation_path, const SetupFile &setup, 
   }
   std::printf("Writing to swarm dir %s\n", rust_debug_str(swarm_directory).c_str());
   const auto positions = parse_input_coordinates(swarm_filename);
-  const char *dev = std::getenv("LIGHTDOCK_B200_DEVICE");
-  LoadedCase lc = load_case(simulation_path, setup, method, "", dev ? std::atoi(dev) : 0, true);
+  const double t_inputs = now_ms();
+  LoadedCase lc = load_case(simulation_path, setup, method, "", device, true);
+  const double t_loaded = now_ms();
   std::printf("Creating GSO with %zu glowworms\n", positions.size());
   GSO gso(positions, lc.seed, lc.scoring.get(), setup.use_anm, setup.anm_rec, setup.anm_lig, swarm_directory);
   std::printf("Starting optimization (%u steps)\n", steps);
   std::fflush(stdout);
   gso.run(steps);
+  const double t_done = now_ms();
+  if (std::getenv("LDB200_TIMING")) {
+    double c[4] = {0, 0, 0, 0};
+    if (const auto *cs = dynamic_cast<const CudaScore *>(lc.scoring.get())) ld_get_create_ms(cs->handle(), c);
+    std::fprintf(stderr,
+                 "[ldb200 timing] until_main_inputs_ms=%.1f load_case_ms=%.1f (ld_create: context_wait=%.1f complex=%.1f "
+                 "groups=%.1f cells=%.1f) gso_ms=%.1f energy_calls=%llu total_in_main_ms=%.1f\n",
+                 t_inputs, t_loaded - t_inputs, c[0], c[1], c[2], c[3], t_done - t_loaded,
+                 (unsigned long long)gso.swarm.energy_calls, t_done);
+  }
   return 0;
 }
 
@@ -73,8 +93,20 @@ int main(int argc, char **argv) {
   }
   const size_t slash = setup_filename.find_last_of('/');
   const std::string simulation_path = slash == std::string::npos ? "" : setup_filename.substr(0, slash);
+  // Scoring runs on CUDA device $LIGHTDOCK_B200_DEVICE (default 0).  Unless the user has narrowed the visible devices
+  // already, narrow them to that one before the first CUDA call: on an 8-GPU box the runtime otherwise initialises all
+  // eight (seconds, for a run whose 100 steps take 40 ms).  The context is then created on a helper thread while this
+  // thread parses the structures, the ANM files and the 13 MB DCparams.
+  int device = 0;
+  if (const char *dev = std::getenv("LIGHTDOCK_B200_DEVICE")) device = std::atoi(dev);
+  if (!std::getenv("CUDA_VISIBLE_DEVICES") && device >= 0) {
+    setenv("CUDA_VISIBLE_DEVICES", std::to_string(device).c_str(), 1);
+    device = 0;
+  }
+  std::thread warm([device] { ld_init_device(device); });  // errors resurface, with their message, in ld_create
+  struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{warm};
   try {
-    return simulate(simulation_path, setup, swarm_filename, (uint32_t)steps64, method);
+    return simulate(simulation_path, setup, swarm_filename, (uint32_t)steps64, method, device);
   } catch (const std::exception &e) {
     // the reference panics here; mirror the message and the panic exit status
     std::fprintf(stderr, "thread '<unnamed>' panicked: %s\n", e.what());

@@ -26,6 +26,8 @@
 #include <vector>
 
 #include "gso.hpp"
+#include "pdb.hpp"
+#include "sharding.hpp"
 #include "simulate.hpp"
 
 using namespace lightdock;
@@ -136,6 +138,26 @@ int main(int argc, char **argv) {
     std::printf("%zu swarms, %llu steps, %s scoring on %zu GPU(s), %d host threads each\n", ns, job.steps,
                 method_name(method), G, host_threads);
     std::fflush(stdout);
+    // which GPU scores which swarm: cost-aware and deterministic (host/sharding.hpp); results do not depend on it
+    std::vector<std::vector<size_t>> mine(G);
+    {
+      const std::string dir = simulation_path.empty() ? std::string("lightdock_") : simulation_path + "/lightdock_";
+      const PDB rec_pdb = open_pdb(dir + setup.receptor_pdb);  // the files load_case reads (src/constants.rs:18)
+      const PDB lig_pdb = open_pdb(dir + setup.ligand_pdb);
+      std::vector<double> rxyz, lxyz;
+      for (const auto &a : rec_pdb.atoms) { rxyz.push_back(a.x); rxyz.push_back(a.y); rxyz.push_back(a.z); }
+      for (const auto &a : lig_pdb.atoms) { lxyz.push_back(a.x); lxyz.push_back(a.y); lxyz.push_back(a.z); }
+      const SwarmCostModel model(rxyz, lxyz);
+      std::vector<double> cost(ns);
+      for (size_t s = 0; s < ns; ++s) {
+        double c[3] = {0, 0, 0};
+        for (const auto &p : positions[s])
+          for (int d = 0; d < 3 && p.size() >= 3; ++d) c[d] += p[d] / (double)positions[s].size();
+        cost[s] = model.cost(c);
+      }
+      const std::vector<int> gpu_of = assign_swarms_lpt(cost, (int)G);
+      for (size_t s = 0; s < ns; ++s) mine[(size_t)gpu_of[s]].push_back(s);
+    }
     std::vector<std::exception_ptr> errors(G);
     std::vector<uint64_t> calls(G, 0);
     std::vector<std::vector<std::pair<std::string, std::string>>> failed(G);  // (swarm dir, message) per GPU
@@ -145,11 +167,11 @@ int main(int argc, char **argv) {
         try {
           LoadedCase lc = load_case(simulation_path, setup, method, "", devices[g], false);
           MultiGSO multi(lc.scoring.get());
-          for (size_t s = g; s < ns; s += G)
+          for (size_t s : mine[g])
             multi.add(positions[s], lc.seed, setup.use_anm, setup.anm_rec, setup.anm_lig, dirs[s]);
           multi.run((uint32_t)job.steps, host_threads);
           calls[g] = multi.energy_calls();
-          for (const auto &f : multi.failures()) failed[g].emplace_back(dirs[g + f.first * G], f.second);
+          for (const auto &f : multi.failures()) failed[g].emplace_back(dirs[mine[g][f.first]], f.second);
         } catch (...) {
           errors[g] = std::current_exception();
         }

@@ -18,7 +18,7 @@ DFIRE_TABLE_LEN = 169 * 169 * 20
 EXPORTS = ["ld_create", "ld_destroy", "ld_pose_len", "ld_score_batch", "ld_score_batch_device",
            "ld_score_batch_detail", "ld_transform_batch", "ld_get_stats", "ld_set_rec_splits",
            "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version", "ld_set_path", "ld_path_info", "ld_device_count", "ld_score_batch_begin", "ld_score_batch_end", "ld_get_stats_slot",
-           "ld_set_option"]
+           "ld_set_option", "ld_init_device", "ld_get_create_ms"]
 
 PATH_AUTO, PATH_GENERIC, PATH_RIGID = 0, 1, 2
 
@@ -87,6 +87,8 @@ def load_library():
         lib.ld_probe_peaks.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ld_get_stats_slot.argtypes = [C.c_void_p, C.c_int32, C.POINTER(BatchStats)]
         lib.ld_set_option.argtypes = [C.c_char_p, C.c_double]
+        lib.ld_init_device.argtypes = [C.c_int32]
+        lib.ld_get_create_ms.argtypes = [C.c_void_p, C.c_void_p]
         # experiment knobs of the tools (tools/units_sweep.py, ...): forwarded through the API, the library itself
         # never reads the environment
         for env, key in (("LDB200_ROWS", "rigid_rows"), ("LDB200_CELL", "cell_size"),
@@ -239,11 +241,23 @@ class Scorer:
     def path_info(self):
         return self.lib.ld_path_info(self.h).decode()
 
+    def create_ms(self):
+        """ld_create's time split: CUDA context, complex, receptor groups, cell lists (ms)."""
+        out = (C.c_double * 4)()
+        _check(self.lib, self.lib.ld_get_create_ms(self.h, out))
+        return dict(zip(("context", "complex", "groups", "cells"), out))
+
     def set_profiling(self, on):
         _check(self.lib, self.lib.ld_set_profiling(self.h, int(bool(on))))
 
     def stats(self, slot=None):
         return handle_stats(self.lib, self.h, slot)
+
+
+def set_option(key, value):
+    """Process-wide tuning default for handles created afterwards (include/lightdock_b200.h: ld_set_option)."""
+    lib = load_library()
+    _check(lib, lib.ld_set_option(key.encode(), float(value)))
 
 
 def handle_stats(lib, h, slot=None):

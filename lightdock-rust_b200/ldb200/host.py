@@ -39,6 +39,8 @@ def load_host_library():
         lib.ldh_slerp.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         lib.ldh_rotate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.ldh_find_neighbors.argtypes = [C.c_int] + [C.c_void_p] * 5
+        lib.ldh_shard_swarms.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                         C.c_void_p]
         lib.ldh_parse_f64.argtypes = [C.c_char_p, C.c_void_p]
         lib.ldh_save_swarm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint, C.c_char_p]
         lib.ldh_build_model.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p] + [C.c_void_p] * 10
@@ -66,6 +68,21 @@ def rotate(q, v):
     q, v, out = np.asarray(q, np.float64), np.asarray(v, np.float64), np.empty(3)
     load_host_library().ldh_rotate(q.ctypes.data, v.ctypes.data, out.ctypes.data)
     return out
+
+
+def shard_swarms(rec_xyz, lig_xyz, centres, n_gpus):
+    """Host-only: the cost-aware, deterministic swarm -> GPU map of host/sharding.hpp (what lightdock-rust-multi and
+    bench.py use).  centres [n_swarms][3] = mean translation of each swarm.  Returns (gpu_of [n_swarms], cost)."""
+    lib = load_host_library()
+    rec = np.ascontiguousarray(rec_xyz, np.float64).reshape(-1, 3)
+    lig = np.ascontiguousarray(lig_xyz, np.float64).reshape(-1, 3)
+    cen = np.ascontiguousarray(centres, np.float64).reshape(-1, 3)
+    cost = np.zeros(len(cen))
+    gpu = np.zeros(len(cen), np.int32)
+    if lib.ldh_shard_swarms(len(rec), rec.ctypes.data, len(lig), lig.ctypes.data, len(cen), cen.ctypes.data, int(n_gpus),
+                            cost.ctypes.data, gpu.ctypes.data):
+        raise _err(lib)
+    return gpu, cost
 
 
 def parse_f64(token):

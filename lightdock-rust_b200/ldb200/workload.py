@@ -86,5 +86,17 @@ def synthetic_1k4c_swarms(n_swarms=400, n_glowworms=200, seed=324324):
 
 
 def shard_swarms(n_swarms, rank, world):
-    """Swarm s -> GPU s mod G: the swarm ids owned by `rank`."""
+    """Swarm s -> GPU s mod G (the round-1 map): the swarm ids owned by `rank`."""
     return list(range(rank, n_swarms, world))
+
+
+def shard_swarms_cost_aware(poses, rec_xyz, lig_xyz, rank, world):
+    """The swarm ids owned by `rank` under the cost-aware deterministic map of host/sharding.hpp (what
+    lightdock-rust-multi uses): expected in-reach atom pairs at each swarm's centre, longest-processing-time first.
+    poses [n_swarms][n_glowworms][pose_len].  Every rank computes the same map; no communication."""
+    from . import host
+    if world == 1:
+        return list(range(len(poses)))
+    centres = np.asarray(poses)[:, :, :3].mean(axis=1)
+    gpu, _ = host.shard_swarms(rec_xyz, lig_xyz, centres, world)
+    return [s for s in range(len(poses)) if gpu[s] == rank]

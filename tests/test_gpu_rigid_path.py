@@ -29,7 +29,8 @@ def _rigid(cx):
 
 
 def test_path_selection():
-    """AUTO = RIGID where it applies; ligand ANM or DNA scoring stay on the generic kernel; forcing is an error."""
+    """AUTO = the ligand-frame kernel where it applies (DFIRE; a ligand with ANM modes takes its FLEX instance); DNA
+    scoring stays on the generic kernel and forcing it there is an error."""
     cx, pos, _ = case("1k4c", O.DFIRE)
     sc = scorer_from_oracle(cx)
     assert sc.path_info().startswith("rigid path on"), sc.path_info()
@@ -38,14 +39,18 @@ def test_path_selection():
     sc.set_path(ldb200.PATH_GENERIC)
     sc.energy(pos[:4])
     assert sc.stats()["path"] == ldb200.PATH_GENERIC
-    for name, method in (("2uuy", O.DFIRE), ("1azp", O.DNA)):
-        cx2, pos2, _ = case(name, method)
-        sc2 = scorer_from_oracle(cx2)
-        assert sc2.path_info().startswith("rigid path off"), sc2.path_info()
-        sc2.energy(pos2[:4])
-        assert sc2.stats()["path"] == ldb200.PATH_GENERIC
-        with pytest.raises(ldb200.LdError):
-            sc2.set_path(ldb200.PATH_RIGID)
+    cx2, pos2, _ = case("2uuy", O.DFIRE)
+    sc2 = scorer_from_oracle(cx2)
+    assert sc2.path_info().startswith("rigid path on (flexible ligand"), sc2.path_info()
+    sc2.energy(pos2[:4])
+    assert sc2.stats()["path"] == ldb200.PATH_RIGID
+    cx3, pos3, _ = case("1azp", O.DNA)
+    sc3 = scorer_from_oracle(cx3)
+    assert sc3.path_info().startswith("rigid path off"), sc3.path_info()
+    sc3.energy(pos3[:4])
+    assert sc3.stats()["path"] == ldb200.PATH_GENERIC
+    with pytest.raises(ldb200.LdError):
+        sc3.set_path(ldb200.PATH_RIGID)
 
 
 @pytest.mark.parametrize("name", RIGID_CASES)
@@ -322,3 +327,124 @@ def test_device_calls_on_different_streams_do_not_race(name, method):
     assert np.array_equal(sc.energy(b), want_b)
     torch.cuda.synchronize()
     assert np.array_equal(ea.cpu().numpy(), want_a)
+
+
+# ---- FLEX: ligands WITH ANM modes on the ligand-frame path (per-pose ligand blocks, slack lists, fixed-point sums) ---
+FLEX_CASES = ["1czy", "2uuy", "ab_icode"]  # DFIRE + ANM on both partners (BASELINE configs[0], the shipped ANM examples)
+
+
+@pytest.mark.parametrize("name", FLEX_CASES)
+def test_flex_start_positions_parity(name):
+    """First call on a fresh handle: no slack has been learnt, so every pose whose ligand moves is scored by brute
+    force over all ligand tiles; afterwards the lists are rebuilt with the slacks the poses need and the same poses
+    go through the cell lists.  Both must satisfy the parity bar, and because the FLEX sums are exact integers the
+    two passes must agree BIT FOR BIT."""
+    cx, pos, _ = case(name, O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    assert sc.path_info().startswith("rigid path on (flexible ligand"), sc.path_info()
+    poses = pos[:200]
+    e_ref, d_ref = cx.energy(poses, detail=True)
+    e1, d1 = sc.energy_detail(poses)
+    assert sc.stats()["path"] == ldb200.PATH_RIGID
+    assert_parity(e1, d1, e_ref, d_ref, cx.method)
+    assert "rebuilt 1 times" in sc.path_info(), sc.path_info()
+    e2, d2 = sc.energy_detail(poses)
+    assert_parity(e2, d2, e_ref, d_ref, cx.method)
+    assert np.array_equal(e1, e2), "brute-force pass and cell-list pass must give the same bits"
+    assert d2["n_pairs_tested"].sum() < d1["n_pairs_tested"].sum(), "the second pass must go through the lists"
+    assert "rebuilt 1 times" in sc.path_info(), "no further growth for the same poses"
+    assert np.array_equal(sc.energy(poses), e2), "plain and detail instantiations must give the same bits"
+
+
+@pytest.mark.parametrize("name", FLEX_CASES)
+def test_flex_equals_generic_and_is_batch_invariant(name):
+    """Against the generic kernel (lab frame, sphere culling) on 2,000 perturbed poses: every discrete output
+    identical, energies to 1e-9; and a pose's bits do not depend on the batch, the order or the slack history."""
+    cx, pos, _ = case(name, O.DFIRE)
+    rng = np.random.default_rng(31)
+    poses = np.tile(pos, (10, 1))
+    poses[:, :3] += rng.normal(0, 1.5, size=(len(poses), 3))
+    poses[:, 7:] *= rng.uniform(0.5, 1.3, size=(len(poses), 1))
+    sc = scorer_from_oracle(cx)
+    e_f, d_f = sc.energy_detail(poses)
+    sc.set_path(ldb200.PATH_GENERIC)
+    e_g, d_g = sc.energy_detail(poses)
+    for k in DISCRETE:
+        np.testing.assert_array_equal(d_f[k], d_g[k], err_msg=k)
+    assert np.max(np.abs(e_f - e_g) / np.abs(e_g)) < 1e-9
+    sc.set_path(ldb200.PATH_RIGID)
+    perm = rng.permutation(len(poses))
+    assert np.array_equal(sc.energy(poses[perm]), e_f[perm])
+    assert np.array_equal(sc.energy(poses[:7]), e_f[:7])
+    one_by_one = np.array([sc.energy(poses[i:i + 1])[0] for i in range(0, 24)])
+    assert np.array_equal(one_by_one, e_f[:24])
+    fresh = scorer_from_oracle(cx)  # no slack learnt: brute force, then lists -- same bits as the grown handle
+    assert np.array_equal(fresh.energy(poses[:300]), e_f[:300])
+
+
+def test_flex_random_close_poses_and_large_extents():
+    """Ligand pushed into the receptor with ANM extents far beyond anything a previous call has seen: poses that
+    exceed the learnt slack take the brute-force route inside the same launch; parity must hold either way."""
+    cx, pos, _ = case("2uuy", O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    sc.energy(pos)  # learn the slacks of the shipped start positions
+    rng = np.random.default_rng(3)
+    poses = random_poses(rng, 48, cx.pose_len, centre=cx.rec.coords.mean(axis=0), spread=10.0, ext_scale=3.0)
+    poses[::3, 7:] *= 6.0  # extents up to ~50: tiles move by tens of A
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    e_ref, d_ref = cx.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
+    assert d_ref["n_interface_pairs"].max() > 0
+
+
+def test_flex_decision_thresholds_exact():
+    """The threshold complex of test_gpu_parity (pairs on / next to every bin edge, the 15 A cut-off and the 2.45 A
+    interface edge) with ONE ANM mode on the ligand that shifts every atom along x: the displaced positions are the
+    threshold positions, so the FLEX instance must hand them to its exact path like the rigid one does."""
+    from test_gpu_parity import _threshold_complex
+    rec, lig = _threshold_complex()
+    shift = 0.37
+    lig.coords = lig.coords - np.array([shift, 0.0, 0.0])
+    lig.n_modes = 1
+    lig.modes = np.tile(np.array([1.0, 0.0, 0.0]), lig.n)  # [k=1][atom][xyz]: unit displacement along x
+    rec.n_modes = 1
+    rec.modes = np.zeros(rec.n * 3)
+    pot, _ = O.real_or_synthetic_dcparams()
+    cx = O.Complex(rec, lig, O.DFIRE, True, pot)
+    sc = scorer_from_oracle(cx)
+    assert sc.path_info().startswith("rigid path on (flexible ligand"), sc.path_info()
+    base = np.array([[0, 0, 0, 1, 0, 0, 0], [0, 0, 0, 0, 1, 0, 0], [1e-9, 0, 0, 1, 0, 0, 0],
+                     [0, 2e-4, 0, 1, 0, 0, 0], [0.25, 0, 0, 1, 0, 0, 0]], dtype=np.float64)
+    poses = np.hstack([base, np.zeros((len(base), 1)), np.full((len(base), 1), shift)])  # rec extent 0, lig extent = shift
+    for rep in range(2):  # brute force, then through the lists
+        e_gpu, d_gpu = sc.energy_detail(poses)
+        e_ref, d_ref = cx.energy(poses, detail=True)
+        assert_parity(e_gpu, d_gpu, e_ref, d_ref, O.DFIRE)
+        assert d_gpu["n_exact_fallback"][0] > 0, "threshold pairs must take the exact FP64 path"
+
+
+@pytest.mark.parametrize("name", ["1k4c", "2uuy"])
+def test_device_cell_lists_equal_host_lists(name):
+    """The ligand-frame cell lists are built on the device (csrc/ld_cells.cuh); the round-1 host builder is kept as a
+    cross-check.  Same predicate, same f64 arithmetic: the two handles must test the same pairs and agree on every
+    discrete output; energies may differ only by the summation order a (boundary) list entry could change."""
+    cx, pos, _ = case(name, O.DFIRE)
+    poses = pos[:64]
+    sc_dev = scorer_from_oracle(cx)
+    ldb200.set_option("cells_on_host", 1)
+    try:
+        sc_host = scorer_from_oracle(cx)
+    finally:
+        ldb200.set_option("cells_on_host", 0)
+    for rep in range(2):  # 2uuy (FLEX): brute force first, then through lists rebuilt with the learnt slacks
+        e_d, d_d = sc_dev.energy_detail(poses)
+        e_h, d_h = sc_host.energy_detail(poses)
+        for k in DISCRETE:
+            np.testing.assert_array_equal(d_d[k], d_h[k], err_msg=k)
+        assert np.max(np.abs(e_d - e_h) / np.abs(e_h)) < 1e-12
+        a, b = d_d["n_pairs_tested"].sum(), d_h["n_pairs_tested"].sum()
+        assert b <= a <= b * 1.0001, (a, b)
+    info_d, info_h = sc_dev.path_info(), sc_host.path_info()
+    entries = lambda s: int(s.split(" list entries")[0].split()[-1])
+    assert entries(info_h) <= entries(info_d) <= entries(info_h) * 1.0001, (info_d, info_h)
+    assert sc_dev.create_ms()["cells"] < 50.0, sc_dev.create_ms()

@@ -48,22 +48,23 @@ def test_cli_reproduces_1azp_golden_trajectory(tmp_path):
         compare_gso_files(str(tmp_path / "swarm_0" / f"gso_{s}.out"), os.path.join(g, "swarm_0", f"gso_{s}.out"))
 
 
-@pytest.mark.parametrize("name,steps", [("1czy", 100), ("2uuy", 100), ("ab_icode", 30)])
+@pytest.mark.parametrize("name,steps", [("1czy", 100), ("2uuy", 100), ("ab_icode", 100)])
 def test_host_gso_matches_oracle_gso_dfire_anm(name, steps, tmp_path, monkeypatch):
     """BASELINE configs with ANM on both partners (1czy protein-peptide, 2uuy = the shipped DFIRE + ANM
     protein-protein example, ab_icode with insertion codes) for the reference's full 100 steps: product host + GPU
-    (generic DFIRE kernel) against the oracle's GSO, same seed; discrete fields of the final state exact."""
+    (ligand-frame DFIRE kernel, FLEX instance) against the oracle's GSO, same seed; discrete fields of the final
+    state exact."""
     from ldb200 import host
     cx, pos, seed = case(name, O.DFIRE)
     g = os.path.join(GOLDEN, name)
     O.write_dcparams(str(tmp_path / "DCparams"), cx.potential)
     monkeypatch.setenv("LIGHTDOCK_DATA", str(tmp_path))
     c = host.Case(os.path.join(g, "setup.json"), "dfire", anm_dir=g)
-    assert c.path_info().startswith("rigid path off"), c.path_info()
+    assert c.path_info().startswith("rigid path on (flexible ligand"), c.path_info()
     start = [f for f in sorted(os.listdir(g)) if f.startswith("initial_positions")]
     start = os.path.join(g, start[0]) if start else os.path.join(g, "init", "initial_positions_0.dat")
     state, calls = c.gso(start, steps)
-    final, tr, ocalls = cx.gso_run(pos, seed, steps, trace=True)
+    final, tr, ocalls = cx.gso_run(pos, seed, steps, trace=True, threads=oracle_threads())
     last = tr[-1]
     assert calls == ocalls
     np.testing.assert_array_equal(state[:, 2], last[:, 2])            # neighbour counts

@@ -62,8 +62,8 @@ def _free_port():
 
 
 def test_two_rank_gloo_aggregation(tmp_path):
-    """N > 1 host logic on CPU: each rank owns swarm s mod 2, results are combined the way bench.py does
-    (sum of poses, MAX of time), and the union of the shards equals the single-rank pose set."""
+    """N > 1 host logic on CPU: each rank owns the swarms the cost-aware map gives it, results are combined the way
+    bench.py does (sum of poses, MAX of time), and the union of the shards equals the single-rank pose set."""
     script = tmp_path / "rank.py"
     script.write_text(textwrap.dedent(f"""
         import os, sys, json
@@ -72,8 +72,12 @@ def test_two_rank_gloo_aggregation(tmp_path):
         from ldb200 import workload
         rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
         dist.init_process_group("gloo")
-        mine = workload.shard_swarms(12, rank, world)
-        poses = workload.synthetic_1k4c_swarms(12, 5)[mine].reshape(-1, 7)
+        g = workload.GOLDEN_1K4C
+        rec = workload.read_pdb_coords(g + "/lightdock_receptor_membrane.pdb")
+        lig = workload.read_pdb_coords(g + "/lightdock_ligand.pdb")
+        all_poses = workload.synthetic_1k4c_swarms(12, 5)
+        mine = workload.shard_swarms_cost_aware(all_poses, rec, lig, rank, world)   # what bench.py does
+        poses = all_poses[mine].reshape(-1, 7)
         t = torch.tensor([10.0 + 5.0 * rank], dtype=torch.float64)      # pretend per-rank elapsed ms
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         n = torch.tensor([poses.shape[0]], dtype=torch.int64)
@@ -94,6 +98,31 @@ def test_two_rank_gloo_aggregation(tmp_path):
     full = workload.synthetic_1k4c_swarms(12, 5).reshape(-1, 7)
     assert out["n"] == 60 and out["max_ms"] == 15.0
     assert abs(out["checksum"] - full.sum()) < 1e-6
+
+
+def test_cost_aware_sharding_is_a_balanced_deterministic_partition():
+    """host/sharding.hpp: every swarm on exactly one GPU, the same map on every call, and a flatter predicted load
+    than the round-1 `s mod G` map on the bench workload (whose static map left the slowest of 8 ranks 10 % above the
+    mean)."""
+    from ldb200 import host
+    g = workload.GOLDEN_1K4C
+    rec = workload.read_pdb_coords(g + "/lightdock_receptor_membrane.pdb")
+    lig = workload.read_pdb_coords(g + "/lightdock_ligand.pdb")
+    poses = workload.synthetic_1k4c_swarms(400, 8)
+    centres = poses[:, :, :3].mean(axis=1)
+    for G in (2, 4, 8):
+        gpu, cost = host.shard_swarms(rec, lig, centres, G)
+        gpu2, _ = host.shard_swarms(rec, lig, centres, G)
+        assert np.array_equal(gpu, gpu2) and set(gpu.tolist()) == set(range(G))
+        owned = [workload.shard_swarms_cost_aware(poses, rec, lig, r, G) for r in range(G)]
+        assert sorted(sum(owned, [])) == list(range(400))
+        lpt = np.array([cost[gpu == r].sum() for r in range(G)])
+        mod = np.array([cost[r::G].sum() for r in range(G)])
+        assert lpt.max() / lpt.mean() < 1.005 and lpt.max() / lpt.mean() <= mod.max() / mod.mean()
+    assert (cost > 0).all() and cost.max() / cost.min() > 3, "the bench swarms do differ in cost"
+    # a swarm far from the receptor costs (almost) nothing, one on top of it the most
+    _, c = host.shard_swarms(rec, lig, np.array([[500.0, 0, 0], rec.mean(axis=0)]), 2)
+    assert c[0] < 2 and c[1] > 1e5
 
 
 def test_reference_arm_runs_on_cpu():

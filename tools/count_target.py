@@ -1,0 +1,41 @@
+"""One large batch of one configuration through the C ABI, for `ncu -k regex:<kernel> -s <skip> -c 1` captures of the
+per-kernel counters bench.py's rooflines use (tools/capture_counts.sh).  Prints the batch size.
+
+    python tools/count_target.py <1czy|1ppe|2uuy|ab_icode|1azp|1k4c_bench> [n_warm]
+Launch order: 1 warm-up call of the same batch (FLEX handles learn their slacks and rebuild their lists there), then the
+captured call.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in ("", "oracle", "lightdock-rust_b200", "tests"):
+    sys.path.insert(0, os.path.join(ROOT, p))
+import oracle as O  # noqa: E402
+from helpers import case, scorer_from_oracle  # noqa: E402
+from ldb200 import workload  # noqa: E402
+
+
+def config_poses(name):
+    """The 20,000-pose batch of a BASELINE config: its 200 shipped start poses x 100, translations jittered by 1 A
+    (seeded), ANM extents kept.  1k4c_bench: the 80,000 poses of the headline workload."""
+    if name == "1k4c_bench":
+        cx, _, _ = case("1k4c", O.DFIRE)
+        return cx, np.ascontiguousarray(workload.synthetic_1k4c_swarms(400, 200).reshape(-1, 7))
+    cx, pos, _ = case(name, O.DNA if name == "1azp" else O.DFIRE)
+    rng = np.random.default_rng(1)
+    big = np.tile(pos, (100, 1))
+    big[:, :3] += rng.normal(0, 1.0, size=(len(big), 3))
+    return cx, big
+
+
+if __name__ == "__main__":
+    name = sys.argv[1]
+    cx, poses = config_poses(name)
+    sc = scorer_from_oracle(cx)
+    for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 1):
+        sc.energy(poses)
+    sc.energy(poses)
+    print(name, len(poses), "poses", sc.path_info()[:80])
