@@ -57,6 +57,7 @@ struct Options {
   double cell_size = 1.0;         // ligand-frame cell size in A
   int units_per_sm = 16;          // rigid kernel: work units per SM
   int default_path = LD_PATH_AUTO;
+  int flex = 1;                   // 0: ligands with ANM modes stay on the generic kernel (no FLEX instance of the ligand-frame path)
   int cells_on_host = 0;          // 1: build the ligand-frame cell lists with host threads (the round-1 builder; cross-check)
 };
 Options g_opt;
@@ -69,6 +70,7 @@ extern "C" int ld_set_option(const char *key, double value) {
   else if (k == "cell_size") g_opt.cell_size = std::max(0.5, std::min(8.0, value));
   else if (k == "units_per_sm") g_opt.units_per_sm = std::max(1, (int)value);
   else if (k == "cells_on_host") g_opt.cells_on_host = value != 0.0;
+  else if (k == "flex") g_opt.flex = value != 0.0;
   else if (k == "default_path") {
     if (value != LD_PATH_AUTO && value != LD_PATH_GENERIC) return fail(LD_EINVAL, "ld_set_option: default_path is AUTO or GENERIC");
     g_opt.default_path = (int)value;
@@ -98,7 +100,7 @@ struct Workspace {
   double *d_prep = nullptr;             // rigid path: [cap_prep][RG_PREP] per-pose rotation data
   int64_t cap_prep = 0;
   float4 *d_lig4p = nullptr;            // FLEX: [cap_flex][n_lig_pad] per-pose ligand blocks (ligand frame, f32)
-  unsigned char *d_flag = nullptr;      // FLEX: [cap_flex] 1 = pose scored by brute force
+  float *d_flag = nullptr;              // FLEX: [cap_flex] 0, or the displacement that sends the pose to the brute-force route
   int64_t cap_flex = 0;
   ld_batch_stats stats{};
   // profiling: events bracketing every kernel of the last call (4 per chunk)
@@ -513,6 +515,7 @@ static int build_cells(ld_handle *h) {
   rc.thr_out = (float)(225.0 + delta);
   rc.half_minus_eps = (float)(0.5 - 2.5e-5);
   rc.delta = (float)(1.02 * delta);
+  rc.grid_maxabs = (float)(maxabs * 1.000001);
   if (h->d_rc) CU(cudaMemcpy(h->d_rc, &rc, sizeof(RigidComplex), cudaMemcpyHostToDevice));
   char buf[640];
   snprintf(buf, sizeof buf,
@@ -544,6 +547,9 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
     rows_max = (int)std::min<long>(RG_MAX_ROWS, avail / RG_ROW_BYTES);
     rows_max = std::min(rows_max, g_opt.rigid_rows);
     if (rows_max < 1) { h->rigid_info = "rigid path off: ligand + one table row exceed shared memory"; return LD_OK; }
+  } else if (!g_opt.flex) {
+    h->rigid_info = "rigid path off: the ligand has ANM modes (FLEX disabled by ld_set_option)";
+    return LD_OK;
   } else {
     // FLEX: one ligand block per warp next to the table rows; prefer many rows (fewer, fuller receptor groups) as
     // long as enough warps fit to keep the SM busy
@@ -1166,7 +1172,8 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
     bb.lig_words = lig_words;
     h->w->stats.rec_splits = splits;
     if ((rc = prof_mark(h, st)) != LD_OK) return rc;
-    transform_kernel<<<(unsigned)nc, 256, 0, st>>>(cx, bb, (int)nc);
+    transform_kernel<<<(unsigned)((nc + TRANSFORM_PP - 1) / TRANSFORM_PP), 256,
+                       (size_t)TRANSFORM_PP * (cx.n_rec_modes + cx.n_lig_modes) * sizeof(double), st>>>(cx, bb, (int)nc);
     ++launches;
     if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     if (cx.n_rec_tiles > 0) {
@@ -1394,7 +1401,8 @@ extern "C" int ld_transform_batch(ld_handle *h, int64_t n, const double *poses, 
     bb.poses = h->w->d_poses + (size_t)p0 * cx.pose_len;
     bb.lig_blocks = h->w->d_lig_blocks;
     bb.rec_blocks = h->w->d_rec_blocks;
-    transform_kernel<<<(unsigned)nc, 256, 0, h->w->stream>>>(cx, bb, (int)nc);
+    transform_kernel<<<(unsigned)((nc + TRANSFORM_PP - 1) / TRANSFORM_PP), 256,
+                       (size_t)TRANSFORM_PP * (cx.n_rec_modes + cx.n_lig_modes) * sizeof(double), h->w->stream>>>(cx, bb, (int)nc);
     CU(cudaGetLastError());
     lb.resize((size_t)nc * h->lig_block);
     CU(cudaMemcpyAsync(lb.data(), h->w->d_lig_blocks, lb.size(), cudaMemcpyDeviceToHost, h->w->stream));

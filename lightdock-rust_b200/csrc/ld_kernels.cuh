@@ -110,97 +110,152 @@ __device__ __forceinline__ float warp_max_f(float v) {
   return v;
 }
 
-// Kernel 1: pose transform.  grid = poses, block = 256.
+// Kernel 1: pose transform.  grid = ceil(poses / TRANSFORM_PP), block = 256.
+// A CTA transforms TRANSFORM_PP poses at once: thread = atom, and the atom's ANM mode vectors are read ONCE for all of
+// them (one pose per CTA re-read every mode of both partners per pose from L2: 300 KB per pose for 1czy, which made
+// this kernel L2-bandwidth bound and 30-45 % of the device time of the ANM configurations).  Per pose the operations
+// and their order are the reference's: rotate, + translation, then mode k = 0, 1, ... each as multiply-then-add.
+constexpr int TRANSFORM_PP = 4;
 __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
-  __shared__ float s_max[2][8];
-  const int p = blockIdx.x;
-  if (p >= n_poses) return;
-  const double *pose = bb.poses + (size_t)p * cx.pose_len;
-  const double tx = pose[0], ty = pose[1], tz = pose[2];
-  const Quat q = {pose[3], pose[4], pose[5], pose[6]};
-  // inverse(): conjugate / norm2, src/qt.rs:24-34,48-50,187-198
-  const double n2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q.w, q.w), __dmul_rn(q.x, q.x)), __dmul_rn(q.y, q.y)),
-                              __dmul_rn(q.z, q.z));
-  const Quat qi = {__ddiv_rn(q.w, n2), __ddiv_rn(-q.x, n2), __ddiv_rn(-q.y, n2), __ddiv_rn(-q.z, n2)};
-  const double *rec_ext = pose + 7;
-  const double *lig_ext = pose + 7 + cx.n_rec_modes;
+  __shared__ float s_max[TRANSFORM_PP][2][8];
+  __shared__ double s_pose[TRANSFORM_PP][11];  // tx ty tz | q | q^-1
+  extern __shared__ double s_ext[];            // [TRANSFORM_PP][n_rec_modes + n_lig_modes]
+  const int p0 = blockIdx.x * TRANSFORM_PP, np = min(TRANSFORM_PP, n_poses - p0);
+  const int n_ext = cx.n_rec_modes + cx.n_lig_modes;
+  if (threadIdx.x < np) {
+    const double *pose = bb.poses + (size_t)(p0 + threadIdx.x) * cx.pose_len;
+    const Quat q = {pose[3], pose[4], pose[5], pose[6]};
+    // inverse(): conjugate / norm2, src/qt.rs:24-34,48-50,187-198
+    const double n2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q.w, q.w), __dmul_rn(q.x, q.x)), __dmul_rn(q.y, q.y)),
+                                __dmul_rn(q.z, q.z));
+    double *o = s_pose[threadIdx.x];
+    o[0] = pose[0]; o[1] = pose[1]; o[2] = pose[2];
+    o[3] = q.w; o[4] = q.x; o[5] = q.y; o[6] = q.z;
+    o[7] = __ddiv_rn(q.w, n2); o[8] = __ddiv_rn(-q.x, n2); o[9] = __ddiv_rn(-q.y, n2); o[10] = __ddiv_rn(-q.z, n2);
+  }
+  for (int i = threadIdx.x; i < np * n_ext; i += blockDim.x)
+    s_ext[i] = bb.poses[(size_t)(p0 + i / n_ext) * cx.pose_len + 7 + i % n_ext];
+  __syncthreads();
 
-  unsigned char *lb = bb.lig_blocks + (size_t)p * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles, cx.method);
-  double *ox = reinterpret_cast<double *>(lb), *oy = ox + cx.n_lig_pad, *oz = oy + cx.n_lig_pad;
-  float4 *of4 = reinterpret_cast<float4 *>(lb + lig_off_f4(cx.n_lig_pad));    // DFIRE
-  double2 *od4 = reinterpret_cast<double2 *>(lb + lig_off_f4(cx.n_lig_pad));  // DNA/pyDock
-  float4 *osph = reinterpret_cast<float4 *>(lb + lig_off_sph(cx.n_lig_pad, cx.method));
-  float4 *ometa = reinterpret_cast<float4 *>(lb + lig_off_meta(cx.n_lig_pad, cx.n_lig_tiles, cx.method));
-  float lmax = 0.f, rmax = 0.f;
+  const size_t lbs = lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles, cx.method);
+  const size_t rbs = rec_block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
+  float lmax[TRANSFORM_PP], rmax[TRANSFORM_PP];
+#pragma unroll
+  for (int p = 0; p < TRANSFORM_PP; ++p) lmax[p] = rmax[p] = 0.f;
   for (int i = threadIdx.x; i < cx.n_lig_pad; i += blockDim.x) {
-    double x = LIG_PAD, y = LIG_PAD, z = LIG_PAD;
+    double x[TRANSFORM_PP], y[TRANSFORM_PP], z[TRANSFORM_PP];
     float tw = 0.f;  // DFIRE: (float)(type * RG_SLOTS), see dfire_items()
-    if (i < cx.n_lig) {
-      // rotate(): self * (0, v) * self.inverse(), src/qt.rs:57-61
+    const bool real = i < cx.n_lig;
+    if (real) {
       const Quat v = {0.0, cx.lig_x[i], cx.lig_y[i], cx.lig_z[i]};
-      const Quat r = qmul(qmul(q, v), qi);
-      x = __dadd_rn(r.x, tx);  // src/dfire.rs:286-288
-      y = __dadd_rn(r.y, ty);
-      z = __dadd_rn(r.z, tz);
-      for (int k = 0; k < cx.n_lig_modes; ++k) {  // src/dfire.rs:290-301
-        const double e = lig_ext[k];
-        const double *m = cx.lig_modes + (size_t)k * 3 * cx.n_lig_pad;
-        x = __dadd_rn(x, __dmul_rn(m[i], e));
-        y = __dadd_rn(y, __dmul_rn(m[cx.n_lig_pad + i], e));
-        z = __dadd_rn(z, __dmul_rn(m[2 * cx.n_lig_pad + i], e));
+#pragma unroll
+      for (int p = 0; p < TRANSFORM_PP; ++p) {
+        if (p >= np) break;
+        const double *o = s_pose[p];
+        const Quat q = {o[3], o[4], o[5], o[6]}, qi = {o[7], o[8], o[9], o[10]};
+        // rotate(): self * (0, v) * self.inverse(), src/qt.rs:57-61
+        const Quat r = qmul(qmul(q, v), qi);
+        x[p] = __dadd_rn(r.x, o[0]);  // src/dfire.rs:286-288
+        y[p] = __dadd_rn(r.y, o[1]);
+        z[p] = __dadd_rn(r.z, o[2]);
       }
-      lmax = fmaxf(lmax, fmaxf(fabsf((float)x), fmaxf(fabsf((float)y), fabsf((float)z))));
+      for (int k = 0; k < cx.n_lig_modes; ++k) {  // src/dfire.rs:290-301
+        const double *m = cx.lig_modes + (size_t)k * 3 * cx.n_lig_pad;
+        const double mx = m[i], my = m[cx.n_lig_pad + i], mz = m[2 * cx.n_lig_pad + i];
+#pragma unroll
+        for (int p = 0; p < TRANSFORM_PP; ++p) {
+          if (p >= np) break;
+          const double e = s_ext[p * n_ext + cx.n_rec_modes + k];
+          x[p] = __dadd_rn(x[p], __dmul_rn(mx, e));
+          y[p] = __dadd_rn(y[p], __dmul_rn(my, e));
+          z[p] = __dadd_rn(z[p], __dmul_rn(mz, e));
+        }
+      }
       if (cx.method == 0) tw = (float)((cx.lig_tb20[i] / 20) * RG_SLOTS);
     }
-    ox[i] = x; oy[i] = y; oz[i] = z;
-    if (cx.method == 0) {
-      of4[i] = make_float4((float)x, (float)y, (float)z, tw);
-    } else {
-      od4[2 * i] = make_double2(x, y);
-      od4[2 * i + 1] = make_double2(z, cx.lig_q[i]);  // pads carry charge 0
+    const double lq = (cx.method != 0 && real) ? cx.lig_q[i] : 0.0;  // pads carry charge 0
+#pragma unroll
+    for (int p = 0; p < TRANSFORM_PP; ++p) {
+      if (p >= np) break;
+      if (!real) x[p] = y[p] = z[p] = LIG_PAD;
+      else lmax[p] = fmaxf(lmax[p], fmaxf(fabsf((float)x[p]), fmaxf(fabsf((float)y[p]), fabsf((float)z[p]))));
+      unsigned char *lb = bb.lig_blocks + (size_t)(p0 + p) * lbs;
+      double *ox = reinterpret_cast<double *>(lb);
+      ox[i] = x[p]; ox[cx.n_lig_pad + i] = y[p]; ox[2 * cx.n_lig_pad + i] = z[p];
+      if (cx.method == 0) {
+        reinterpret_cast<float4 *>(lb + lig_off_f4(cx.n_lig_pad))[i] = make_float4((float)x[p], (float)y[p], (float)z[p], tw);
+      } else {
+        double2 *od4 = reinterpret_cast<double2 *>(lb + lig_off_f4(cx.n_lig_pad));
+        od4[2 * i] = make_double2(x[p], y[p]);
+        od4[2 * i + 1] = make_double2(z[p], lq);
+      }
     }
   }
-  double *rx = nullptr, *ry = nullptr, *rz = nullptr;
-  float4 *rsph = nullptr, *rmeta = nullptr;
   if (cx.n_rec_modes > 0) {  // src/dfire.rs:304-320
-    unsigned char *rb = bb.rec_blocks + (size_t)p * rec_block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
-    rx = reinterpret_cast<double *>(rb); ry = rx + cx.n_rec_pad; rz = ry + cx.n_rec_pad;
-    rsph = reinterpret_cast<float4 *>(rz + cx.n_rec_pad);
-    rmeta = rsph + cx.n_rec_tiles;
     for (int i = threadIdx.x; i < cx.n_rec_pad; i += blockDim.x) {
-      double x = cx.rec_x[i], y = cx.rec_y[i], z = cx.rec_z[i];
+      double x[TRANSFORM_PP], y[TRANSFORM_PP], z[TRANSFORM_PP];
+      const double x0 = cx.rec_x[i], y0 = cx.rec_y[i], z0 = cx.rec_z[i];
+#pragma unroll
+      for (int p = 0; p < TRANSFORM_PP; ++p) { x[p] = x0; y[p] = y0; z[p] = z0; }
       if (i < cx.n_rec) {
         for (int k = 0; k < cx.n_rec_modes; ++k) {
-          const double e = rec_ext[k];
           const double *m = cx.rec_modes + (size_t)k * 3 * cx.n_rec_pad;
-          x = __dadd_rn(x, __dmul_rn(m[i], e));
-          y = __dadd_rn(y, __dmul_rn(m[cx.n_rec_pad + i], e));
-          z = __dadd_rn(z, __dmul_rn(m[2 * cx.n_rec_pad + i], e));
+          const double mx = m[i], my = m[cx.n_rec_pad + i], mz = m[2 * cx.n_rec_pad + i];
+#pragma unroll
+          for (int p = 0; p < TRANSFORM_PP; ++p) {
+            if (p >= np) break;
+            const double e = s_ext[p * n_ext + k];
+            x[p] = __dadd_rn(x[p], __dmul_rn(mx, e));
+            y[p] = __dadd_rn(y[p], __dmul_rn(my, e));
+            z[p] = __dadd_rn(z[p], __dmul_rn(mz, e));
+          }
         }
-        rmax = fmaxf(rmax, fmaxf(fabsf((float)x), fmaxf(fabsf((float)y), fabsf((float)z))));
       }
-      rx[i] = x; ry[i] = y; rz[i] = z;
+#pragma unroll
+      for (int p = 0; p < TRANSFORM_PP; ++p) {
+        if (p >= np) break;
+        if (i < cx.n_rec)
+          rmax[p] = fmaxf(rmax[p], fmaxf(fabsf((float)x[p]), fmaxf(fabsf((float)y[p]), fabsf((float)z[p]))));
+        double *rx = reinterpret_cast<double *>(bb.rec_blocks + (size_t)(p0 + p) * rbs);
+        rx[i] = x[p]; rx[cx.n_rec_pad + i] = y[p]; rx[2 * cx.n_rec_pad + i] = z[p];
+      }
     }
   }
-  lmax = warp_max_f(lmax);
-  rmax = warp_max_f(rmax);
-  if ((threadIdx.x & 31) == 0) { s_max[0][threadIdx.x >> 5] = lmax; s_max[1][threadIdx.x >> 5] = rmax; }
-  __syncthreads();  // block-scope visibility of the coordinates just written + the per-warp maxima
-  if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < 8; ++w) { a = fmaxf(a, s_max[0][w]); b = fmaxf(b, s_max[1][w]); }
-    // inflate: the f32 conversions above round to nearest
-    *ometa = make_float4(a * 1.0001f + 1.0f, 0.f, 0.f, 0.f);
-    if (rmeta) *rmeta = make_float4(b * 1.0001f + 1.0f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int p = 0; p < TRANSFORM_PP; ++p) {
+    const float a = warp_max_f(lmax[p]), b = warp_max_f(rmax[p]);
+    if ((threadIdx.x & 31) == 0) { s_max[p][0][threadIdx.x >> 5] = a; s_max[p][1][threadIdx.x >> 5] = b; }
   }
-  for (int t = threadIdx.x; t < cx.n_lig_tiles; t += blockDim.x) {
+  __syncthreads();  // block-scope visibility of the coordinates just written + the per-warp maxima
+  if (threadIdx.x < np) {
+    const int p = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < 8; ++w) { a = fmaxf(a, s_max[p][0][w]); b = fmaxf(b, s_max[p][1][w]); }
+    // inflate: the f32 conversions above round to nearest
+    unsigned char *lb = bb.lig_blocks + (size_t)(p0 + p) * lbs;
+    *reinterpret_cast<float4 *>(lb + lig_off_meta(cx.n_lig_pad, cx.n_lig_tiles, cx.method)) =
+        make_float4(a * 1.0001f + 1.0f, 0.f, 0.f, 0.f);
+    if (cx.n_rec_modes > 0) {
+      unsigned char *rb = bb.rec_blocks + (size_t)(p0 + p) * rbs;
+      reinterpret_cast<float4 *>(rb + (size_t)cx.n_rec_pad * 24)[cx.n_rec_tiles] = make_float4(b * 1.0001f + 1.0f, 0.f, 0.f, 0.f);
+    }
+  }
+  for (int w = threadIdx.x; w < np * cx.n_lig_tiles; w += blockDim.x) {
+    const int p = w / cx.n_lig_tiles, t = w % cx.n_lig_tiles;
+    unsigned char *lb = bb.lig_blocks + (size_t)(p0 + p) * lbs;
+    const double *ox = reinterpret_cast<const double *>(lb);
     const int a = t * LIG_TILE, b = min(a + LIG_TILE, cx.n_lig);
-    osph[t] = tile_sphere(ox, oy, oz, a, b);
+    reinterpret_cast<float4 *>(lb + lig_off_sph(cx.n_lig_pad, cx.method))[t] =
+        tile_sphere(ox, ox + cx.n_lig_pad, ox + 2 * cx.n_lig_pad, a, b);
   }
   if (cx.n_rec_modes > 0)
-    for (int t = threadIdx.x; t < cx.n_rec_tiles; t += blockDim.x) {
+    for (int w = threadIdx.x; w < np * cx.n_rec_tiles; w += blockDim.x) {
+      const int p = w / cx.n_rec_tiles, t = w % cx.n_rec_tiles;
+      unsigned char *rb = bb.rec_blocks + (size_t)(p0 + p) * rbs;
+      const double *rx = reinterpret_cast<const double *>(rb);
       const int a = t * REC_TILE, b = min(a + REC_TILE, cx.n_rec);
-      rsph[t] = tile_sphere(rx, ry, rz, a, b);
+      reinterpret_cast<float4 *>(rb + (size_t)cx.n_rec_pad * 24)[t] =
+          tile_sphere(rx, rx + cx.n_rec_pad, rx + 2 * cx.n_rec_pad, a, b);
     }
 }
 

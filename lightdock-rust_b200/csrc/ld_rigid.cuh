@@ -81,6 +81,7 @@ struct RigidComplex {
   const long long *potx_fx;             // potx * fx_scale rounded to nearest: same layout
   double fx_scale;                      // 2^k
   const float *tile_slack;              // [n_lig_tiles] slack the current lists were built with
+  float grid_maxabs;                    // largest |coordinate| inside the cell grid (the M of the FP32 error bound)
 };
 
 // ligand copies: 1 (rigid: shared by the CTA) or one per warp (FLEX: each warp works on its own pose)
@@ -130,7 +131,9 @@ __global__ void __launch_bounds__(256) rigid_prep_kernel(const double *poses, in
 //   lig4p[p][j]    ligand-frame position l_j + R^T D_j, D_j = sum_k mode_k[j] * extent_k (src/dfire.rs:290-301 gives
 //                  the lab-frame R l_j + t + D_j; the same point seen from the ligand's frame), rounded to f32, with
 //                  the table column offset in .w (copied from the static lig4)
-//   pose_flag[p]   1 if some ligand tile moved further than the slack its cell lists were built with
+//   pose_flag[p]   0 if every ligand tile stayed within the slack its cell lists were built with; otherwise the
+//                  pose's largest tile displacement (> 0): the pair kernel then scores the pose against every ligand
+//                  tile and widens its FP32 margins to the larger coordinates that can be in range
 //   need[t]        running maximum (over every pose ever prepared) of tile t's displacement, for the host to grow
 //                  the slacks; non-negative floats compared as integers
 // The displacements only feed the f32 coordinates and the (conservative, inflated) slack test; every decision that
@@ -139,12 +142,12 @@ constexpr int FLEX_PP = 8;
 constexpr int FLEX_THREADS = 128;
 __global__ void __launch_bounds__(FLEX_THREADS)
     flex_prep_kernel(const RigidComplex rc, const double *__restrict__ poses, int n_poses, double *__restrict__ prep,
-                     float4 *__restrict__ lig4p, unsigned char *__restrict__ pose_flag, int *__restrict__ need) {
+                     float4 *__restrict__ lig4p, float *__restrict__ pose_flag, int *__restrict__ need) {
   extern __shared__ __align__(16) unsigned char smem_flex[];
   double *sM = reinterpret_cast<double *>(smem_flex);                       // [FLEX_PP][16]
   double *sE = sM + FLEX_PP * RG_PREP;                                      // [FLEX_PP][n_lig_modes]
   int *sD = reinterpret_cast<int *>(sE + FLEX_PP * max(rc.n_lig_modes, 1)); // [FLEX_PP][n_lig_tiles] max |D|^2 (float bits)
-  __shared__ int s_flag[FLEX_PP];
+  __shared__ int s_flag[FLEX_PP], s_dmax[FLEX_PP];
   const int p0 = blockIdx.x * FLEX_PP, np = min(FLEX_PP, n_poses - p0);
   const int tid = threadIdx.x;
   if (tid < np) {
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(FLEX_THREADS)
 #pragma unroll
     for (int i = 0; i < RG_PREP; ++i) g[i] = o[i];
     s_flag[tid] = 0;
+    s_dmax[tid] = 0;
   }
   for (int i = tid; i < np * rc.n_lig_modes; i += FLEX_THREADS) {
     const int p = i / rc.n_lig_modes, k = i % rc.n_lig_modes;
@@ -215,10 +219,11 @@ __global__ void __launch_bounds__(FLEX_THREADS)
     // displacement of the tile, inflated (f32 square root rounded up, plus the f32 rounding of the coordinates)
     const float d = __fsqrt_ru(__int_as_float(sD[p * rc.n_lig_tiles + t])) * 1.000001f + 1.0e-5f;
     if (d > rc.tile_slack[t]) s_flag[p] = 1;
+    atomicMax(&s_dmax[p], __float_as_int(d));
     if (__float_as_int(d) > need[t]) atomicMax(&need[t], __float_as_int(d));
   }
   __syncthreads();
-  if (tid < np) pose_flag[p0 + tid] = (unsigned char)s_flag[tid];
+  if (tid < np) pose_flag[p0 + tid] = s_flag[tid] ? __int_as_float(s_dmax[tid]) : 0.f;
 }
 __host__ __device__ inline size_t flex_prep_smem(int n_lig_modes, int n_lig_tiles) {
   return (size_t)FLEX_PP * RG_PREP * 8 + (size_t)FLEX_PP * (n_lig_modes > 1 ? n_lig_modes : 1) * 8 +
@@ -293,14 +298,14 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
                                           uint32_t lane_sw, bool active, int o, int lt, float rxf, float ryf,
                                           float rzf, unsigned rowoff, int p, int pos_base,
                                           typename RgAcc<FLEX>::type &acc0, typename RgAcc<FLEX>::type &acc1,
-                                          unsigned &ifr_mask, const RigidComplex *rc_dev, const double *prep) {
+                                          unsigned &ifr_mask, const RigidComplex *rc_dev, const double *prep,
+                                          float thr_out, float hme, float delta) {
   ld_pose_detail *dt = DETAIL ? reinterpret_cast<ld_pose_detail *>(bb.detail) + p : nullptr;
   const int lane = threadIdx.x & 31;
   const float ax = __shfl_sync(0xffffffffu, rxf, o), ay = __shfl_sync(0xffffffffu, ryf, o),
               az = __shfl_sync(0xffffffffu, rzf, o);
   const unsigned rb = __shfl_sync(0xffffffffu, rowoff, o);
   if (!active) return;
-  const float thr_out = rc.thr_out, hme = rc.half_minus_eps, delta = rc.delta;
   const int jbase = lt * LIG_TILE;
   // tile base (128-byte aligned) | per-lane slot: atom (k ^ lane) & 7 of the tile, so that any 8 consecutive
   // lanes read 8 different 16-byte slots -> conflict-free LDS.128 whatever tiles the lanes hold
@@ -400,7 +405,7 @@ template <bool DETAIL, bool FLEX>
 __global__ void __launch_bounds__(RG_THREADS, 1)
     dfire_rigid_kernel(const RigidComplex rc, const BatchBuffers bb, int n_poses, int poses_per_unit, int n_chunks,
                        unsigned *unit_counter, const RigidComplex *rc_dev, const double *prep_all,
-                       const float4 *__restrict__ lig4p, const unsigned char *__restrict__ pose_flag) {
+                       const float4 *__restrict__ lig4p, const float *__restrict__ pose_flag) {
   typedef typename RgAcc<FLEX>::type acc_t;
   unsigned char *smem_raw = smem_rigid;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
@@ -473,11 +478,24 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
       if (p >= p1) break;
       const double *prep = prep_all + (size_t)p * RG_PREP;
       bool brute = false;
+      // FP32 classification margins (see rigid_row): the handle's, valid for coordinates inside the cell grid
+      float thr_out = rc.thr_out, hme = rc.half_minus_eps, delta102 = rc.delta, reach_abs = 3.0e38f;
       if (FLEX) {
         // this pose's ligand block (ligand frame, f32) into the warp's slice of shared memory
         const float4 *src = lig4p + (size_t)p * rc.n_lig_pad;
         for (int i = lane; i < rc.n_lig_pad; i += 32) l4[i] = __ldg(src + i);
-        brute = pose_flag[p] != 0;
+        const float dmax = pose_flag[p];
+        brute = dmax != 0.f;
+        if (brute) {
+          // A tile moved further than its slack: every ligand tile is a candidate, and an atom can be in range up to
+          // dmax outside the grid, so the bound M on the coordinates (hence delta) grows by dmax; beyond the range
+          // the bin-space test was proven for (delta < 0.01) nothing is decided in FP32 (hme < 0: all exact).
+          reach_abs = rc.grid_maxabs + dmax + 0.1f;
+          const float d = 2.0e-4f + 1.3e-5f * reach_abs;
+          thr_out = 225.0f + d;
+          delta102 = 1.02f * d;
+          hme = d < 0.01f ? rc.half_minus_eps : -1.0f;
+        }
         __syncwarp();
       }
       float fx, fy, fz;
@@ -508,7 +526,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
         my_n = (int)rowoff == -1 ? 0 : (int)ce.y;  // pad lanes own nothing
         if (FLEX && brute) {  // every ligand tile, whatever the lists say: entry k of the "list" is tile k
           my_off = 0u;
-          my_n = (int)rowoff == -1 ? 0 : rc.n_lig_tiles;
+          // an atom further out than the grid grown by dmax has no partner within 15 A
+          const bool far = fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))) > reach_abs;
+          my_n = ((int)rowoff == -1 || far || !(fx == fx)) ? 0 : rc.n_lig_tiles;
         }
       }
       auto tile_at = [&](unsigned idx) -> unsigned {
@@ -578,7 +598,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
         act = act_nxt; o = o_nxt; lt = lt_nxt;
         have = produce();
         rigid_row<DETAIL, FLEX>(rc, bb, l4_addr, lane_sw, act, o, (int)lt, fx, fy, fz, rowoff, p, pos_base, acc0,
-                                acc1, ifr_mask, rc_dev, prep);
+                                acc1, ifr_mask, rc_dev, prep, thr_out, hme, delta102);
       }
       __syncwarp();  // FLEX: also "every lane is done with this pose's ligand block"
       const acc_t tsum = warp_sum(rg_join(acc0, acc1));

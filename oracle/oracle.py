@@ -77,7 +77,16 @@ class Atom:
 
 
 def read_pdb(path):
-    chains = {}  # chain id -> {(resseq, icode, resname) -> [atoms]} ; dicts keep insertion order
+    """Atoms in the order `for chain in pdb.chains() { for residue in chain.residues() { for atom in residue.atoms()`
+    visits them (src/dfire.rs:128-133) with pdbtbx 0.11's containers, restated from its published data model (the
+    crate is not vendored under /root/reference; Cargo.toml:13 pins "0.11"): first model only; a chain per chain id in
+    order of first appearance (a later record with an earlier chain's id joins that chain); inside a chain a residue
+    per (serial number, insertion code) in order of first appearance; inside a residue a conformer per (residue name,
+    alternative location) in order of first appearance -- atoms WITHOUT an alternative location form their own
+    conformer --, and Residue::atoms() walks the conformers in that order.  Pinned only as far as the reference's
+    fixtures go: every BASELINE structure is contiguous and alt-loc free except four residues of
+    example/2uuy/lightdock_2UUY_lig.pdb; behaviour on other layouts is "parity unpinned" (DESIGN.md)."""
+    chains = {}  # chain id -> {(resseq, icode) -> {(resname, altloc) -> [atoms]}} ; dicts keep insertion order
     with open(path) as f:
         for line in f:
             rec = line[:6]
@@ -87,16 +96,21 @@ def read_pdb(path):
                 continue
             a = Atom()
             a.name = line[12:16].strip()
+            alt = line[16:17].strip()
             a.resname = line[17:20].strip()
             a.chain = line[21]
             a.resseq = int(line[22:26])
             a.icode = line[26].strip()
             a.x, a.y, a.z = float(line[30:38]), float(line[38:46]), float(line[46:54])
-            chains.setdefault(a.chain, {}).setdefault((a.resseq, a.icode, a.resname), []).append(a)
+            chains.setdefault(a.chain, {}).setdefault((a.resseq, a.icode), {}).setdefault((a.resname, alt), []).append(a)
     atoms = []
     for ch in chains.values():
         for res in ch.values():
-            atoms.extend(res)
+            names = {k[0] for k in res}
+            if len(names) > 1:  # Residue::name() is None when conformers disagree: the reference panics (src/dfire.rs:134-137)
+                raise ValueError("PDB Parsing Error: Residue name error")
+            for conf in res.values():
+                atoms.extend(conf)
     return atoms
 
 
