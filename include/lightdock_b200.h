@@ -138,6 +138,39 @@ int ld_score_batch_end(ld_handle *h, int32_t slot, double *energies);
 int ld_score_batch_device(ld_handle *h, int64_t n_poses, const double *d_poses, double *d_energies,
                           void *stream);
 
+/* ---- Device-resident GSO -------------------------------------------------------------------
+ * The whole optimisation loop of GSO::run (src/lib.rs:46-58) on the device, for n_swarms independent swarms of the
+ * handle's complex advanced in lock-step: Swarm::update_luciferin (src/swarm.rs:66-70, src/glowworm.rs:61-72),
+ * Swarm::movement_phase (src/swarm.rs:72-126: snapshot, neighbour search, probabilities, one StdRng draw per glowworm,
+ * Glowworm::move_towards incl. Quaternion::slerp src/qt.rs:67-91, update_vision_range) and the scoring pass of the
+ * glowworms that moved -- no host round trip per step.  Each swarm consumes the ChaCha20 stream of
+ * `StdRng::seed_from_u64(seeds[s])` exactly as a stand-alone reference process would (the stream is evaluated on the
+ * device).  All arithmetic is f64 in the reference's operation order; the only place where the device can round
+ * differently from a host run is acos/sin inside slerp (CUDA's libm vs the host's), i.e. poses agree to ~1e-15
+ * relative per step, far inside the 1e-6 contract, instead of bit for bit -- which is why the drop-in CLI keeps the
+ * host loop by default and takes this one on request (LIGHTDOCK_GSO=device).
+ * A swarm that hits what is a panic in the reference (roulette overrun / draw of exactly 0, src/glowworm.rs:114-126)
+ * stops at that step, as its own process would; the other swarms go on (failed_step reports it).
+ *
+ * positions: [n_swarms][n_glowworms][ld_pose_len(h)] start poses (src/swarm.rs:26-64); seeds: [n_swarms].
+ * One ld_gso per handle at a time; between ld_gso_create and ld_gso_destroy the handle's other scoring calls may be
+ * used only while no ld_gso_run is executing (they share the handle's slot-0 work buffers and stream). */
+typedef struct ld_gso ld_gso;
+#define LD_GSO_MAX_GLOWWORMS 1024
+int ld_gso_create(ld_handle *h, int32_t n_swarms, int32_t n_glowworms, const double *positions, const uint64_t *seeds,
+                  ld_gso **out);
+/* Advances every swarm by n_steps GSO steps (step numbering continues from the previous call) and waits. */
+int ld_gso_run(ld_gso *g, int32_t n_steps);
+/* The swarm state as Swarm::save prints it (src/swarm.rs:128-167), after the steps run so far: poses
+ * [S][n][pose_len], luciferin / vision_range / scoring [S][n], n_neighbors [S][n], failed_step [S] (0 = running).
+ * Any pointer may be NULL. */
+int ld_gso_state(ld_gso *g, double *poses, double *luciferin, double *vision_range, double *scoring,
+                 int32_t *n_neighbors, int32_t *failed_step);
+/* Steps run so far / Score::energy evaluations so far (glowworms rescored: `moved || step == 0`, src/glowworm.rs:62). */
+int32_t ld_gso_steps(const ld_gso *g);
+int64_t ld_gso_energy_calls(const ld_gso *g);
+int ld_gso_destroy(ld_gso *g);
+
 /* Same as ld_score_batch plus the per-pose diagnostics.  iface_rec [n_poses][n_rec] and iface_lig
  * [n_poses][n_lig] (0/1 bytes, ORIGINAL atom order; src/dfire.rs:322-323) may be NULL. */
 int ld_score_batch_detail(ld_handle *h, int64_t n_poses, const double *poses, double *energies,

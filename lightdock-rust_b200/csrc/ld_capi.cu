@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ld_cells.cuh"
+#include "ld_gso.cuh"
 #include "ld_kernels.cuh"
 #include "ld_rigid.cuh"
 
@@ -1055,8 +1056,11 @@ static int ensure_poses(ld_handle *h, int64_t n, bool detail) {
 
 // Launches transform -> pair -> finalize for poses [0, n) living on the device.
 // If host_iface_* are given (detail mode) the bitmaps of each chunk are copied back as they are produced.
+// d_n_live (device-resident callers): the number of real rows, known only on the device; the launches are sized for
+// n and every kernel skips the rows beyond *d_n_live.
 static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_energies, cudaStream_t st,
-                      ld_pose_detail *d_detail, std::vector<unsigned> *host_ifr, std::vector<unsigned> *host_ifl) {
+                      ld_pose_detail *d_detail, std::vector<unsigned> *host_ifr, std::vector<unsigned> *host_ifl,
+                      const int *d_n_live = nullptr) {
   Nvtx range_launch("ld: kernel launches (prep/transform, pair, finalize)");
   const DeviceComplex &cx = h->cx;
   h->w->stats = ld_batch_stats{};
@@ -1090,6 +1094,8 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       bb.rec_splits = 1;
       bb.tiles_per_split = rg.n_groups;
       bb.lig_words = lig_words;
+      bb.n_live = d_n_live;
+      bb.n_live_off = (int)p0;
       h->w->stats.rec_splits = 1;
       h->w->stats.path = LD_PATH_RIGID;
       if (!h->w->d_unit_counter) CU(cudaMalloc(reinterpret_cast<void **>(&h->w->d_unit_counter), sizeof(unsigned)));
@@ -1107,10 +1113,10 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       // FLEX adds the per-pose f32 ligand block and the slack test
       if (h->flex)
         flex_prep_kernel<<<(unsigned)((nc + FLEX_PP - 1) / FLEX_PP), FLEX_THREADS,
-                           flex_prep_smem(cx.n_lig_modes, cx.n_lig_tiles), st>>>(rg, bb.poses, (int)nc, h->w->d_prep,
+                           flex_prep_smem(cx.n_lig_modes, cx.n_lig_tiles), st>>>(rg, bb, bb.poses, (int)nc, h->w->d_prep,
                                                                                  h->w->d_lig4p, h->w->d_flag, h->d_need);
       else
-        rigid_prep_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(bb.poses, (int)nc, cx.pose_len, h->w->d_prep);
+        rigid_prep_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(bb, bb.poses, (int)nc, cx.pose_len, h->w->d_prep);
       ++launches;
       if ((rc = prof_mark(h, st)) != LD_OK) return rc;
       CU(cudaMemsetAsync(h->w->d_iface_lig, 0, (size_t)nc * lig_words * sizeof(unsigned), st));
@@ -1170,6 +1176,8 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
     bb.rec_splits = splits;
     bb.tiles_per_split = (std::max(1, cx.n_rec_tiles) + splits - 1) / splits;
     bb.lig_words = lig_words;
+    bb.n_live = d_n_live;
+    bb.n_live_off = (int)p0;
     h->w->stats.rec_splits = splits;
     if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     transform_kernel<<<(unsigned)((nc + TRANSFORM_PP - 1) / TRANSFORM_PP), 256,
@@ -1373,6 +1381,169 @@ extern "C" int ld_score_batch_end(ld_handle *h, int32_t slot, double *energies) 
   if (h->flex && use_rigid(h)) return grow_flex_slack(h);
   return LD_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident GSO (ld_gso.cuh)
+struct ld_gso {
+  ld_handle *h = nullptr;
+  GsoState st{};
+  int cur = 0;                 // buffer of st.poses holding the current poses
+  int step = 0;                // GSO steps run so far
+  int cap_steps = 0;           // entries of st.n_packed
+  int64_t energy_calls = 0;
+  std::vector<void *> owned;
+  int *h_counts = nullptr;     // pinned: n_packed of the steps of one ld_gso_run call
+};
+
+extern "C" int ld_gso_destroy(ld_gso *g) {
+  if (!g) return LD_OK;
+  cudaSetDevice(g->h->device);
+  if (g->h->ws[0].stream) cudaStreamSynchronize(g->h->ws[0].stream);
+  for (void *p : g->owned) cudaFree(p);
+  cudaFreeHost(g->h_counts);
+  delete g;
+  return LD_OK;
+}
+
+template <typename T>
+static int gso_alloc(ld_gso *g, T **p, size_t count) {
+  *p = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T)));
+  g->owned.push_back(*p);
+  return LD_OK;
+}
+
+static int gso_create_impl(ld_gso *g, const double *positions, const uint64_t *seeds) {
+  GsoState &st = g->st;
+  const size_t G = (size_t)st.n_swarms * st.n_glow, pl = (size_t)st.pose_len;
+  cudaStream_t stream = g->h->ws[0].stream;
+  int rc;
+  double *p0 = nullptr, *p1 = nullptr, *lum = nullptr, *vis = nullptr, *sc = nullptr, *packed = nullptr, *en = nullptr;
+  int *nn = nullptr, *slot = nullptr, *np = nullptr, *failed = nullptr;
+  uint32_t *keys = nullptr;
+  g->cap_steps = 1 << 16;
+  if ((rc = gso_alloc(g, &p0, G * pl)) || (rc = gso_alloc(g, &p1, G * pl)) || (rc = gso_alloc(g, &lum, G)) ||
+      (rc = gso_alloc(g, &vis, G)) || (rc = gso_alloc(g, &sc, G)) || (rc = gso_alloc(g, &packed, G * pl)) ||
+      (rc = gso_alloc(g, &en, G)) || (rc = gso_alloc(g, &nn, G)) || (rc = gso_alloc(g, &slot, G)) ||
+      (rc = gso_alloc(g, &np, (size_t)g->cap_steps)) || (rc = gso_alloc(g, &failed, (size_t)st.n_swarms)) ||
+      (rc = gso_alloc(g, &keys, (size_t)st.n_swarms * 8)))
+    return rc;
+  CU(cudaHostAlloc(reinterpret_cast<void **>(&g->h_counts), (size_t)g->cap_steps * sizeof(int), cudaHostAllocDefault));
+  st.poses[0] = p0; st.poses[1] = p1; st.luciferin = lum; st.vision = vis; st.scoring = sc; st.packed = packed;
+  st.energies = en; st.n_neighbors = nn; st.slot = slot; st.n_packed = np; st.failed = failed; st.keys = keys;
+  // Glowworm::new (src/glowworm.rs:29-59): luciferin 5, vision range 0.2, scoring 0, no neighbours; step 0 = every
+  // glowworm is scored by the first update_luciferin, so the first packed batch is every pose, in order
+  std::vector<double> h_lum(G, 5.0), h_vis(G, 0.2);
+  std::vector<int> h_slot(G);
+  std::iota(h_slot.begin(), h_slot.end(), 0);
+  // StdRng::seed_from_u64 (rand_core 0.5): the u64 expanded to the 256-bit ChaCha key by PCG32 output steps
+  std::vector<uint32_t> h_keys((size_t)st.n_swarms * 8);
+  for (int s = 0; s < st.n_swarms; ++s) {
+    uint64_t state = seeds[s];
+    for (int w = 0; w < 8; ++w) {
+      state = state * 6364136223846793005ULL + 11634580027462260723ULL;
+      const uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
+      const uint32_t rot = (uint32_t)(state >> 59);
+      h_keys[(size_t)s * 8 + w] = (xorshifted >> rot) | (xorshifted << ((32u - rot) & 31u));
+    }
+  }
+  const int first = (int)G;
+  CU(cudaMemcpyAsync(p0, positions, G * pl * sizeof(double), cudaMemcpyHostToDevice, stream));
+  CU(cudaMemcpyAsync(packed, positions, G * pl * sizeof(double), cudaMemcpyHostToDevice, stream));
+  CU(cudaMemcpyAsync(lum, h_lum.data(), G * sizeof(double), cudaMemcpyHostToDevice, stream));
+  CU(cudaMemcpyAsync(vis, h_vis.data(), G * sizeof(double), cudaMemcpyHostToDevice, stream));
+  CU(cudaMemcpyAsync(slot, h_slot.data(), G * sizeof(int), cudaMemcpyHostToDevice, stream));
+  CU(cudaMemcpyAsync(keys, h_keys.data(), h_keys.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  CU(cudaMemsetAsync(sc, 0, G * sizeof(double), stream));
+  CU(cudaMemsetAsync(nn, 0, G * sizeof(int), stream));
+  CU(cudaMemsetAsync(failed, 0, (size_t)st.n_swarms * sizeof(int), stream));
+  CU(cudaMemsetAsync(np, 0, (size_t)g->cap_steps * sizeof(int), stream));
+  CU(cudaMemcpyAsync(np, &first, sizeof(int), cudaMemcpyHostToDevice, stream));
+  CU(cudaStreamSynchronize(stream));  // the host vectors above go out of scope
+  return LD_OK;
+}
+
+extern "C" int ld_gso_create(ld_handle *h, int32_t n_swarms, int32_t n_glowworms, const double *positions,
+                             const uint64_t *seeds, ld_gso **out) {
+  if (out) *out = nullptr;
+  if (!h || !out || n_swarms <= 0 || n_glowworms <= 0 || !positions || !seeds)
+    return fail(LD_EINVAL, "ld_gso_create: bad argument");
+  if (n_glowworms > LD_GSO_MAX_GLOWWORMS)
+    return fail(LD_ELIMIT, "ld_gso_create: more than LD_GSO_MAX_GLOWWORMS glowworms per swarm");
+  if ((int64_t)n_swarms * n_glowworms > (int64_t)1 << 30) return fail(LD_ELIMIT, "ld_gso_create: too many glowworms");
+  if (h->ws[0].pending >= 0) return fail(LD_EINVAL, "ld_gso_create: slot 0 has a batch pending");
+  CU(cudaSetDevice(h->device));
+  ld_gso *g = new ld_gso();
+  g->h = h;
+  g->st.n_swarms = n_swarms;
+  g->st.n_glow = n_glowworms;
+  g->st.pose_len = h->cx.pose_len;
+  g->st.n_rec_ext = h->cx.n_rec_modes;
+  g->st.n_lig_ext = h->cx.n_lig_modes;
+  const int rc = gso_create_impl(g, positions, seeds);
+  if (rc != LD_OK) {
+    const std::string keep = g_err;
+    ld_gso_destroy(g);
+    g_err = keep;
+    return rc;
+  }
+  *out = g;
+  return LD_OK;
+}
+
+extern "C" int ld_gso_run(ld_gso *g, int32_t n_steps) {
+  if (!g || n_steps < 0) return fail(LD_EINVAL, "ld_gso_run: bad argument");
+  if (n_steps == 0) return LD_OK;
+  ld_handle *h = g->h;
+  if (g->step + n_steps >= g->cap_steps) return fail(LD_ELIMIT, "ld_gso_run: step counter capacity exceeded");
+  h->w = &h->ws[0];
+  if (h->w->pending >= 0) return fail(LD_EINVAL, "ld_gso_run: slot 0 has a batch pending");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t stream = h->w->stream;
+  const GsoState &st = g->st;
+  const int64_t G = (int64_t)st.n_swarms * st.n_glow;
+  const unsigned threads = (unsigned)((st.n_glow + 31) / 32 * 32);
+  const size_t smem = (size_t)st.n_glow * 4 * sizeof(double);
+  const int first = g->step;
+  Nvtx range("ld_gso_run");
+  for (int k = 0; k < n_steps; ++k) {
+    const int step = g->step + 1;  // 1-based, src/lib.rs:47
+    // update_luciferin's scoring pass: the rows packed by the previous step (all poses before step 1)
+    int rc = run_device(h, G, st.packed, st.energies, stream, nullptr, nullptr, nullptr, st.n_packed + (step - 1));
+    if (rc != LD_OK) return rc;
+    gso_step_kernel<<<(unsigned)st.n_swarms, threads, smem, stream>>>(st, step, g->cur);
+    CU(cudaGetLastError());
+    g->cur ^= 1;
+    g->step = step;
+  }
+  CU(cudaMemcpyAsync(g->h_counts, st.n_packed + first, (size_t)n_steps * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  const bool flex = h->flex && use_rigid(h);
+  if (flex) CU(cudaMemcpyAsync(h->h_need, h->d_need, (size_t)h->cx.n_lig_tiles * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CU(cudaStreamSynchronize(stream));
+  for (int k = 0; k < n_steps; ++k) g->energy_calls += g->h_counts[k];
+  if (flex) return grow_flex_slack(h);  // poses beyond the slacks were scored by brute force (exact); lists grow for the next call
+  return LD_OK;
+}
+
+extern "C" int ld_gso_state(ld_gso *g, double *poses, double *luciferin, double *vision_range, double *scoring,
+                            int32_t *n_neighbors, int32_t *failed_step) {
+  if (!g) return fail(LD_EINVAL, "ld_gso_state: bad argument");
+  CU(cudaSetDevice(g->h->device));
+  cudaStream_t stream = g->h->ws[0].stream;
+  const GsoState &st = g->st;
+  const size_t G = (size_t)st.n_swarms * st.n_glow;
+  if (poses) CU(cudaMemcpyAsync(poses, st.poses[g->cur], G * st.pose_len * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (luciferin) CU(cudaMemcpyAsync(luciferin, st.luciferin, G * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (vision_range) CU(cudaMemcpyAsync(vision_range, st.vision, G * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (scoring) CU(cudaMemcpyAsync(scoring, st.scoring, G * sizeof(double), cudaMemcpyDeviceToHost, stream));
+  if (n_neighbors) CU(cudaMemcpyAsync(n_neighbors, st.n_neighbors, G * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  if (failed_step) CU(cudaMemcpyAsync(failed_step, st.failed, (size_t)st.n_swarms * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  CU(cudaStreamSynchronize(stream));
+  return LD_OK;
+}
+
+extern "C" int32_t ld_gso_steps(const ld_gso *g) { return g ? g->step : LD_EINVAL; }
+extern "C" int64_t ld_gso_energy_calls(const ld_gso *g) { return g ? g->energy_calls : LD_EINVAL; }
 
 extern "C" int ld_score_batch_detail(ld_handle *h, int64_t n_poses, const double *poses, double *energies,
                                      ld_pose_detail *detail, uint8_t *iface_rec, uint8_t *iface_lig) {

@@ -119,6 +119,14 @@ struct BatchBuffers {
   int rec_splits;
   int tiles_per_split;
   int lig_words;
+  // Device-resident callers (ld_gso.cuh) only know on the DEVICE how many of the rows are real: when n_live is set,
+  // rows at and beyond *n_live - n_live_off are skipped by every kernel (the launch is sized for the capacity).
+  const int *n_live;
+  int n_live_off;
 };
+__device__ __forceinline__ int live_poses(const BatchBuffers &bb, int n_poses) {
+  if (bb.n_live == nullptr) return n_poses;
+  return max(0, min(n_poses, *bb.n_live - bb.n_live_off));
+}
 
 }  // namespace ldb200

@@ -117,10 +117,12 @@ __device__ __forceinline__ float warp_max_f(float v) {
 // and their order are the reference's: rotate, + translation, then mode k = 0, 1, ... each as multiply-then-add.
 constexpr int TRANSFORM_PP = 4;
 __global__ void __launch_bounds__(256) transform_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
+  n_poses = live_poses(bb, n_poses);
   __shared__ float s_max[TRANSFORM_PP][2][8];
   __shared__ double s_pose[TRANSFORM_PP][11];  // tx ty tz | q | q^-1
   extern __shared__ double s_ext[];            // [TRANSFORM_PP][n_rec_modes + n_lig_modes]
   const int p0 = blockIdx.x * TRANSFORM_PP, np = min(TRANSFORM_PP, n_poses - p0);
+  if (np <= 0) return;  // CTA-uniform (device-resident callers: rows beyond the live count)
   const int n_ext = cx.n_rec_modes + cx.n_lig_modes;
   if (threadIdx.x < np) {
     const double *pose = bb.poses + (size_t)(p0 + threadIdx.x) * cx.pose_len;
@@ -534,7 +536,7 @@ __global__ void __launch_bounds__(PAIR_THREADS, 2)
     dfire_pair_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int pose = blockIdx.x / bb.rec_splits, split = blockIdx.x % bb.rec_splits;
-  if (pose >= n_poses) return;
+  if (pose >= live_poses(bb, n_poses)) return;
   const int t0 = split * bb.tiles_per_split;
   const int t1 = min(t0 + bb.tiles_per_split, cx.n_rec_tiles);
   const PairSmem s = carve(smem_raw, cx, bb);
@@ -881,7 +883,7 @@ __global__ void __launch_bounds__(DNA_THREADS, DNA_CTAS_PER_SM)
     dna_pair_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int pose = blockIdx.x / bb.rec_splits, split = blockIdx.x % bb.rec_splits;
-  if (pose >= n_poses) return;
+  if (pose >= live_poses(bb, n_poses)) return;
   const int t0 = split * bb.tiles_per_split;
   const int t1 = min(t0 + bb.tiles_per_split, cx.n_rec_tiles);
   const PairSmem s = carve(smem_raw, cx, bb);
@@ -979,7 +981,7 @@ template <bool DETAIL>
 __global__ void __launch_bounds__(128) finalize_kernel(const DeviceComplex cx, const BatchBuffers bb, int n_poses) {
   const int pose = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  if (pose >= n_poses) return;
+  if (pose >= live_poses(bb, n_poses)) return;
   const unsigned *ifr = bb.iface_rec + (size_t)pose * cx.n_rec_tiles;
   const unsigned *ifl = bb.iface_lig + (size_t)pose * bb.rec_splits * bb.lig_words;
   unsigned hr = 0, hl = 0, hm = 0;

@@ -101,9 +101,10 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 //   prep[9..11] M t          -> ligand-frame position of a lab-frame point r is  M r - M t
 //   prep[12..15] q^-1 = conj(q)/norm2(q) exactly as Quaternion::inverse computes it (src/qt.rs:24-34,48-50),
 //               for the exact path.
-__global__ void __launch_bounds__(256) rigid_prep_kernel(const double *poses, int n_poses, int pose_len, double *prep) {
+__global__ void __launch_bounds__(256)
+    rigid_prep_kernel(const BatchBuffers bb, const double *poses, int n_poses, int pose_len, double *prep) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_poses) return;
+  if (p >= live_poses(bb, n_poses)) return;
   const double *pose = poses + (size_t)p * pose_len;
   const double tx = pose[0], ty = pose[1], tz = pose[2];
   const double qw = pose[3], qx = pose[4], qy = pose[5], qz = pose[6];
@@ -141,14 +142,17 @@ __global__ void __launch_bounds__(256) rigid_prep_kernel(const double *poses, in
 constexpr int FLEX_PP = 8;
 constexpr int FLEX_THREADS = 128;
 __global__ void __launch_bounds__(FLEX_THREADS)
-    flex_prep_kernel(const RigidComplex rc, const double *__restrict__ poses, int n_poses, double *__restrict__ prep,
-                     float4 *__restrict__ lig4p, float *__restrict__ pose_flag, int *__restrict__ need) {
+    flex_prep_kernel(const RigidComplex rc, const BatchBuffers bb, const double *__restrict__ poses, int n_poses,
+                     double *__restrict__ prep, float4 *__restrict__ lig4p, float *__restrict__ pose_flag,
+                     int *__restrict__ need) {
+  n_poses = live_poses(bb, n_poses);
   extern __shared__ __align__(16) unsigned char smem_flex[];
   double *sM = reinterpret_cast<double *>(smem_flex);                       // [FLEX_PP][16]
   double *sE = sM + FLEX_PP * RG_PREP;                                      // [FLEX_PP][n_lig_modes]
   int *sD = reinterpret_cast<int *>(sE + FLEX_PP * max(rc.n_lig_modes, 1)); // [FLEX_PP][n_lig_tiles] max |D|^2 (float bits)
   __shared__ int s_flag[FLEX_PP], s_dmax[FLEX_PP];
   const int p0 = blockIdx.x * FLEX_PP, np = min(FLEX_PP, n_poses - p0);
+  if (np <= 0) return;  // CTA-uniform
   const int tid = threadIdx.x;
   if (tid < np) {
     const double *pose = poses + (size_t)(p0 + tid) * rc.pose_len;
@@ -407,6 +411,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
                        unsigned *unit_counter, const RigidComplex *rc_dev, const double *prep_all,
                        const float4 *__restrict__ lig4p, const float *__restrict__ pose_flag) {
   typedef typename RgAcc<FLEX>::type acc_t;
+  n_poses = live_poses(bb, n_poses);
   unsigned char *smem_raw = smem_rigid;
   uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw);
   int *s_unit = reinterpret_cast<int *>(smem_raw + 8);
@@ -444,6 +449,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
     const int g = rc.group_order[u / n_chunks];
     const int p0 = (u % n_chunks) * poses_per_unit;
     const int p1 = min(p0 + poses_per_unit, n_poses);
+    if (p0 >= p1) continue;  // CTA-uniform: a unit beyond the live rows (device-resident callers)
     if (g != cur_g) {  // CTA-uniform
       if (threadIdx.x == 0) {
         fence_proxy_async();

@@ -520,4 +520,142 @@ void MultiGSO::run(uint32_t steps, int host_threads) {
   run_lane(all, scoring, steps, std::max(1, host_threads));
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+DeviceGSO::DeviceGSO(const Score *s) : scoring(s) {
+  if (!dynamic_cast<const CudaScore *>(s))
+    throw std::runtime_error("DeviceGSO needs a scoring object that lives on the GPU (CudaScore)");
+}
+
+void DeviceGSO::add(const std::vector<std::vector<double>> &positions, uint64_t seed, bool use_anm, size_t rec_num_anm,
+                    size_t lig_num_anm, std::string output_directory) {
+  pending_.push_back(Pending{positions, seed, use_anm, rec_num_anm, lig_num_anm, std::move(output_directory)});
+}
+
+namespace {
+struct GsoGuard {  // ld_gso_destroy on every exit path
+  ld_gso *g = nullptr;
+  ~GsoGuard() { ld_gso_destroy(g); }
+};
+}  // namespace
+
+void DeviceGSO::run(uint32_t steps, int host_threads) {
+  const size_t S = pending_.size();
+  swarms.clear();
+  failures_.clear();
+  energy_calls_ = 0;
+  if (S == 0) return;
+  const CudaScore *cs = dynamic_cast<const CudaScore *>(scoring);
+  const size_t pl = scoring->pose_len();
+  const size_t n = pending_[0].positions.size();
+  if (n == 0) return;
+  // pose rows as Swarm::add_glowworms + gather_poses make them (src/swarm.rs:26-64): translation, rotation, then the
+  // first pose_len - 7 extents; a start row with fewer columns is an out-of-bounds panic in the reference
+  std::vector<double> rows(S * n * pl);
+  std::vector<uint64_t> seeds(S);
+  for (size_t s = 0; s < S; ++s) {
+    const Pending &p = pending_[s];
+    if (p.positions.size() != n) throw std::runtime_error("DeviceGSO: every swarm must have the same number of glowworms");
+    const size_t want = 7 + (p.use_anm ? p.rec_num_anm + p.lig_num_anm : 0);
+    if (want != pl) throw std::runtime_error("DeviceGSO: swarm set-up does not match the scoring object's pose length");
+    for (size_t i = 0; i < n; ++i) {
+      if (p.positions[i].size() < pl)
+        throw std::runtime_error("index out of bounds: start position has fewer columns than the pose");
+      std::copy(p.positions[i].begin(), p.positions[i].begin() + pl, rows.begin() + (s * n + i) * pl);
+    }
+    seeds[s] = p.seed;
+  }
+  GsoGuard guard;
+  if (ld_gso_create(cs->handle(), (int32_t)S, (int32_t)n, rows.data(), seeds.data(), &guard.g) != LD_OK)
+    throw std::runtime_error(std::string("ld_gso_create: ") + ld_last_error());
+
+  // swarm state on the host, double-buffered: one copy is being written to disk while the next is fetched
+  struct Snapshot {
+    std::vector<double> poses, luciferin, vision, scoring;
+    std::vector<int32_t> n_neighbors, failed;
+  } snap[2];
+  for (Snapshot &b : snap) {
+    b.poses.resize(S * n * pl); b.luciferin.resize(S * n); b.vision.resize(S * n); b.scoring.resize(S * n);
+    b.n_neighbors.resize(S * n); b.failed.resize(S);
+  }
+  auto materialise = [&](const Snapshot &b, size_t s) {
+    const Pending &p = pending_[s];
+    Swarm sw;
+    std::vector<std::vector<double>> pos(n);
+    for (size_t i = 0; i < n; ++i) pos[i].assign(b.poses.begin() + (s * n + i) * pl, b.poses.begin() + (s * n + i + 1) * pl);
+    sw.add_glowworms(pos, scoring, p.use_anm, p.rec_num_anm, p.lig_num_anm);
+    for (size_t i = 0; i < n; ++i) {
+      Glowworm &g = sw.glowworms[i];
+      g.luciferin = b.luciferin[s * n + i];
+      g.vision_range = b.vision[s * n + i];
+      g.scoring = b.scoring[s * n + i];
+      g.neighbors.assign((size_t)b.n_neighbors[s * n + i], 0u);  // the count is what Swarm::save prints
+    }
+    return sw;
+  };
+  std::vector<std::string> save_error(S);
+  std::vector<int32_t> failed_at(S, 0);
+  std::thread writer;
+  auto join_writer = [&] { if (writer.joinable()) writer.join(); };
+  struct Joiner { std::function<void()> f; ~Joiner() { f(); } } joiner{join_writer};
+  uint32_t done = 0;
+  int which = 0;
+  const int nt = std::max(1, std::min<int>(host_threads, (int)S));
+  while (done < steps) {
+    // run up to the next step whose state is saved: 1, 10, 20, ... (src/lib.rs:51)
+    const uint32_t next = done == 0 ? 1 : std::min<uint32_t>(steps, (done / 10 + 1) * 10);
+    {
+      NvtxRange r("ld_gso_run (device-resident steps)");
+      for (uint32_t k = done; k < next; ++k) log_line(LogLevel::Info, "lightdock", "Step " + std::to_string(k + 1));
+      if (ld_gso_run(guard.g, (int32_t)(next - done)) != LD_OK)
+        throw std::runtime_error(std::string("ld_gso_run: ") + ld_last_error());
+    }
+    done = next;
+    const bool save_step = done % 10 == 0 || done == 1;
+    if (!save_step && done < steps) continue;
+    join_writer();  // the previous snapshot's files are on disk; its buffer is two saves old after the flip
+    Snapshot &b = snap[which];
+    which ^= 1;
+    if (ld_gso_state(guard.g, b.poses.data(), b.luciferin.data(), b.vision.data(), b.scoring.data(), b.n_neighbors.data(),
+                     b.failed.data()) != LD_OK)
+      throw std::runtime_error(std::string("ld_gso_state: ") + ld_last_error());
+    for (size_t s = 0; s < S; ++s)
+      if (b.failed[s] && !failed_at[s]) failed_at[s] = b.failed[s];
+    if (!save_step) break;
+    const uint32_t step = done;
+    writer = std::thread([&, step, nt, bp = &b] {
+      NvtxRange r("save (overlaps the next device steps)");
+      std::vector<std::thread> pool;
+      for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&, t] {
+          for (size_t s = (size_t)t; s < S; s += (size_t)nt) {
+            if (bp->failed[s] || pending_[s].output_directory.empty() || !save_error[s].empty()) continue;
+            try {
+              materialise(*bp, s).save(step, pending_[s].output_directory);
+            } catch (const std::exception &e) {
+              save_error[s] = std::string("step ") + std::to_string(step) + ": " + e.what();
+            }
+          }
+        });
+      for (auto &th : pool) th.join();
+    });
+  }
+  join_writer();
+  if (steps == 0) {  // nothing ran: the state is the start state
+    if (ld_gso_state(guard.g, snap[0].poses.data(), snap[0].luciferin.data(), snap[0].vision.data(), snap[0].scoring.data(),
+                     snap[0].n_neighbors.data(), snap[0].failed.data()) != LD_OK)
+      throw std::runtime_error(std::string("ld_gso_state: ") + ld_last_error());
+    which = 1;
+  }
+  const Snapshot &last = snap[which ^ 1];
+  swarms.reserve(S);
+  for (size_t s = 0; s < S; ++s) swarms.push_back(materialise(last, s));
+  energy_calls_ = (uint64_t)ld_gso_energy_calls(guard.g);
+  for (size_t s = 0; s < S; ++s) {
+    if (failed_at[s])  // src/glowworm.rs:114-126: the reference indexes past its probabilities and panics
+      failures_.emplace_back(s, "step " + std::to_string(failed_at[s]) + ": index out of bounds in select_random_neighbor");
+    else if (!save_error[s].empty())
+      failures_.emplace_back(s, save_error[s]);
+  }
+}
+
 }  // namespace lightdock

@@ -110,4 +110,34 @@ struct MultiGSO {
   void run_lane(const std::vector<size_t> &mine, const Score *sc, uint32_t steps, int host_threads);
 };
 
+// The same optimisation with the WHOLE step on the device (include/lightdock_b200.h: ld_gso_*):
+// luciferin update, neighbour search, roulette (the swarm's own ChaCha20 stream, evaluated on the device), move_towards
+// and the rescoring of the glowworms that moved run without a host round trip per step; the host only fetches the
+// swarm state at the steps Swarm::save writes (1 and every 10th, src/lib.rs:51) and writes the files while the device
+// runs on.  Same interface as MultiGSO.  Every decision is taken in the reference's f64 operation order; poses can
+// differ from a host run in the last bits (CUDA's acos/sin inside slerp), so this path is opt-in (LIGHTDOCK_GSO=device
+// in the drivers) and the byte-identical host loop stays the default.  All swarms must have the same glowworm count.
+struct DeviceGSO {
+  const Score *scoring;
+  std::vector<Swarm> swarms;  // state after run(): poses, luciferin, scoring, vision range, neighbour COUNT per glowworm
+  explicit DeviceGSO(const Score *s);  // throws unless `s` scores on the GPU (CudaScore)
+  void add(const std::vector<std::vector<double>> &positions, uint64_t seed, bool use_anm, size_t rec_num_anm,
+           size_t lig_num_anm, std::string output_directory);
+  void run(uint32_t steps, int host_threads = 1);
+  uint64_t energy_calls() const { return energy_calls_; }
+  std::vector<std::pair<size_t, std::string>> failures() const { return failures_; }
+
+ private:
+  struct Pending {
+    std::vector<std::vector<double>> positions;
+    uint64_t seed;
+    bool use_anm;
+    size_t rec_num_anm, lig_num_anm;
+    std::string output_directory;
+  };
+  std::vector<Pending> pending_;
+  uint64_t energy_calls_ = 0;
+  std::vector<std::pair<size_t, std::string>> failures_;
+};
+
 }  // namespace lightdock

@@ -181,6 +181,42 @@ int ldh_case_multi_gso(ldh_case *c, int n_swarms, int n_glowworms, const double 
   LDH_CATCH(-1)
 }
 
+// The same run with the whole GSO step on the device (DeviceGSO -> ld_gso_*).  Arguments as ldh_case_multi_gso.
+int ldh_case_device_gso(ldh_case *c, int n_swarms, int n_glowworms, const double *positions,
+                        const unsigned long long *seeds, unsigned steps, int host_threads, const char *const *out_dirs,
+                        double *final_state, unsigned long long *energy_calls) {
+  LDH_TRY
+  const SetupFile &s = c->lc.setup;
+  const size_t pl = c->lc.scoring->pose_len();
+  DeviceGSO multi(c->lc.scoring.get());
+  for (int w = 0; w < n_swarms; ++w) {
+    std::vector<std::vector<double>> pos(n_glowworms);
+    for (int g = 0; g < n_glowworms; ++g) {
+      const double *row = positions + ((size_t)w * n_glowworms + g) * pl;
+      pos[g].assign(row, row + pl);
+    }
+    multi.add(pos, seeds[w], s.use_anm, s.anm_rec, s.anm_lig, out_dirs && out_dirs[w] ? out_dirs[w] : "");
+  }
+  multi.run(steps, host_threads);
+  if (energy_calls) *energy_calls = multi.energy_calls();
+  const auto failures = multi.failures();
+  if (final_state)
+    for (int w = 0; w < n_swarms; ++w)
+      for (int i = 0; i < n_glowworms; ++i) {
+        const Glowworm &g = multi.swarms[w].glowworms[i];
+        double *r = final_state + ((size_t)w * n_glowworms + i) * (4 + pl);
+        r[0] = g.luciferin; r[1] = g.scoring; r[2] = (double)g.neighbors.size(); r[3] = g.vision_range;
+        g.write_pose(r + 4);
+      }
+  if (!failures.empty()) {
+    std::string msg = std::to_string(failures.size()) + " swarm(s) stopped early:";
+    for (const auto &f : failures) msg += " [" + std::to_string(f.first) + "] " + f.second + ";";
+    throw std::runtime_error(msg);
+  }
+  return 0;
+  LDH_CATCH(-1)
+}
+
 // Host-only pieces, testable without a GPU ------------------------------------------------------
 // The neighbour search of Swarm::movement_phase on a given swarm state.  xyz [n][3]; out_offsets [n+1];
 // out_idx must hold n*(n-1) entries.  Returns the total number of neighbours.

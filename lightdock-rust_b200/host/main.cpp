@@ -3,6 +3,7 @@
 // Same argv, same progress lines, same path-resolution quirks (PDBs relative to the setup.json
 // directory; rec_nm.npy / lig_nm.npy, data/DCparams and swarm_N/ relative to the CWD), same
 // swarm_N/gso_<step>.out files.  Scoring runs on CUDA device $LIGHTDOCK_B200_DEVICE (default 0).
+// LIGHTDOCK_GSO=device moves the whole GSO step onto the GPU as well (host/gso.hpp: DeviceGSO).
 #include <sys/stat.h>
 
 #include <algorithm>
@@ -44,10 +45,26 @@ static int simulate(const std::string &simulation_path, const SetupFile &setup, 
   LoadedCase lc = load_case(simulation_path, setup, method, "", device, true);
   const double t_loaded = now_ms();
   std::printf("Creating GSO with %zu glowworms\n", positions.size());
-  GSO gso(positions, lc.seed, lc.scoring.get(), setup.use_anm, setup.anm_rec, setup.anm_lig, swarm_directory);
-  std::printf("Starting optimization (%u steps)\n", steps);
-  std::fflush(stdout);
-  gso.run(steps);
+  // LIGHTDOCK_GSO=device: the whole GSO step runs on the GPU (DeviceGSO, ld_gso_*); default: the host loop, whose
+  // trajectories are byte-identical to the reference's
+  const char *gso_mode = std::getenv("LIGHTDOCK_GSO");
+  const bool on_device = gso_mode && std::string(gso_mode) == "device";
+  uint64_t energy_calls = 0;
+  if (on_device) {
+    DeviceGSO gso(lc.scoring.get());
+    gso.add(positions, lc.seed, setup.use_anm, setup.anm_rec, setup.anm_lig, swarm_directory);
+    std::printf("Starting optimization (%u steps)\n", steps);
+    std::fflush(stdout);
+    gso.run(steps);
+    energy_calls = gso.energy_calls();
+    if (!gso.failures().empty()) throw std::runtime_error(gso.failures()[0].second);
+  } else {
+    GSO gso(positions, lc.seed, lc.scoring.get(), setup.use_anm, setup.anm_rec, setup.anm_lig, swarm_directory);
+    std::printf("Starting optimization (%u steps)\n", steps);
+    std::fflush(stdout);
+    gso.run(steps);
+    energy_calls = gso.swarm.energy_calls;
+  }
   const double t_done = now_ms();
   if (std::getenv("LDB200_TIMING")) {
     double c[4] = {0, 0, 0, 0};
@@ -56,7 +73,7 @@ static int simulate(const std::string &simulation_path, const SetupFile &setup, 
                  "[ldb200 timing] until_main_inputs_ms=%.1f load_case_ms=%.1f (ld_create: context_wait=%.1f complex=%.1f "
                  "groups=%.1f cells=%.1f) gso_ms=%.1f energy_calls=%llu total_in_main_ms=%.1f\n",
                  t_inputs, t_loaded - t_inputs, c[0], c[1], c[2], c[3], t_done - t_loaded,
-                 (unsigned long long)gso.swarm.energy_calls, t_done);
+                 (unsigned long long)energy_calls, t_done);
   }
   return 0;
 }

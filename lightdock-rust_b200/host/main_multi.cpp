@@ -166,12 +166,21 @@ int main(int argc, char **argv) {
       drivers.emplace_back([&, g] {
         try {
           LoadedCase lc = load_case(simulation_path, setup, method, "", devices[g], false);
-          MultiGSO multi(lc.scoring.get());
-          for (size_t s : mine[g])
-            multi.add(positions[s], lc.seed, setup.use_anm, setup.anm_rec, setup.anm_lig, dirs[s]);
-          multi.run((uint32_t)job.steps, host_threads);
-          calls[g] = multi.energy_calls();
-          for (const auto &f : multi.failures()) failed[g].emplace_back(dirs[mine[g][f.first]], f.second);
+          auto drive = [&](auto &multi) {
+            for (size_t s : mine[g])
+              multi.add(positions[s], lc.seed, setup.use_anm, setup.anm_rec, setup.anm_lig, dirs[s]);
+            multi.run((uint32_t)job.steps, host_threads);
+            calls[g] = multi.energy_calls();
+            for (const auto &f : multi.failures()) failed[g].emplace_back(dirs[mine[g][f.first]], f.second);
+          };
+          const char *gso_mode = std::getenv("LIGHTDOCK_GSO");  // "device": the GSO step itself runs on the GPU
+          if (gso_mode && std::string(gso_mode) == "device") {
+            DeviceGSO multi(lc.scoring.get());
+            drive(multi);
+          } else {
+            MultiGSO multi(lc.scoring.get());
+            drive(multi);
+          }
         } catch (...) {
           errors[g] = std::current_exception();
         }

@@ -18,7 +18,8 @@ DFIRE_TABLE_LEN = 169 * 169 * 20
 EXPORTS = ["ld_create", "ld_destroy", "ld_pose_len", "ld_score_batch", "ld_score_batch_device",
            "ld_score_batch_detail", "ld_transform_batch", "ld_get_stats", "ld_set_rec_splits",
            "ld_set_profiling", "ld_probe_peaks", "ld_last_error", "ld_version", "ld_set_path", "ld_path_info", "ld_device_count", "ld_score_batch_begin", "ld_score_batch_end", "ld_get_stats_slot",
-           "ld_set_option", "ld_init_device", "ld_get_create_ms"]
+           "ld_set_option", "ld_init_device", "ld_get_create_ms",
+           "ld_gso_create", "ld_gso_run", "ld_gso_state", "ld_gso_steps", "ld_gso_energy_calls", "ld_gso_destroy"]
 
 PATH_AUTO, PATH_GENERIC, PATH_RIGID = 0, 1, 2
 
@@ -89,6 +90,14 @@ def load_library():
         lib.ld_set_option.argtypes = [C.c_char_p, C.c_double]
         lib.ld_init_device.argtypes = [C.c_int32]
         lib.ld_get_create_ms.argtypes = [C.c_void_p, C.c_void_p]
+        lib.ld_gso_create.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.ld_gso_run.argtypes = [C.c_void_p, C.c_int32]
+        lib.ld_gso_state.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        lib.ld_gso_steps.argtypes = [C.c_void_p]
+        lib.ld_gso_steps.restype = C.c_int32
+        lib.ld_gso_energy_calls.argtypes = [C.c_void_p]
+        lib.ld_gso_energy_calls.restype = C.c_int64
+        lib.ld_gso_destroy.argtypes = [C.c_void_p]
         # experiment knobs of the tools (tools/units_sweep.py, ...): forwarded through the API, the library itself
         # never reads the environment
         for env, key in (("LDB200_ROWS", "rigid_rows"), ("LDB200_CELL", "cell_size"),

@@ -34,6 +34,7 @@ def load_host_library():
         lib.ldh_case_gso.argtypes = [C.c_void_p, C.c_char_p, C.c_uint, C.c_char_p, C.c_void_p, C.c_void_p]
         lib.ldh_case_multi_gso.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ldh_case_device_gso.argtypes = lib.ldh_case_multi_gso.argtypes
         lib.ldh_rng_draws.restype = C.c_double
         lib.ldh_rng_draws.argtypes = [C.c_ulonglong, C.c_int, C.c_void_p]
         lib.ldh_slerp.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
@@ -190,7 +191,12 @@ class Case:
             raise _err(self.lib)
         return state, calls.value
 
-    def multi_gso(self, positions, seeds, steps, host_threads=1, out_dirs=None):
+    def device_gso(self, positions, seeds, steps, host_threads=1, out_dirs=None):
+        """multi_gso with the whole GSO step on the device (DeviceGSO -> ld_gso_*): same arguments, same results up to
+        the last-bit difference of CUDA's acos/sin inside slerp."""
+        return self.multi_gso(positions, seeds, steps, host_threads, out_dirs, _entry="ldh_case_device_gso")
+
+    def multi_gso(self, positions, seeds, steps, host_threads=1, out_dirs=None, _entry="ldh_case_multi_gso"):
         positions = np.ascontiguousarray(positions, np.float64)
         ns, ng, pl = positions.shape
         assert pl == self.pose_len
@@ -200,7 +206,7 @@ class Case:
         dirs = None
         if out_dirs is not None:
             dirs = (C.c_char_p * ns)(*[d.encode() for d in out_dirs])
-        if self.lib.ldh_case_multi_gso(self.c, ns, ng, positions.ctypes.data, seeds.ctypes.data, steps, host_threads,
-                                       dirs, state.ctypes.data, C.addressof(calls)):
+        if getattr(self.lib, _entry)(self.c, ns, ng, positions.ctypes.data, seeds.ctypes.data, steps, host_threads,
+                                     dirs, state.ctypes.data, C.addressof(calls)):
             raise _err(self.lib)
         return state, calls.value

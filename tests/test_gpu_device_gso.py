@@ -1,0 +1,141 @@
+"""GPU: the device-resident GSO (include/lightdock_b200.h ld_gso_*, host/gso.hpp DeviceGSO) against
+the host loop and the oracle.  The step kernel restates src/swarm.rs:66-126 and src/glowworm.rs:61-190 in the
+reference's f64 operation order and evaluates each swarm's ChaCha20 stream on the device, so every discrete field
+(neighbour counts, vision ranges, number of energy evaluations) must equal the host's exactly; poses, scores and
+luciferin agree to the north-star tolerance (the one rounding difference is CUDA's acos/sin inside slerp)."""
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle as O
+from helpers import ENERGY_RTOL, GOLDEN, case
+from test_gpu_trajectory import STEPS, compare_gso_files, oracle_threads
+
+pytestmark = pytest.mark.gpu
+
+POSE_ATOL = 1e-9  # absolute, on translations of tens of A and unit quaternions
+
+
+def assert_same_state(dev, ref):
+    np.testing.assert_array_equal(dev[..., 2], ref[..., 2], err_msg="neighbour counts")
+    np.testing.assert_array_equal(dev[..., 3], ref[..., 3], err_msg="vision range")
+    assert np.abs(dev[..., 4:] - ref[..., 4:]).max() <= POSE_ATOL, "poses"
+    assert (np.abs(dev[..., 1] - ref[..., 1]) <= ENERGY_RTOL * np.abs(ref[..., 1])).all(), "scoring"
+    assert (np.abs(dev[..., 0] - ref[..., 0]) <= ENERGY_RTOL * np.abs(ref[..., 0]) + 1e-12).all(), "luciferin"
+
+
+def start_positions(g):
+    return np.array([[float(x) for x in l.split(" ")] for l in
+                     open(os.path.join(g, "initial_positions_0.dat")).read().splitlines()])
+
+
+def test_device_gso_reproduces_1azp_golden_trajectory_through_the_cli(tmp_path):
+    """example/1azp (DNA + ANM 10/10 + restraints, seed 324324, 100 steps) with LIGHTDOCK_GSO=device: the drop-in CLI
+    writes the same 11 files as the reference, to print precision."""
+    from ldb200 import host
+    g = os.path.join(GOLDEN, "1azp")
+    for f in ("rec_nm.npy", "lig_nm.npy"):
+        shutil.copy(os.path.join(g, f), tmp_path / f)
+    env = dict(os.environ, LIGHTDOCK_GSO="device")
+    r = subprocess.run([host.CLI_PATH, os.path.join(g, "setup.json"), os.path.join(g, "initial_positions_0.dat"),
+                        "100", "dna"], cwd=tmp_path, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.splitlines()[-1] == "Starting optimization (100 steps)"
+    assert sorted(os.listdir(tmp_path / "swarm_0")) == sorted(f"gso_{s}.out" for s in STEPS)
+    for s in STEPS:
+        compare_gso_files(str(tmp_path / "swarm_0" / f"gso_{s}.out"), os.path.join(g, "swarm_0", f"gso_{s}.out"))
+
+
+def test_device_gso_equals_host_gso_dna_with_anm():
+    """Three swarms of 1azp (the shipped one, a jittered copy, another seed), 100 steps: device loop == host loop."""
+    from ldb200 import host
+    g = os.path.join(GOLDEN, "1azp")
+    c = host.Case(os.path.join(g, "setup.json"), "dna", anm_dir=g)
+    pos = start_positions(g)
+    pos2 = pos.copy()
+    pos2[:, :3] += np.random.default_rng(5).normal(0, 0.3, size=(pos.shape[0], 3))
+    start, seeds = np.stack([pos, pos2, pos]), [c.seed, c.seed, 99]
+    ref, calls_ref = c.multi_gso(start, seeds, 100, host_threads=3)
+    dev, calls_dev = c.device_gso(start, seeds, 100, host_threads=3)
+    assert calls_dev == calls_ref
+    assert_same_state(dev, ref)
+    assert not np.array_equal(dev[0], dev[2]), "another seed is another trajectory"
+
+
+@pytest.mark.timeout(1500)
+@pytest.mark.parametrize("name", ["1ppe", "1k4c", "2uuy"])
+def test_device_gso_matches_oracle_gso_dfire(name, tmp_path, monkeypatch):
+    """DFIRE, 100 steps, against the ORACLE's GSO (not the product's host loop): 1ppe and 1k4c on the rigid ligand-frame
+    kernel, 2uuy (ANM on both partners) on its FLEX instance.  Every saved step through the gso files, the final state
+    at full precision."""
+    from ldb200 import host
+    cx, pos, seed = case(name, O.DFIRE)
+    g = os.path.join(GOLDEN, name)
+    O.write_dcparams(str(tmp_path / "DCparams"), cx.potential)
+    monkeypatch.setenv("LIGHTDOCK_DATA", str(tmp_path))
+    c = host.Case(os.path.join(g, "setup.json"), "dfire", anm_dir=g)
+    assert c.path_info().startswith("rigid path on"), c.path_info()
+    os.makedirs(tmp_path / "gpu"); os.makedirs(tmp_path / "cpu")
+    state, calls = c.device_gso(pos[None], [seed], 100, out_dirs=[str(tmp_path / "gpu")])
+    final, tr, ocalls = cx.gso_run(pos, seed, 100, out_dir=str(tmp_path / "cpu"), trace=True, threads=oracle_threads())
+    for s in STEPS:
+        compare_gso_files(str(tmp_path / "gpu" / f"gso_{s}.out"), str(tmp_path / "cpu" / f"gso_{s}.out"))
+    last = tr[-1]
+    assert calls == ocalls
+    np.testing.assert_array_equal(state[0][:, 2], last[:, 2])
+    np.testing.assert_array_equal(state[0][:, 3], last[:, 3])
+    assert np.abs(state[0][:, 4:] - last[:, 5:]).max() <= POSE_ATOL
+    assert (np.abs(state[0][:, 1] - last[:, 1]) <= ENERGY_RTOL * np.abs(last[:, 1])).all()
+
+
+def test_device_gso_many_swarms_and_chunked_runs(monkeypatch, tmp_path):
+    """48 synthetic 1k4c swarms, 25 steps: the device loop equals the host MultiGSO on every swarm; running the steps in
+    several ld_gso_run calls (1 + 9 + 10 + 5, what DeviceGSO does around the save points) is what one call gives; and
+    the rows-beyond-the-live-count skipping of the scoring kernels leaves no trace (moved-only rescoring)."""
+    import ctypes as C
+    import ldb200
+    from ldb200 import host, workload
+    dc_dir, _ = workload.ensure_dcparams_dir(str(tmp_path))
+    monkeypatch.setenv("LIGHTDOCK_DATA", dc_dir)
+    c = host.Case(os.path.join(workload.GOLDEN_1K4C, "setup.json"), "dfire")
+    pos = workload.synthetic_1k4c_swarms(48, 200)
+    seeds = np.arange(48, dtype=np.uint64) + 324324
+    ref, calls_ref = c.multi_gso(pos, seeds, 25, host_threads=8)
+    dev, calls_dev = c.device_gso(pos, seeds, 25, host_threads=8)
+    assert calls_dev == calls_ref
+    assert calls_ref < 48 * 200 * 25, "only the glowworms that moved are rescored"
+    assert_same_state(dev, ref)
+    # the raw C ABI, one call of 25 steps
+    lib = ldb200.load_library()
+    g = C.c_void_p()
+    flat = np.ascontiguousarray(pos, np.float64)
+    assert lib.ld_gso_create(C.c_void_p(c.ld_handle()), 48, 200, flat.ctypes.data, seeds.ctypes.data, C.byref(g)) == 0, \
+        lib.ld_last_error()
+    assert lib.ld_gso_run(g, 25) == 0, lib.ld_last_error()
+    assert lib.ld_gso_steps(g) == 25 and lib.ld_gso_energy_calls(g) == calls_ref
+    poses = np.empty((48, 200, 7)); lum = np.empty((48, 200)); vis = np.empty((48, 200)); sc = np.empty((48, 200))
+    nn = np.empty((48, 200), np.int32); failed = np.empty(48, np.int32)
+    assert lib.ld_gso_state(g, poses.ctypes.data, lum.ctypes.data, vis.ctypes.data, sc.ctypes.data, nn.ctypes.data,
+                            failed.ctypes.data) == 0
+    lib.ld_gso_destroy(g)
+    assert not failed.any()
+    assert np.array_equal(poses, dev[..., 4:]) and np.array_equal(lum, dev[..., 0]) and np.array_equal(sc, dev[..., 1])
+    assert np.array_equal(nn, dev[..., 2].astype(np.int32)) and np.array_equal(vis, dev[..., 3])
+
+
+def test_device_gso_rng_stream_is_the_reference_stream():
+    """One step of a swarm in which every glowworm sees every brighter one (huge vision range is not settable, so use
+    the known-answer route instead): the device's draws are StdRng::seed_from_u64(seed).gen::<f64>() -- checked through
+    the host mirror's stream (pinned to src/qt.rs:451-462 in test_host_cpu) by comparing a 30-step trajectory, whose
+    roulette choices consume 30 x 200 draws, for two seeds that differ only in the stream."""
+    from ldb200 import host
+    g = os.path.join(GOLDEN, "1azp")
+    c = host.Case(os.path.join(g, "setup.json"), "dna", anm_dir=g)
+    pos = start_positions(g)
+    for seed in (1, 2**63 + 12345):
+        ref, _ = c.multi_gso(pos[None], [seed], 30)
+        dev, _ = c.device_gso(pos[None], [seed], 30)
+        assert_same_state(dev, ref)
