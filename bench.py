@@ -452,6 +452,28 @@ def run_b200(args, rank, world, local_rank):
             gso["note"] = ("the kernel's time follows the executed pair tests: poses after %d GSO steps need %.2fx the pair "
                            "tests of the start poses `value` is measured on" % (args.gso_steps, tested[1] / max(tested[0], 1.0)))
 
+    # ---- the same GSO run with the whole step on the device (DeviceGSO -> ld_gso_*) ----
+    gso_dev = None
+    if args.gso_steps > 0:
+        case.device_gso(all_poses[mine], seeds, 1, host_threads=threads)  # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        dev_state, dev_calls = case.device_gso(all_poses[mine], seeds, args.gso_steps, host_threads=threads)
+        dev_s = max_over_ranks(time.perf_counter() - t0)
+        calls_d = torch.tensor([dev_calls], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(calls_d, op=dist.ReduceOp.SUM)
+        same_discrete = bool(np.array_equal(dev_state[..., 2:4], final_state[..., 2:4]) and dev_calls == calls)
+        gso_dev = {"steps": args.gso_steps, "swarms": args.swarms, "energy_calls": int(calls_d.item()), "wall_s": dev_s,
+                   "poses_per_s": calls_d.item() / dev_s,
+                   "vs_host_loop": {"neighbour_counts_vision_ranges_energy_calls_identical": same_discrete,
+                                    "max_abs_pose_diff": float(np.abs(dev_state[..., 4:] - final_state[..., 4:]).max()),
+                                    "max_rel_scoring_diff": float(np.max(np.abs(dev_state[..., 1] - final_state[..., 1])
+                                                                         / np.maximum(np.abs(final_state[..., 1]), 1e-300)))},
+                   "what": "the same swarms, seeds and steps with the GSO step itself on the GPU (gso_step_kernel + moved-only "
+                           "scoring pass per step, no host round trip; ChaCha20 draws on the device); wall clock of "
+                           "DeviceGSO::run incl. ld_gso_create, the state read-backs at the save points and ld_gso_destroy"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -541,7 +563,7 @@ def run_b200(args, rank, world, local_rank):
                    "d2h_bytes_per_step": n_local * 8, "ms_per_step": e2e_s / args.steps * 1e3,
                    "api": "ld_score_batch (C ABI, host buffers)"},
            "gpu_launches": launches_per_step * args.steps, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-           "gso_run": gso, "configs": configs}
+           "gso_run": gso, "gso_device_run": gso_dev, "configs": configs}
     if world == 1 and not args.no_single_swarm_runs:
         out["single_swarm_runs"] = single_swarm_runs(dc_dir)
     print(json.dumps(out), flush=True)
@@ -593,6 +615,19 @@ def single_swarm_runs(dc_dir):
                          "gso_100_steps_ms": nums.get("gso_ms"), "energy_calls": int(nums.get("energy_calls", 0))}
         out[name] = {"method": method, "wall_s": dt if ok else None, "readme_m3pro_1core_wall_s": README_M3_SECONDS[name],
                      "breakdown": breakdown}
+        # the same run with LIGHTDOCK_GSO=device (the GSO step on the GPU too)
+        with tempfile.TemporaryDirectory() as tmp:
+            for f in ("rec_nm.npy", "lig_nm.npy"):
+                if os.path.exists(os.path.join(g, f)):
+                    shutil.copy(os.path.join(g, f), os.path.join(tmp, f))
+            env = dict(os.environ, LIGHTDOCK_DATA=dc_dir, LDB200_TIMING="1", LIGHTDOCK_GSO="device")
+            t = time.perf_counter()
+            r = subprocess.run([host.CLI_PATH, os.path.join(g, "setup.json"), start, "100", method], cwd=tmp, env=env,
+                               capture_output=True, text=True)
+            dt = time.perf_counter() - t
+            ok = r.returncode == 0 and os.path.exists(os.path.join(tmp, "swarm_0", "gso_100.out"))
+        m = re.search(r"gso_ms=([0-9.]+)", r.stderr)
+        out[name]["device_gso"] = {"wall_s": dt if ok else None, "gso_100_steps_ms": float(m.group(1)) if m else None}
     return out
 
 

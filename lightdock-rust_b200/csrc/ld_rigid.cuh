@@ -50,6 +50,18 @@ namespace ldb200 {
 constexpr int RG_THREADS = LDB200_RG_THREADS;
 constexpr int RG_WARPS = RG_THREADS / 32;
 constexpr int RG_MAX_ROWS = 4;
+// Variants of the row loop (A/B'd on B200):
+//   LDB200_RG_CLASSIFY 0: cut-off by d2f <= 225 + delta, per-pair bit for the pairs the exact path must redo
+//                      1: cut-off by the proven index, one max() per pair; the exact-path pairs are found by a second
+//                         look at the (rare) items whose largest margin fails
+//   LDB200_RG_GATHER_ALL 1: unpredicated table gather + add (non-fast pairs read a zero)
+#ifndef LDB200_RG_CLASSIFY
+#define LDB200_RG_CLASSIFY 0
+#endif
+#ifndef LDB200_RG_GATHER_ALL
+#define LDB200_RG_GATHER_ALL 0
+#endif
+constexpr uint32_t RG_ZERO_OFF = 16;  // 8 zero bytes in the CTA's shared-memory header
 
 struct RigidComplex {
   int n_groups, n_rec_pos;  // n_rec_pos = n_groups * 32 (type-grouped receptor positions, pads interspersed)
@@ -281,9 +293,10 @@ __device__ __noinline__ int rigid_exact_pair(const RigidComplex *__restrict__ rc
 //   m = u + MAGIC  -> rint(u) in the low mantissa bits,  g = u - rint(u) = frac(t_f32) - 0.5 (exact).
 // If |g| <= 0.5 - eps_t (eps_t = 1.02*delta*rsqrt.approx(d2f) + 2.5e-5 > E_t) then floor(t_ref) = rint(u): the bin
 // is the reference's.
-// d2f <= 225 + delta together with that leaves indices 0..28 only (index 29 needs t >= 29 + eps_t, i.e.
-// d2f > 225 + delta); such a pair's table value is added in the hot loop, every other pair with
-// d2f <= 225 + delta goes to rigid_exact_pair.  The interface test t <= 3.9 (dist <= 6.0025) is kept out of
+// For such a pair the index also decides the cut-off: rint(u) <= 28 means t_ref < 29, i.e. dist < 225, and its table
+// value is added in the hot loop; rint(u) >= 29 means t_ref >= 29 + eps_t - E_t > 29, i.e. dist > 225: skipped.
+// Every pair that fails the margin test and has d2f <= 225 + delta goes to rigid_exact_pair (found by a second look
+// at the item, taken only when the item's largest |g| + delta/d exceeds the margin).  The interface test t <= 3.9 (dist <= 6.0025) is kept out of
 // the hot loop: a per-item min(d2f) sends the rare items with a contact below 2.45 A + to a second pass
 // that decides it in FP32 outside 6.0025 +- delta and with rigid_exact_pair inside.
 __device__ __forceinline__ float4 lds_f4(uint32_t off) { return *reinterpret_cast<const float4 *>(smem_rigid + off); }
@@ -311,15 +324,17 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
   const unsigned rb = __shfl_sync(0xffffffffu, rowoff, o);
   if (!active) return;
   const int jbase = lt * LIG_TILE;
-  // tile base (128-byte aligned) | per-lane slot: atom (k ^ lane) & 7 of the tile, so that any 8 consecutive
-  // lanes read 8 different 16-byte slots -> conflict-free LDS.128 whatever tiles the lanes hold
-  const uint32_t tile_addr = l4_addr + (uint32_t)lt * (LIG_TILE * 16);
+  // per-lane slot: atom (k ^ lane) & 7 of the tile, so that any 8 consecutive lanes read 8 different 16-byte slots
+  // -> conflict-free LDS.128 whatever tiles the lanes hold
+  // tile base (128-byte aligned) | the lane's slot bits: slot k of this lane is one XOR away
+  const uint32_t tile_addr = (l4_addr + (uint32_t)lt * (LIG_TILE * 16)) | lane_sw;
+  float worst = 0.f;  // largest |g| + delta/d of the item: above hme, some pair could not be decided in FP32
   unsigned slow_bits = 0u;
   unsigned n_fast = 0;
   float mind2 = 3.0e38f;
 #pragma unroll
   for (int k = 0; k < LIG_TILE; ++k) {
-    const float4 a = lds_f4(tile_addr | (lane_sw ^ (uint32_t)(k << 4)));
+    const float4 a = lds_f4(tile_addr ^ (uint32_t)(k << 4));
     const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
     const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     mind2 = fminf(mind2, d2);
@@ -328,12 +343,33 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
     const float u = fmaf(d, 2.0f, -1.5f);  // t - 0.5 in [-1.5, 28.5]: rint(u) = -1 for t < 0, see RG_SLOT0
     const float m = __fadd_rn(u, RG_MAGIC);
     const float g = __fsub_rn(u, __fsub_rn(m, RG_MAGIC));
+    const float marg = fmaf(delta, rs, fabsf(g));  // |g| + delta/d
+#if LDB200_RG_CLASSIFY == 0
     const bool inr = d2 <= thr_out;
-    const bool fast = inr & (fmaf(delta, rs, fabsf(g)) <= hme);  // |g| + delta/d <= 0.5 - 2.5e-5
+    const bool fast = inr & (marg <= hme);  // |g| + delta/d <= 0.5 - 2.5e-5
     if (inr & !fast) slow_bits |= 1u << k;
+#else
+    // |g| + delta/d <= 0.5 - 2.5e-5: floor(t_ref) = rint(u) is proven, so the index alone says whether the pair is
+    // inside the cut-off (rint(u) <= 28 <=> t_ref < 29 <=> dist < 225; rint(u) >= 29 => t_ref > 29: outside)
+    worst = fmaxf(worst, marg);
+    const bool fast = (marg <= hme) & (m <= RG_MAGIC + 28.0f);
+#endif
     // a.w = ligand type * RG_SLOTS as a float: adding it to m (both integers < 2^24) is exact and leaves
     // MAGIC_BITS + type*RG_SLOTS + index in the mantissa -> one shift-add gives the byte address
     const uint32_t addr = ((uint32_t)__float_as_int(__fadd_rn(m, a.w)) << 3) + rb;
+#if LDB200_RG_GATHER_ALL
+    // every pair gathers and adds; a pair that is not `fast` reads the 8 zero bytes of the CTA header instead (one
+    // broadcast address for all such lanes): no predicate stays live across the loads, so the eight gathers and
+    // additions of an item schedule freely
+    const uint32_t addr_eff = fast ? addr : RG_ZERO_OFF;
+    if (k & 1) rg_add(acc1, addr_eff);
+    else rg_add(acc0, addr_eff);
+    if (DETAIL && fast) {
+      ++n_fast;
+      atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[dfire_bin_fast(__float_as_int(m) - (int)RG_MAGIC_BITS)]),
+                1ull);
+    }
+#else
     if (fast) {
       if (k & 1) rg_add(acc1, addr);
       else rg_add(acc0, addr);
@@ -343,12 +379,26 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
                   1ull);
       }
     }
+#endif
   }
+#if LDB200_RG_CLASSIFY != 0
+  if (!(worst <= hme)) {  // rare (1e-3 of the items): which pairs?  Same operations as above, hence the same bits
+    for (int k = 0; k < LIG_TILE; ++k) {
+      const float4 a = lds_f4(tile_addr ^ (uint32_t)(k << 4));
+      const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
+      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      const float rs = rsqrt_approx(d2);
+      const float u = fmaf(d2 * rs, 2.0f, -1.5f);
+      const float g = __fsub_rn(u, __fsub_rn(__fadd_rn(u, RG_MAGIC), RG_MAGIC));
+      if ((d2 <= thr_out) & !(fmaf(delta, rs, fabsf(g)) <= hme)) slow_bits |= 1u << k;
+    }
+  }
+#endif
   if (mind2 <= 6.0025f + delta) {  // rare: a contact near or below the 2.45 A interface edge (src/dfire.rs:339-342)
     const double *pose = bb.poses + (size_t)p * rc_dev->pose_len;
     for (int k = 0; k < LIG_TILE; ++k) {
       if ((slow_bits >> k) & 1u) continue;  // the exact path below owns this pair entirely
-      const float4 a = lds_f4(tile_addr | (lane_sw ^ (uint32_t)(k << 4)));
+      const float4 a = lds_f4(tile_addr ^ (uint32_t)(k << 4));
       const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
       const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));  // same operations as above: same bits
       if (d2 > 6.0025f + delta) continue;
@@ -430,6 +480,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
+    *reinterpret_cast<unsigned long long *>(smem_raw + RG_ZERO_OFF) = 0ull;
   }
   __syncthreads();
   uint32_t phase = 0;
