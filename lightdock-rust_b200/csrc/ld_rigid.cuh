@@ -50,18 +50,6 @@ namespace ldb200 {
 constexpr int RG_THREADS = LDB200_RG_THREADS;
 constexpr int RG_WARPS = RG_THREADS / 32;
 constexpr int RG_MAX_ROWS = 4;
-// Variants of the row loop (A/B'd on B200):
-//   LDB200_RG_CLASSIFY 0: cut-off by d2f <= 225 + delta, per-pair bit for the pairs the exact path must redo
-//                      1: cut-off by the proven index, one max() per pair; the exact-path pairs are found by a second
-//                         look at the (rare) items whose largest margin fails
-//   LDB200_RG_GATHER_ALL 1: unpredicated table gather + add (non-fast pairs read a zero)
-#ifndef LDB200_RG_CLASSIFY
-#define LDB200_RG_CLASSIFY 0
-#endif
-#ifndef LDB200_RG_GATHER_ALL
-#define LDB200_RG_GATHER_ALL 0
-#endif
-constexpr uint32_t RG_ZERO_OFF = 16;  // 8 zero bytes in the CTA's shared-memory header
 
 struct RigidComplex {
   int n_groups, n_rec_pos;  // n_rec_pos = n_groups * 32 (type-grouped receptor positions, pads interspersed)
@@ -293,10 +281,9 @@ __device__ __noinline__ int rigid_exact_pair(const RigidComplex *__restrict__ rc
 //   m = u + MAGIC  -> rint(u) in the low mantissa bits,  g = u - rint(u) = frac(t_f32) - 0.5 (exact).
 // If |g| <= 0.5 - eps_t (eps_t = 1.02*delta*rsqrt.approx(d2f) + 2.5e-5 > E_t) then floor(t_ref) = rint(u): the bin
 // is the reference's.
-// For such a pair the index also decides the cut-off: rint(u) <= 28 means t_ref < 29, i.e. dist < 225, and its table
-// value is added in the hot loop; rint(u) >= 29 means t_ref >= 29 + eps_t - E_t > 29, i.e. dist > 225: skipped.
-// Every pair that fails the margin test and has d2f <= 225 + delta goes to rigid_exact_pair (found by a second look
-// at the item, taken only when the item's largest |g| + delta/d exceeds the margin).  The interface test t <= 3.9 (dist <= 6.0025) is kept out of
+// d2f <= 225 + delta together with that leaves indices 0..28 only (index 29 needs t >= 29 + eps_t, i.e.
+// d2f > 225 + delta); such a pair's table value is added in the hot loop, every other pair with
+// d2f <= 225 + delta goes to rigid_exact_pair.  The interface test t <= 3.9 (dist <= 6.0025) is kept out of
 // the hot loop: a per-item min(d2f) sends the rare items with a contact below 2.45 A + to a second pass
 // that decides it in FP32 outside 6.0025 +- delta and with rigid_exact_pair inside.
 __device__ __forceinline__ float4 lds_f4(uint32_t off) { return *reinterpret_cast<const float4 *>(smem_rigid + off); }
@@ -307,16 +294,22 @@ template <bool FLEX> struct RgAcc { typedef double type; };
 template <> struct RgAcc<true> { typedef long long type; };
 __device__ __forceinline__ void rg_add(double &acc, uint32_t addr) { acc = __dadd_rn(acc, lds_f64(addr)); }
 __device__ __forceinline__ void rg_add(long long &acc, uint32_t addr) { acc += lds_i64(addr); }
+__device__ __forceinline__ double rg_join(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ long long rg_join(long long a, long long b) { return a + b; }
 __device__ __forceinline__ void rg_add_exact(double &acc, double v, double) { acc = __dadd_rn(acc, v); }
 __device__ __forceinline__ void rg_add_exact(long long &acc, double v, double scale) { acc += __double2ll_rn(v * scale); }
 
-template <bool DETAIL, bool FLEX>
+// GTAB: the table rows are read from global memory (L2) instead of the CTA's shared-memory rows (pose-major kernel):
+// `rowoff` is then the byte offset of (receptor type, ligand type 0, index 4) in `tab` minus what the magic-number index
+// carries, and the eight values of an item are loaded together and added afterwards, so that the loads overlap.
+template <bool DETAIL, bool FLEX, bool GTAB>
 __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuffers &bb, uint32_t l4_addr,
                                           uint32_t lane_sw, bool active, int o, int lt, float rxf, float ryf,
                                           float rzf, unsigned rowoff, int p, int pos_base,
                                           typename RgAcc<FLEX>::type &acc0, typename RgAcc<FLEX>::type &acc1,
                                           unsigned &ifr_mask, const RigidComplex *rc_dev, const double *prep,
-                                          float thr_out, float hme, float delta) {
+                                          float thr_out, float hme, float delta, const unsigned char *tab) {
+  typedef typename RgAcc<FLEX>::type acc_t;
   ld_pose_detail *dt = DETAIL ? reinterpret_cast<ld_pose_detail *>(bb.detail) + p : nullptr;
   const int lane = threadIdx.x & 31;
   const float ax = __shfl_sync(0xffffffffu, rxf, o), ay = __shfl_sync(0xffffffffu, ryf, o),
@@ -328,10 +321,10 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
   // -> conflict-free LDS.128 whatever tiles the lanes hold
   // tile base (128-byte aligned) | the lane's slot bits: slot k of this lane is one XOR away
   const uint32_t tile_addr = (l4_addr + (uint32_t)lt * (LIG_TILE * 16)) | lane_sw;
-  float worst = 0.f;  // largest |g| + delta/d of the item: above hme, some pair could not be decided in FP32
   unsigned slow_bits = 0u;
   unsigned n_fast = 0;
   float mind2 = 3.0e38f;
+  acc_t vals[GTAB ? LIG_TILE : 1];
 #pragma unroll
   for (int k = 0; k < LIG_TILE; ++k) {
     const float4 a = lds_f4(tile_addr ^ (uint32_t)(k << 4));
@@ -344,33 +337,20 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
     const float m = __fadd_rn(u, RG_MAGIC);
     const float g = __fsub_rn(u, __fsub_rn(m, RG_MAGIC));
     const float marg = fmaf(delta, rs, fabsf(g));  // |g| + delta/d
-#if LDB200_RG_CLASSIFY == 0
     const bool inr = d2 <= thr_out;
     const bool fast = inr & (marg <= hme);  // |g| + delta/d <= 0.5 - 2.5e-5
     if (inr & !fast) slow_bits |= 1u << k;
-#else
-    // |g| + delta/d <= 0.5 - 2.5e-5: floor(t_ref) = rint(u) is proven, so the index alone says whether the pair is
-    // inside the cut-off (rint(u) <= 28 <=> t_ref < 29 <=> dist < 225; rint(u) >= 29 => t_ref > 29: outside)
-    worst = fmaxf(worst, marg);
-    const bool fast = (marg <= hme) & (m <= RG_MAGIC + 28.0f);
-#endif
     // a.w = ligand type * RG_SLOTS as a float: adding it to m (both integers < 2^24) is exact and leaves
     // MAGIC_BITS + type*RG_SLOTS + index in the mantissa -> one shift-add gives the byte address
     const uint32_t addr = ((uint32_t)__float_as_int(__fadd_rn(m, a.w)) << 3) + rb;
-#if LDB200_RG_GATHER_ALL
-    // every pair gathers and adds; a pair that is not `fast` reads the 8 zero bytes of the CTA header instead (one
-    // broadcast address for all such lanes): no predicate stays live across the loads, so the eight gathers and
-    // additions of an item schedule freely
-    const uint32_t addr_eff = fast ? addr : RG_ZERO_OFF;
-    if (k & 1) rg_add(acc1, addr_eff);
-    else rg_add(acc0, addr_eff);
-    if (DETAIL && fast) {
-      ++n_fast;
-      atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[dfire_bin_fast(__float_as_int(m) - (int)RG_MAGIC_BITS)]),
-                1ull);
-    }
-#else
-    if (fast) {
+    if (GTAB) {
+      vals[k] = fast ? __ldg(reinterpret_cast<const acc_t *>(tab + addr)) : (acc_t)0;
+      if (DETAIL && fast) {
+        ++n_fast;
+        atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[dfire_bin_fast(__float_as_int(m) - (int)RG_MAGIC_BITS)]),
+                  1ull);
+      }
+    } else if (fast) {
       if (k & 1) rg_add(acc1, addr);
       else rg_add(acc0, addr);
       if (DETAIL) {
@@ -379,21 +359,14 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
                   1ull);
       }
     }
-#endif
   }
-#if LDB200_RG_CLASSIFY != 0
-  if (!(worst <= hme)) {  // rare (1e-3 of the items): which pairs?  Same operations as above, hence the same bits
+  if (GTAB) {  // same order of additions as the shared-memory form: k ascending, even k -> acc0, odd k -> acc1
+#pragma unroll
     for (int k = 0; k < LIG_TILE; ++k) {
-      const float4 a = lds_f4(tile_addr ^ (uint32_t)(k << 4));
-      const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
-      const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-      const float rs = rsqrt_approx(d2);
-      const float u = fmaf(d2 * rs, 2.0f, -1.5f);
-      const float g = __fsub_rn(u, __fsub_rn(__fadd_rn(u, RG_MAGIC), RG_MAGIC));
-      if ((d2 <= thr_out) & !(fmaf(delta, rs, fabsf(g)) <= hme)) slow_bits |= 1u << k;
+      if (k & 1) acc1 = rg_join(acc1, vals[k]);
+      else acc0 = rg_join(acc0, vals[k]);
     }
   }
-#endif
   if (mind2 <= 6.0025f + delta) {  // rare: a contact near or below the 2.45 A interface edge (src/dfire.rs:339-342)
     const double *pose = bb.poses + (size_t)p * rc_dev->pose_len;
     for (int k = 0; k < LIG_TILE; ++k) {
@@ -444,14 +417,128 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
   }
 }
 
-__device__ __forceinline__ double rg_join(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ long long rg_join(long long a, long long b) { return a + b; }
 // Sum of a lane value over the warp in a fixed order (f64) / exactly (fixed point).
 __device__ __forceinline__ long long warp_sum(long long v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
   return v;
 }
+
+// One (receptor group, pose): the group's 32 atoms (one per lane) against the ligand of pose p.  Adds the table values
+// to acc0/acc1 (per-lane partial sums, fixed order) and ORs the lanes' interface flags into ifr_mask.
+//   rowoff   per lane: where the lane's table row starts (shared-memory byte address, or byte offset in `tab` for
+//            GTAB), minus what the magic-number index carries; 0xffffffff = pad lane
+//   prep     the pose's rotation data (rigid_prep_kernel), global or shared memory
+//   brute..reach_abs  FLEX only: the pose left its slacks -> every ligand tile is a candidate, with margins widened to
+//            the coordinates that can then be in range
+template <bool DETAIL, bool FLEX, bool GTAB>
+__device__ __forceinline__ void rg_score_group(const RigidComplex &rc, const BatchBuffers &bb, uint32_t l4_addr,
+                                               uint32_t lane_sw, unsigned rowoff, int p, int pos_base,
+                                               const double *prep, bool brute, float thr_out, float hme,
+                                               float delta102, float reach_abs, typename RgAcc<FLEX>::type &acc0,
+                                               typename RgAcc<FLEX>::type &acc1, unsigned &ifr_mask,
+                                               const RigidComplex *rc_dev, const unsigned char *tab) {
+  const int lane = threadIdx.x & 31;
+  float fx, fy, fz;
+  unsigned my_off;
+  int my_n;
+  {
+    // receptor atom -> ligand frame: M r - M t (rigid_prep_kernel)
+    double ax = rc.rec_x[pos_base + lane], ay = rc.rec_y[pos_base + lane], az = rc.rec_z[pos_base + lane];
+    if (rc.n_rec_modes > 0) {  // src/dfire.rs:304-320 (lab frame)
+      const double *pose = bb.poses + (size_t)p * rc.pose_len;
+      for (int k = 0; k < rc.n_rec_modes; ++k) {
+        const double e = pose[7 + k];
+        const double *m = rc.rec_modes + (size_t)k * 3 * rc.n_rec_pos + pos_base + lane;
+        ax = __dadd_rn(ax, __dmul_rn(m[0], e));
+        ay = __dadd_rn(ay, __dmul_rn(m[rc.n_rec_pos], e));
+        az = __dadd_rn(az, __dmul_rn(m[2 * rc.n_rec_pos], e));
+      }
+    }
+    fx = (float)(fma(prep[0], ax, fma(prep[1], ay, fma(prep[2], az, -prep[9]))));
+    fy = (float)(fma(prep[3], ax, fma(prep[4], ay, fma(prep[5], az, -prep[10]))));
+    fz = (float)(fma(prep[6], ax, fma(prep[7], ay, fma(prep[8], az, -prep[11]))));
+    const int cxi = __float2int_rd((fx - rc.gx0) * rc.inv_h), cyi = __float2int_rd((fy - rc.gy0) * rc.inv_h),
+              czi = __float2int_rd((fz - rc.gz0) * rc.inv_h);
+    uint2 ce = make_uint2(0u, 0u);
+    if ((unsigned)cxi < (unsigned)rc.nx && (unsigned)cyi < (unsigned)rc.ny && (unsigned)czi < (unsigned)rc.nz)
+      ce = __ldg(rc.cells + ((size_t)czi * rc.ny + cyi) * rc.nx + cxi);
+    my_off = ce.x;
+    my_n = (int)rowoff == -1 ? 0 : (int)ce.y;  // pad lanes own nothing
+    if (FLEX && brute) {  // every ligand tile, whatever the lists say: entry k of the "list" is tile k
+      my_off = 0u;
+      // an atom further out than the grid grown by dmax has no partner within 15 A
+      const bool far = fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))) > reach_abs;
+      my_n = ((int)rowoff == -1 || far || !(fx == fx)) ? 0 : rc.n_lig_tiles;
+    }
+  }
+  auto tile_at = [&](unsigned idx) -> unsigned {
+    return (FLEX && brute) ? idx : (unsigned)__ldg(rc.cell_tiles + idx);
+  };
+
+  // Work items = (owner lane, ligand tile) for every entry of the 32 lanes' cell lists, scored 32 at a time.
+  //  (1) an owner with >= 32 entries fills whole rows on its own: lane i takes entry r*32 + i of its list;
+  //  (2) the tails (n mod 32 entries per owner) are pooled: an inclusive scan of the tail lengths numbers
+  //      them, item k belongs to the lane o = #{l : end_l <= k} (5-step binary search over the ends with
+  //      register shuffles) and is entry k - end_{o-1} of o's tail.
+  // The next row's (owner, tile) is produced before the current row is scored, so its list read is in flight.
+  unsigned big = __ballot_sync(0xffffffffu, my_n >= 32);
+  int big_o = 0, big_left = 0;       // current whole-row owner, entries left in whole rows
+  unsigned big_off = 0u;
+  const int tail_n = my_n & 31;
+  const unsigned tail_off = my_off + (unsigned)(my_n & ~31);
+  int end = tail_n;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, end, d);
+    if (lane >= d) end += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, end, 31);
+  int k0 = 0;
+  bool act = false, act_nxt = false;
+  int o = 0, o_nxt = 0;
+  unsigned lt = 0u, lt_nxt = 0u;
+  auto produce = [&]() -> bool {  // warp-uniform control flow; fills (act_nxt, o_nxt, lt_nxt)
+    if (big_left == 0 && big != 0u) {
+      big_o = __ffs(big) - 1;
+      big &= big - 1;
+      big_left = __shfl_sync(0xffffffffu, my_n, big_o) & ~31;
+      big_off = __shfl_sync(0xffffffffu, my_off, big_o);
+    }
+    if (big_left > 0) {
+      o_nxt = big_o;
+      lt_nxt = tile_at(big_off + lane);
+      act_nxt = true;
+      big_off += 32u;
+      big_left -= 32;
+      return true;
+    }
+    if (k0 < total) {
+      const int k = k0 + lane;
+      int oo = 0;
+#pragma unroll
+      for (int step = 16; step > 0; step >>= 1) {
+        const int v = __shfl_sync(0xffffffffu, end, oo + step - 1);
+        if (v <= k) oo += step;
+      }
+      const int prev = __shfl_sync(0xffffffffu, end, (oo - 1) & 31);
+      const unsigned off = __shfl_sync(0xffffffffu, tail_off, oo);
+      o_nxt = oo;
+      act_nxt = k < total;
+      lt_nxt = 0u;
+      if (act_nxt) lt_nxt = tile_at(off + (unsigned)(k - (oo > 0 ? prev : 0)));
+      k0 += 32;
+      return true;
+    }
+    return false;
+  };
+  bool have = produce();
+  while (have) {
+    act = act_nxt; o = o_nxt; lt = lt_nxt;
+    have = produce();
+    rigid_row<DETAIL, FLEX, GTAB>(rc, bb, l4_addr, lane_sw, act, o, (int)lt, fx, fy, fz, rowoff, p, pos_base, acc0,
+                                  acc1, ifr_mask, rc_dev, prep, thr_out, hme, delta102, tab);
+  }}
 
 // lig4p / pose_flag: FLEX only -- per-pose ligand blocks [n_poses][n_lig_pad] and 1 = "a tile moved further than its
 // slack: score this pose against every ligand tile" (both written by flex_prep_kernel).
@@ -480,7 +567,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
-    *reinterpret_cast<unsigned long long *>(smem_raw + RG_ZERO_OFF) = 0ull;
   }
   __syncthreads();
   uint32_t phase = 0;
@@ -555,113 +641,98 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
         }
         __syncwarp();
       }
-      float fx, fy, fz;
-      unsigned my_off;
-      int my_n;
-      {
-        // receptor atom -> ligand frame: M r - M t (rigid_prep_kernel)
-        double ax = rc.rec_x[pos_base + lane], ay = rc.rec_y[pos_base + lane], az = rc.rec_z[pos_base + lane];
-        if (rc.n_rec_modes > 0) {  // src/dfire.rs:304-320 (lab frame)
-          const double *pose = bb.poses + (size_t)p * rc.pose_len;
-          for (int k = 0; k < rc.n_rec_modes; ++k) {
-            const double e = pose[7 + k];
-            const double *m = rc.rec_modes + (size_t)k * 3 * rc.n_rec_pos + pos_base + lane;
-            ax = __dadd_rn(ax, __dmul_rn(m[0], e));
-            ay = __dadd_rn(ay, __dmul_rn(m[rc.n_rec_pos], e));
-            az = __dadd_rn(az, __dmul_rn(m[2 * rc.n_rec_pos], e));
-          }
-        }
-        fx = (float)(fma(prep[0], ax, fma(prep[1], ay, fma(prep[2], az, -prep[9]))));
-        fy = (float)(fma(prep[3], ax, fma(prep[4], ay, fma(prep[5], az, -prep[10]))));
-        fz = (float)(fma(prep[6], ax, fma(prep[7], ay, fma(prep[8], az, -prep[11]))));
-        const int cxi = __float2int_rd((fx - rc.gx0) * rc.inv_h), cyi = __float2int_rd((fy - rc.gy0) * rc.inv_h),
-                  czi = __float2int_rd((fz - rc.gz0) * rc.inv_h);
-        uint2 ce = make_uint2(0u, 0u);
-        if ((unsigned)cxi < (unsigned)rc.nx && (unsigned)cyi < (unsigned)rc.ny && (unsigned)czi < (unsigned)rc.nz)
-          ce = __ldg(rc.cells + ((size_t)czi * rc.ny + cyi) * rc.nx + cxi);
-        my_off = ce.x;
-        my_n = (int)rowoff == -1 ? 0 : (int)ce.y;  // pad lanes own nothing
-        if (FLEX && brute) {  // every ligand tile, whatever the lists say: entry k of the "list" is tile k
-          my_off = 0u;
-          // an atom further out than the grid grown by dmax has no partner within 15 A
-          const bool far = fmaxf(fabsf(fx), fmaxf(fabsf(fy), fabsf(fz))) > reach_abs;
-          my_n = ((int)rowoff == -1 || far || !(fx == fx)) ? 0 : rc.n_lig_tiles;
-        }
-      }
-      auto tile_at = [&](unsigned idx) -> unsigned {
-        return (FLEX && brute) ? idx : (unsigned)__ldg(rc.cell_tiles + idx);
-      };
-
       acc_t acc0 = 0, acc1 = 0;
       unsigned ifr_mask = 0u;
-      // Work items = (owner lane, ligand tile) for every entry of the 32 lanes' cell lists, scored 32 at a time.
-      //  (1) an owner with >= 32 entries fills whole rows on its own: lane i takes entry r*32 + i of its list;
-      //  (2) the tails (n mod 32 entries per owner) are pooled: an inclusive scan of the tail lengths numbers
-      //      them, item k belongs to the lane o = #{l : end_l <= k} (5-step binary search over the ends with
-      //      register shuffles) and is entry k - end_{o-1} of o's tail.
-      // The next row's (owner, tile) is produced before the current row is scored, so its list read is in flight.
-      unsigned big = __ballot_sync(0xffffffffu, my_n >= 32);
-      int big_o = 0, big_left = 0;       // current whole-row owner, entries left in whole rows
-      unsigned big_off = 0u;
-      const int tail_n = my_n & 31;
-      const unsigned tail_off = my_off + (unsigned)(my_n & ~31);
-      int end = tail_n;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, end, d);
-        if (lane >= d) end += t;
-      }
-      const int total = __shfl_sync(0xffffffffu, end, 31);
-      int k0 = 0;
-      bool act = false, act_nxt = false;
-      int o = 0, o_nxt = 0;
-      unsigned lt = 0u, lt_nxt = 0u;
-      auto produce = [&]() -> bool {  // warp-uniform control flow; fills (act_nxt, o_nxt, lt_nxt)
-        if (big_left == 0 && big != 0u) {
-          big_o = __ffs(big) - 1;
-          big &= big - 1;
-          big_left = __shfl_sync(0xffffffffu, my_n, big_o) & ~31;
-          big_off = __shfl_sync(0xffffffffu, my_off, big_o);
-        }
-        if (big_left > 0) {
-          o_nxt = big_o;
-          lt_nxt = tile_at(big_off + lane);
-          act_nxt = true;
-          big_off += 32u;
-          big_left -= 32;
-          return true;
-        }
-        if (k0 < total) {
-          const int k = k0 + lane;
-          int oo = 0;
-#pragma unroll
-          for (int step = 16; step > 0; step >>= 1) {
-            const int v = __shfl_sync(0xffffffffu, end, oo + step - 1);
-            if (v <= k) oo += step;
-          }
-          const int prev = __shfl_sync(0xffffffffu, end, (oo - 1) & 31);
-          const unsigned off = __shfl_sync(0xffffffffu, tail_off, oo);
-          o_nxt = oo;
-          act_nxt = k < total;
-          lt_nxt = 0u;
-          if (act_nxt) lt_nxt = tile_at(off + (unsigned)(k - (oo > 0 ? prev : 0)));
-          k0 += 32;
-          return true;
-        }
-        return false;
-      };
-      bool have = produce();
-      while (have) {
-        act = act_nxt; o = o_nxt; lt = lt_nxt;
-        have = produce();
-        rigid_row<DETAIL, FLEX>(rc, bb, l4_addr, lane_sw, act, o, (int)lt, fx, fy, fz, rowoff, p, pos_base, acc0,
-                                acc1, ifr_mask, rc_dev, prep, thr_out, hme, delta102);
-      }
+      rg_score_group<DETAIL, FLEX, false>(rc, bb, l4_addr, lane_sw, rowoff, p, pos_base, prep, brute, thr_out, hme,
+                                          delta102, reach_abs, acc0, acc1, ifr_mask, rc_dev, nullptr);
       __syncwarp();  // FLEX: also "every lane is done with this pose's ligand block"
       const acc_t tsum = warp_sum(rg_join(acc0, acc1));
       const unsigned rbits = __reduce_or_sync(0xffffffffu, ifr_mask);
       if (lane == 0) {
         reinterpret_cast<acc_t *>(bb.partials)[(size_t)p * rc.n_groups + g] = tsum;  // both are 8 bytes
+        bb.iface_rec[(size_t)p * rc.n_groups + g] = rbits;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Pose-major instance for SMALL ligands (a few hundred atoms: 1czy, 1ppe, 2uuy, ab_icode).
+//
+// dfire_rigid_kernel gives a warp one (receptor group, pose) at a time.  For a small complex that is three or four rows
+// of work items, so what a warp does once per task -- fetching the pose's rotation data, (FLEX) staging the pose's
+// ligand block, claiming the task, the warp reduction -- outweighs the pair arithmetic (2uuy: 72 % of the issued
+// instructions).  Here a warp takes (pose, range of groups) instead: the pose's data is fetched and staged ONCE and the
+// groups are walked in a loop.  A CTA then needs the table rows of every receptor type at any time, which no shared
+// memory holds, so the table values are read from the re-indexed table in global memory (L2-resident, 6.9 MB):
+// a small complex makes few enough gathers per pose for that (2uuy: 22,500 per pose, i.e. 0.1 T gathers/s at 4 M
+// poses/s against the 0.29 T/s the box's L2 delivers).  Per-group sums are formed exactly as in the group-major
+// kernel (same lists, same order of additions), so the two instances return the same bits, whatever the range split.
+//
+// Shared memory: [128 B header][ligand block(s): one for the CTA, FLEX: one per warp][16 doubles of rotation data per warp].
+__host__ __device__ inline size_t posemajor_smem_bytes(int n_lig_pad, int warps, bool flex) {
+  return 128 + (size_t)(flex ? warps : 1) * n_lig_pad * 16 + (size_t)warps * RG_PREP * 8;
+}
+template <bool DETAIL, bool FLEX>
+__global__ void __launch_bounds__(RG_THREADS, 1)
+    dfire_posemajor_kernel(const RigidComplex rc, const BatchBuffers bb, int n_poses, int n_splits, int groups_per_split,
+                           unsigned *unit_counter, const RigidComplex *rc_dev, const double *prep_all,
+                           const float4 *__restrict__ lig4p, const float *__restrict__ pose_flag) {
+  typedef typename RgAcc<FLEX>::type acc_t;
+  n_poses = live_poses(bb, n_poses);
+  unsigned char *smem_raw = smem_rigid;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_warps = blockDim.x >> 5;
+  const uint32_t l4_addr = 128u + (FLEX ? (uint32_t)warp * (uint32_t)rc.n_lig_pad * 16u : 0u);
+  float4 *l4 = reinterpret_cast<float4 *>(smem_raw + l4_addr);
+  double *s_prep = reinterpret_cast<double *>(smem_raw + 128 + (size_t)(FLEX ? n_warps : 1) * rc.n_lig_pad * 16) + warp * RG_PREP;
+  const uint32_t lane_sw = (uint32_t)(lane & 7) << 4;
+  const unsigned char *tab = FLEX ? reinterpret_cast<const unsigned char *>(rc.potx_fx)
+                                  : reinterpret_cast<const unsigned char *>(rc.potx);
+  if (!FLEX) {  // the static ligand block, once per CTA
+    for (int i = threadIdx.x; i < rc.n_lig_pad; i += blockDim.x) l4[i] = __ldg(rc.lig4 + i);
+    __syncthreads();
+  }
+  const long long n_units = (long long)n_poses * n_splits;
+  for (;;) {
+    unsigned u = 0;
+    if (lane == 0) u = atomicAdd(unit_counter, 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if ((long long)u >= n_units) break;
+    const int p = (int)(u / (unsigned)n_splits), split = (int)(u % (unsigned)n_splits);
+    const int g0 = split * groups_per_split, g1 = min(g0 + groups_per_split, rc.n_groups);
+    __syncwarp();  // every lane is done with the previous unit's block and rotation data
+    if (lane < RG_PREP) s_prep[lane] = prep_all[(size_t)p * RG_PREP + lane];
+    bool brute = false;
+    float thr_out = rc.thr_out, hme = rc.half_minus_eps, delta102 = rc.delta, reach_abs = 3.0e38f;
+    if (FLEX) {
+      const float4 *src = lig4p + (size_t)p * rc.n_lig_pad;
+      for (int i = lane; i < rc.n_lig_pad; i += 32) l4[i] = __ldg(src + i);
+      const float dmax = pose_flag[p];
+      brute = dmax != 0.f;
+      if (brute) {  // see dfire_rigid_kernel
+        reach_abs = rc.grid_maxabs + dmax + 0.1f;
+        const float d = 2.0e-4f + 1.3e-5f * reach_abs;
+        thr_out = 225.0f + d;
+        delta102 = 1.02f * d;
+        hme = d < 0.01f ? rc.half_minus_eps : -1.0f;
+      }
+    }
+    __syncwarp();
+    for (int g = g0; g < g1; ++g) {
+      const int ia = g * 32 + lane;
+      // byte offset of (receptor type row, ligand type 0, index 4) in `tab` minus what the magic-number index carries
+      const unsigned rowoff = rc.rec_slot[ia] < 0 ? 0xffffffffu
+                                                  : (unsigned)(rc.rec_toff[ia] / DFIRE_ROW) * (unsigned)RG_ROW_BYTES -
+                                                        ((RG_MAGIC_BITS + (unsigned)RG_SLOT0) << 3);
+      acc_t acc0 = 0, acc1 = 0;
+      unsigned ifr_mask = 0u;
+      rg_score_group<DETAIL, FLEX, true>(rc, bb, l4_addr, lane_sw, rowoff, p, g * 32, s_prep, brute, thr_out, hme,
+                                         delta102, reach_abs, acc0, acc1, ifr_mask, rc_dev, tab);
+      const acc_t tsum = warp_sum(rg_join(acc0, acc1));
+      const unsigned rbits = __reduce_or_sync(0xffffffffu, ifr_mask);
+      if (lane == 0) {
+        reinterpret_cast<acc_t *>(bb.partials)[(size_t)p * rc.n_groups + g] = tsum;
         bb.iface_rec[(size_t)p * rc.n_groups + g] = rbits;
       }
     }
