@@ -60,7 +60,6 @@ struct Options {
   int default_path = LD_PATH_AUTO;
   int flex = 1;                   // 0: ligands with ANM modes stay on the generic kernel (no FLEX instance of the ligand-frame path)
   int cells_on_host = 0;          // 1: build the ligand-frame cell lists with host threads (the round-1 builder; cross-check)
-  int pose_major = -1;            // ligand-frame path: -1 = pose-major kernel for small ligands (auto), 0 = never, 1 = whenever it fits
 };
 Options g_opt;
 }  // namespace
@@ -73,7 +72,6 @@ extern "C" int ld_set_option(const char *key, double value) {
   else if (k == "units_per_sm") g_opt.units_per_sm = std::max(1, (int)value);
   else if (k == "cells_on_host") g_opt.cells_on_host = value != 0.0;
   else if (k == "flex") g_opt.flex = value != 0.0;
-  else if (k == "pose_major") g_opt.pose_major = value < 0 ? -1 : (value != 0.0);
   else if (k == "default_path") {
     if (value != LD_PATH_AUTO && value != LD_PATH_GENERIC) return fail(LD_EINVAL, "ld_set_option: default_path is AUTO or GENERIC");
     g_opt.default_path = (int)value;
@@ -143,8 +141,6 @@ struct ld_handle {
   // FLEX: ligand with ANM modes on the ligand-frame path
   bool flex = false;
   int flex_warps = 0, flex_rebuilds = 0;
-  bool pose_major = false;              // small ligand: dfire_posemajor_kernel (warp = pose x group range, table from L2)
-  int pm_warps = 0;
   std::vector<float> tile_slack;        // per ligand tile: slack the current lists were built with
   float *d_tile_slack = nullptr;
   int *d_need = nullptr, *h_need = nullptr;  // running max of the tile displacements seen (float bits), device / pinned
@@ -530,10 +526,6 @@ static int build_cells(ld_handle *h) {
            (double)cx.n_rec / rc.n_groups, rc.rows_max, hh, nc[0], nc[1], nc[2], nonempty, total, longest, delta,
            rigid_smem_bytes(cx.n_lig_pad, rc.rows_max, h->flex ? h->flex_warps : 1));
   h->rigid_info = buf;
-  if (h->pose_major) {
-    snprintf(buf, sizeof buf, ", pose-major kernel (%d warps per CTA, table rows from L2)", h->pm_warps);
-    h->rigid_info += buf;
-  }
   if (h->flex) {
     snprintf(buf, sizeof buf, ", %d warps per CTA, tile slack max %.2f A (rebuilt %d times)", h->flex_warps, max_slack,
              h->flex_rebuilds);
@@ -675,20 +667,6 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   } else {
     CU(cudaFuncSetAttribute(dfire_rigid_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
     CU(cudaFuncSetAttribute(dfire_rigid_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-  }
-  // Pose-major instance (ld_rigid.cuh): pays for small ligands, whose (group, pose) tasks are a handful of rows each
-  {
-    const long per_warp = (long)RG_PREP * 8 + (h->flex ? (long)cx.n_lig_pad * 16 : 0);
-    const long avail = (long)h->max_smem_optin - 128 - (h->flex ? 0 : (long)cx.n_lig_pad * 16);
-    h->pm_warps = (int)std::max<long>(0, std::min<long>(RG_WARPS, avail / per_warp));
-    const bool fits = h->pm_warps >= 12;
-    h->pose_major = fits && (g_opt.pose_major == 1 || (g_opt.pose_major < 0 && cx.n_lig_pad <= 640));
-    if (h->pose_major) {
-      CU(cudaFuncSetAttribute(dfire_posemajor_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-      CU(cudaFuncSetAttribute(dfire_posemajor_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-      CU(cudaFuncSetAttribute(dfire_posemajor_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-      CU(cudaFuncSetAttribute(dfire_posemajor_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
-    }
   }
   CU(cudaMalloc(reinterpret_cast<void **>(&h->d_rc), sizeof(RigidComplex)));
   h->rigid_ok = true;
@@ -1145,32 +1123,6 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       CU(cudaMemsetAsync(h->w->d_iface_lig, 0, (size_t)nc * lig_words * sizeof(unsigned), st));
       CU(cudaMemsetAsync(h->w->d_unit_counter, 0, sizeof(unsigned), st));
       // work units: (group, range of poses); ~16 units per SM and group changes kept rare
-      if (h->pose_major) {
-        // work unit = (pose, range of groups), pulled warp by warp; ranges are split only when the poses alone cannot
-        // occupy the warps (one swarm: 200 poses for 148 x 20 warps), and the split never changes a bit of the result
-        const int warps = h->pm_warps;
-        const int64_t total_warps = (int64_t)h->sm_count * warps;
-        int n_splits = (int)std::max<int64_t>(1, std::min<int64_t>(rg.n_groups, (4 * total_warps + nc - 1) / nc));
-        const int gps = (rg.n_groups + n_splits - 1) / n_splits;
-        n_splits = (rg.n_groups + gps - 1) / gps;
-        const unsigned grid = (unsigned)std::min<int64_t>(h->sm_count, (nc * n_splits + warps - 1) / warps);
-        const size_t smem = posemajor_smem_bytes(rg.n_lig_pad, warps, h->flex);
-        const unsigned threads = (unsigned)warps * 32u;
-        if (h->flex) {
-          if (detail)
-            dfire_posemajor_kernel<true, true><<<grid, threads, smem, st>>>(rg, bb, (int)nc, n_splits, gps, h->w->d_unit_counter,
-                                                                            h->d_rc, h->w->d_prep, h->w->d_lig4p, h->w->d_flag);
-          else
-            dfire_posemajor_kernel<false, true><<<grid, threads, smem, st>>>(rg, bb, (int)nc, n_splits, gps, h->w->d_unit_counter,
-                                                                             h->d_rc, h->w->d_prep, h->w->d_lig4p, h->w->d_flag);
-        } else if (detail) {
-          dfire_posemajor_kernel<true, false><<<grid, threads, smem, st>>>(rg, bb, (int)nc, n_splits, gps, h->w->d_unit_counter,
-                                                                           h->d_rc, h->w->d_prep, nullptr, nullptr);
-        } else {
-          dfire_posemajor_kernel<false, false><<<grid, threads, smem, st>>>(rg, bb, (int)nc, n_splits, gps, h->w->d_unit_counter,
-                                                                            h->d_rc, h->w->d_prep, nullptr, nullptr);
-        }
-      } else {
       const int units_per_sm = g_opt.units_per_sm;
       const int cta_warps = h->flex ? h->flex_warps : RG_WARPS;
       int64_t ppu = (nc * rg.n_groups + (int64_t)h->sm_count * units_per_sm - 1) / ((int64_t)h->sm_count * units_per_sm);
@@ -1193,7 +1145,6 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       } else {
         dfire_rigid_kernel<false, false><<<grid, threads, smem, st>>>(rg, bb, (int)nc, (int)ppu, n_chunks, h->w->d_unit_counter,
                                                                       h->d_rc, h->w->d_prep, nullptr, nullptr);
-      }
       }
       ++launches;
       ++pair_launches;

@@ -47,11 +47,7 @@ constexpr double LIG_PAD = -1.0e30;
 constexpr int RG_SLOT0 = -1;                        // first bin-space index held in a shared-memory row: rint(t - 0.5)
                                                     // is -1 for t < 0 (dist < 0.25), which the reference's saturating
                                                     // `d as usize` sends to index 0, so slot -1 repeats slot 0
-#ifndef LDB200_RG_SLOTS
-#define LDB200_RG_SLOTS 30
-#endif
-constexpr int RG_SLOTS = LDB200_RG_SLOTS;           // indices -1..28 (29, the cut-off itself, is never decided in FP32);
-                                                    // a 31st slot is padding only (odd stride between ligand types)
+constexpr int RG_SLOTS = 30;                        // indices -1..28 (29, the cut-off itself, is never decided in FP32)
 constexpr int RG_PREP = 16;                         // doubles per pose written by rigid_prep_kernel
 constexpr int RG_TB_BYTES = RG_SLOTS * 8;           // one ligand type inside a row
 constexpr int RG_ROW_BYTES = (169 * RG_TB_BYTES + 15) / 16 * 16;  // 40,560

@@ -299,17 +299,13 @@ __device__ __forceinline__ long long rg_join(long long a, long long b) { return 
 __device__ __forceinline__ void rg_add_exact(double &acc, double v, double) { acc = __dadd_rn(acc, v); }
 __device__ __forceinline__ void rg_add_exact(long long &acc, double v, double scale) { acc += __double2ll_rn(v * scale); }
 
-// GTAB: the table rows are read from global memory (L2) instead of the CTA's shared-memory rows (pose-major kernel):
-// `rowoff` is then the byte offset of (receptor type, ligand type 0, index 4) in `tab` minus what the magic-number index
-// carries, and the eight values of an item are loaded together and added afterwards, so that the loads overlap.
-template <bool DETAIL, bool FLEX, bool GTAB>
+template <bool DETAIL, bool FLEX>
 __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuffers &bb, uint32_t l4_addr,
                                           uint32_t lane_sw, bool active, int o, int lt, float rxf, float ryf,
                                           float rzf, unsigned rowoff, int p, int pos_base,
                                           typename RgAcc<FLEX>::type &acc0, typename RgAcc<FLEX>::type &acc1,
                                           unsigned &ifr_mask, const RigidComplex *rc_dev, const double *prep,
-                                          float thr_out, float hme, float delta, const unsigned char *tab) {
-  typedef typename RgAcc<FLEX>::type acc_t;
+                                          float thr_out, float hme, float delta) {
   ld_pose_detail *dt = DETAIL ? reinterpret_cast<ld_pose_detail *>(bb.detail) + p : nullptr;
   const int lane = threadIdx.x & 31;
   const float ax = __shfl_sync(0xffffffffu, rxf, o), ay = __shfl_sync(0xffffffffu, ryf, o),
@@ -324,7 +320,6 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
   unsigned slow_bits = 0u;
   unsigned n_fast = 0;
   float mind2 = 3.0e38f;
-  acc_t vals[GTAB ? LIG_TILE : 1];
 #pragma unroll
   for (int k = 0; k < LIG_TILE; ++k) {
     const float4 a = lds_f4(tile_addr ^ (uint32_t)(k << 4));
@@ -343,14 +338,7 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
     // a.w = ligand type * RG_SLOTS as a float: adding it to m (both integers < 2^24) is exact and leaves
     // MAGIC_BITS + type*RG_SLOTS + index in the mantissa -> one shift-add gives the byte address
     const uint32_t addr = ((uint32_t)__float_as_int(__fadd_rn(m, a.w)) << 3) + rb;
-    if (GTAB) {
-      vals[k] = fast ? __ldg(reinterpret_cast<const acc_t *>(tab + addr)) : (acc_t)0;
-      if (DETAIL && fast) {
-        ++n_fast;
-        atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[dfire_bin_fast(__float_as_int(m) - (int)RG_MAGIC_BITS)]),
-                  1ull);
-      }
-    } else if (fast) {
+    if (fast) {
       if (k & 1) rg_add(acc1, addr);
       else rg_add(acc0, addr);
       if (DETAIL) {
@@ -358,13 +346,6 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
         atomicAdd(reinterpret_cast<unsigned long long *>(&dt->bin_hist[dfire_bin_fast(__float_as_int(m) - (int)RG_MAGIC_BITS)]),
                   1ull);
       }
-    }
-  }
-  if (GTAB) {  // same order of additions as the shared-memory form: k ascending, even k -> acc0, odd k -> acc1
-#pragma unroll
-    for (int k = 0; k < LIG_TILE; ++k) {
-      if (k & 1) acc1 = rg_join(acc1, vals[k]);
-      else acc0 = rg_join(acc0, vals[k]);
     }
   }
   if (mind2 <= 6.0025f + delta) {  // rare: a contact near or below the 2.45 A interface edge (src/dfire.rs:339-342)
@@ -426,18 +407,18 @@ __device__ __forceinline__ long long warp_sum(long long v) {
 
 // One (receptor group, pose): the group's 32 atoms (one per lane) against the ligand of pose p.  Adds the table values
 // to acc0/acc1 (per-lane partial sums, fixed order) and ORs the lanes' interface flags into ifr_mask.
-//   rowoff   per lane: where the lane's table row starts (shared-memory byte address, or byte offset in `tab` for
-//            GTAB), minus what the magic-number index carries; 0xffffffff = pad lane
-//   prep     the pose's rotation data (rigid_prep_kernel), global or shared memory
+//   rowoff   per lane: shared-memory byte address of the lane's table row minus what the magic-number index carries;
+//            0xffffffff = pad lane
+//   prep     the pose's rotation data (rigid_prep_kernel)
 //   brute..reach_abs  FLEX only: the pose left its slacks -> every ligand tile is a candidate, with margins widened to
 //            the coordinates that can then be in range
-template <bool DETAIL, bool FLEX, bool GTAB>
+template <bool DETAIL, bool FLEX>
 __device__ __forceinline__ void rg_score_group(const RigidComplex &rc, const BatchBuffers &bb, uint32_t l4_addr,
                                                uint32_t lane_sw, unsigned rowoff, int p, int pos_base,
                                                const double *prep, bool brute, float thr_out, float hme,
                                                float delta102, float reach_abs, typename RgAcc<FLEX>::type &acc0,
                                                typename RgAcc<FLEX>::type &acc1, unsigned &ifr_mask,
-                                               const RigidComplex *rc_dev, const unsigned char *tab) {
+                                               const RigidComplex *rc_dev) {
   const int lane = threadIdx.x & 31;
   float fx, fy, fz;
   unsigned my_off;
@@ -536,8 +517,8 @@ __device__ __forceinline__ void rg_score_group(const RigidComplex &rc, const Bat
   while (have) {
     act = act_nxt; o = o_nxt; lt = lt_nxt;
     have = produce();
-    rigid_row<DETAIL, FLEX, GTAB>(rc, bb, l4_addr, lane_sw, act, o, (int)lt, fx, fy, fz, rowoff, p, pos_base, acc0,
-                                  acc1, ifr_mask, rc_dev, prep, thr_out, hme, delta102, tab);
+    rigid_row<DETAIL, FLEX>(rc, bb, l4_addr, lane_sw, act, o, (int)lt, fx, fy, fz, rowoff, p, pos_base, acc0, acc1,
+                            ifr_mask, rc_dev, prep, thr_out, hme, delta102);
   }}
 
 // lig4p / pose_flag: FLEX only -- per-pose ligand blocks [n_poses][n_lig_pad] and 1 = "a tile moved further than its
@@ -643,96 +624,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
       }
       acc_t acc0 = 0, acc1 = 0;
       unsigned ifr_mask = 0u;
-      rg_score_group<DETAIL, FLEX, false>(rc, bb, l4_addr, lane_sw, rowoff, p, pos_base, prep, brute, thr_out, hme,
-                                          delta102, reach_abs, acc0, acc1, ifr_mask, rc_dev, nullptr);
+      rg_score_group<DETAIL, FLEX>(rc, bb, l4_addr, lane_sw, rowoff, p, pos_base, prep, brute, thr_out, hme, delta102,
+                                   reach_abs, acc0, acc1, ifr_mask, rc_dev);
       __syncwarp();  // FLEX: also "every lane is done with this pose's ligand block"
       const acc_t tsum = warp_sum(rg_join(acc0, acc1));
       const unsigned rbits = __reduce_or_sync(0xffffffffu, ifr_mask);
       if (lane == 0) {
         reinterpret_cast<acc_t *>(bb.partials)[(size_t)p * rc.n_groups + g] = tsum;  // both are 8 bytes
-        bb.iface_rec[(size_t)p * rc.n_groups + g] = rbits;
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Pose-major instance for SMALL ligands (a few hundred atoms: 1czy, 1ppe, 2uuy, ab_icode).
-//
-// dfire_rigid_kernel gives a warp one (receptor group, pose) at a time.  For a small complex that is three or four rows
-// of work items, so what a warp does once per task -- fetching the pose's rotation data, (FLEX) staging the pose's
-// ligand block, claiming the task, the warp reduction -- outweighs the pair arithmetic (2uuy: 72 % of the issued
-// instructions).  Here a warp takes (pose, range of groups) instead: the pose's data is fetched and staged ONCE and the
-// groups are walked in a loop.  A CTA then needs the table rows of every receptor type at any time, which no shared
-// memory holds, so the table values are read from the re-indexed table in global memory (L2-resident, 6.9 MB):
-// a small complex makes few enough gathers per pose for that (2uuy: 22,500 per pose, i.e. 0.1 T gathers/s at 4 M
-// poses/s against the 0.29 T/s the box's L2 delivers).  Per-group sums are formed exactly as in the group-major
-// kernel (same lists, same order of additions), so the two instances return the same bits, whatever the range split.
-//
-// Shared memory: [128 B header][ligand block(s): one for the CTA, FLEX: one per warp][16 doubles of rotation data per warp].
-__host__ __device__ inline size_t posemajor_smem_bytes(int n_lig_pad, int warps, bool flex) {
-  return 128 + (size_t)(flex ? warps : 1) * n_lig_pad * 16 + (size_t)warps * RG_PREP * 8;
-}
-template <bool DETAIL, bool FLEX>
-__global__ void __launch_bounds__(RG_THREADS, 1)
-    dfire_posemajor_kernel(const RigidComplex rc, const BatchBuffers bb, int n_poses, int n_splits, int groups_per_split,
-                           unsigned *unit_counter, const RigidComplex *rc_dev, const double *prep_all,
-                           const float4 *__restrict__ lig4p, const float *__restrict__ pose_flag) {
-  typedef typename RgAcc<FLEX>::type acc_t;
-  n_poses = live_poses(bb, n_poses);
-  unsigned char *smem_raw = smem_rigid;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int n_warps = blockDim.x >> 5;
-  const uint32_t l4_addr = 128u + (FLEX ? (uint32_t)warp * (uint32_t)rc.n_lig_pad * 16u : 0u);
-  float4 *l4 = reinterpret_cast<float4 *>(smem_raw + l4_addr);
-  double *s_prep = reinterpret_cast<double *>(smem_raw + 128 + (size_t)(FLEX ? n_warps : 1) * rc.n_lig_pad * 16) + warp * RG_PREP;
-  const uint32_t lane_sw = (uint32_t)(lane & 7) << 4;
-  const unsigned char *tab = FLEX ? reinterpret_cast<const unsigned char *>(rc.potx_fx)
-                                  : reinterpret_cast<const unsigned char *>(rc.potx);
-  if (!FLEX) {  // the static ligand block, once per CTA
-    for (int i = threadIdx.x; i < rc.n_lig_pad; i += blockDim.x) l4[i] = __ldg(rc.lig4 + i);
-    __syncthreads();
-  }
-  const long long n_units = (long long)n_poses * n_splits;
-  for (;;) {
-    unsigned u = 0;
-    if (lane == 0) u = atomicAdd(unit_counter, 1u);
-    u = __shfl_sync(0xffffffffu, u, 0);
-    if ((long long)u >= n_units) break;
-    const int p = (int)(u / (unsigned)n_splits), split = (int)(u % (unsigned)n_splits);
-    const int g0 = split * groups_per_split, g1 = min(g0 + groups_per_split, rc.n_groups);
-    __syncwarp();  // every lane is done with the previous unit's block and rotation data
-    if (lane < RG_PREP) s_prep[lane] = prep_all[(size_t)p * RG_PREP + lane];
-    bool brute = false;
-    float thr_out = rc.thr_out, hme = rc.half_minus_eps, delta102 = rc.delta, reach_abs = 3.0e38f;
-    if (FLEX) {
-      const float4 *src = lig4p + (size_t)p * rc.n_lig_pad;
-      for (int i = lane; i < rc.n_lig_pad; i += 32) l4[i] = __ldg(src + i);
-      const float dmax = pose_flag[p];
-      brute = dmax != 0.f;
-      if (brute) {  // see dfire_rigid_kernel
-        reach_abs = rc.grid_maxabs + dmax + 0.1f;
-        const float d = 2.0e-4f + 1.3e-5f * reach_abs;
-        thr_out = 225.0f + d;
-        delta102 = 1.02f * d;
-        hme = d < 0.01f ? rc.half_minus_eps : -1.0f;
-      }
-    }
-    __syncwarp();
-    for (int g = g0; g < g1; ++g) {
-      const int ia = g * 32 + lane;
-      // byte offset of (receptor type row, ligand type 0, index 4) in `tab` minus what the magic-number index carries
-      const unsigned rowoff = rc.rec_slot[ia] < 0 ? 0xffffffffu
-                                                  : (unsigned)(rc.rec_toff[ia] / DFIRE_ROW) * (unsigned)RG_ROW_BYTES -
-                                                        ((RG_MAGIC_BITS + (unsigned)RG_SLOT0) << 3);
-      acc_t acc0 = 0, acc1 = 0;
-      unsigned ifr_mask = 0u;
-      rg_score_group<DETAIL, FLEX, true>(rc, bb, l4_addr, lane_sw, rowoff, p, g * 32, s_prep, brute, thr_out, hme,
-                                         delta102, reach_abs, acc0, acc1, ifr_mask, rc_dev, tab);
-      const acc_t tsum = warp_sum(rg_join(acc0, acc1));
-      const unsigned rbits = __reduce_or_sync(0xffffffffu, ifr_mask);
-      if (lane == 0) {
-        reinterpret_cast<acc_t *>(bb.partials)[(size_t)p * rc.n_groups + g] = tsum;
         bb.iface_rec[(size_t)p * rc.n_groups + g] = rbits;
       }
     }

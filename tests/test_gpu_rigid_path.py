@@ -449,40 +449,3 @@ def test_device_cell_lists_equal_host_lists(name):
     assert entries(info_h) <= entries(info_d) <= entries(info_h) * 1.0001, (info_d, info_h)
     assert sc_dev.create_ms()["cells"] < 50.0, sc_dev.create_ms()
 
-
-# ---- pose-major instance of the ligand-frame kernel (small ligands: warp = pose x group range, table rows from L2) ----
-@pytest.mark.parametrize("name", ["1ppe", "1czy", "2uuy", "ab_icode"])
-def test_pose_major_equals_group_major_bit_for_bit(name):
-    """AUTO selects the pose-major kernel for the small-ligand configurations; with it switched off the same handle
-    type runs the group-major kernel.  Same lists, same per-group order of additions: every output identical, energies
-    BIT FOR BIT, for a large batch (no range split), one swarm (groups split over warps) and single poses."""
-    cx, pos, _ = case(name, O.DFIRE)
-    rng = np.random.default_rng(17)
-    poses = np.tile(pos, (10, 1))
-    poses[:, :3] += rng.normal(0, 1.5, size=(len(poses), 3))
-    pm = scorer_from_oracle(cx)
-    assert "pose-major kernel" in pm.path_info(), pm.path_info()
-    ldb200.set_option("pose_major", 0)
-    try:
-        gm = scorer_from_oracle(cx)
-    finally:
-        ldb200.set_option("pose_major", -1)
-    assert "pose-major kernel" not in gm.path_info() and gm.path_info().startswith("rigid path on"), gm.path_info()
-    for sc in (pm, gm):
-        sc.energy(poses)  # FLEX: learn the slacks (both handles then hold the same lists)
-    e_p, d_p = pm.energy_detail(poses)
-    e_g, d_g = gm.energy_detail(poses)
-    for k in DISCRETE + ("n_pairs_tested", "n_exact_fallback"):
-        np.testing.assert_array_equal(d_p[k], d_g[k], err_msg=k)
-    assert np.array_equal(e_p, e_g)
-    assert np.array_equal(pm.energy(poses), e_p), "plain and detail instantiations"
-    assert np.array_equal(pm.energy(poses[:200]), e_p[:200]), "one swarm: group ranges split over warps"
-    assert np.array_equal(np.array([pm.energy(poses[i:i + 1])[0] for i in range(12)]), e_p[:12])
-    e_ref, d_ref = cx.energy(poses[:64], detail=True)
-    assert_parity(e_p[:64], {k: v[:64] for k, v in d_p.items()}, e_ref, d_ref, cx.method)
-
-
-def test_pose_major_is_not_selected_for_large_ligands():
-    cx, _, _ = case("1k4c", O.DFIRE)
-    sc = scorer_from_oracle(cx)
-    assert sc.path_info().startswith("rigid path on") and "pose-major" not in sc.path_info(), sc.path_info()
