@@ -139,3 +139,84 @@ def test_device_gso_rng_stream_is_the_reference_stream():
         ref, _ = c.multi_gso(pos[None], [seed], 30)
         dev, _ = c.device_gso(pos[None], [seed], 30)
         assert_same_state(dev, ref)
+
+
+def _raw_gso(c, pos, seeds, step_chunks):
+    """The raw C ABI: ld_gso_create, one ld_gso_run per entry of step_chunks, ld_gso_state."""
+    import ctypes as C
+    import ldb200
+    lib = ldb200.load_library()
+    pos = np.ascontiguousarray(pos, np.float64)
+    S, n, pl = pos.shape
+    seeds = np.ascontiguousarray(seeds, np.uint64)
+    g = C.c_void_p()
+    rc = lib.ld_gso_create(C.c_void_p(c.ld_handle()), S, n, pos.ctypes.data, seeds.ctypes.data, C.byref(g))
+    if rc != 0:
+        return rc, lib.ld_last_error().decode()
+    try:
+        for k in step_chunks:
+            assert lib.ld_gso_run(g, k) == 0, lib.ld_last_error()
+        out = dict(poses=np.empty((S, n, pl)), lum=np.empty((S, n)), vis=np.empty((S, n)), sc=np.empty((S, n)),
+                   nn=np.empty((S, n), np.int32), failed=np.empty(S, np.int32))
+        assert lib.ld_gso_state(g, *[out[k].ctypes.data for k in ("poses", "lum", "vis", "sc", "nn", "failed")]) == 0
+        out["steps"] = lib.ld_gso_steps(g)
+        out["calls"] = lib.ld_gso_energy_calls(g)
+    finally:
+        lib.ld_gso_destroy(g)
+    return 0, out
+
+
+def test_device_gso_edge_shapes():
+    """Swarm sizes that are not a multiple of the warp size, a swarm of one glowworm (never moves: one energy call),
+    zero steps (start state, Glowworm::new values), chunked runs == one run, and the glowworm limit."""
+    from ldb200 import host
+    g = os.path.join(GOLDEN, "1azp")
+    c = host.Case(os.path.join(g, "setup.json"), "dna", anm_dir=g)
+    pos = start_positions(g)
+    for n in (37, 1, 64):
+        sub = np.stack([pos[:n], pos[50:50 + n]])
+        ref, calls_ref = c.multi_gso(sub, [c.seed, 7], 15)
+        dev, calls_dev = c.device_gso(sub, [c.seed, 7], 15)
+        assert calls_dev == calls_ref
+        assert_same_state(dev, ref)
+        if n == 1:
+            assert calls_dev == 2 and np.array_equal(dev[..., 4:], sub), "a lone glowworm is scored once and never moves"
+    rc, st = _raw_gso(c, pos[None], [c.seed], [0])
+    assert rc == 0 and st["steps"] == 0 and st["calls"] == 0
+    assert np.array_equal(st["poses"][0], pos) and (st["lum"] == 5.0).all() and (st["vis"] == 0.2).all()
+    assert (st["sc"] == 0.0).all() and not st["nn"].any() and not st["failed"].any()
+    rc, one = _raw_gso(c, pos[None], [c.seed], [7])
+    rc2, chunks = _raw_gso(c, pos[None], [c.seed], [3, 0, 4])
+    assert rc == 0 and rc2 == 0 and one["steps"] == chunks["steps"] == 7 and one["calls"] == chunks["calls"]
+    for k in ("poses", "lum", "vis", "sc", "nn"):
+        assert np.array_equal(one[k], chunks[k]), k
+    big = np.tile(pos[:1], (1025, 1))[None]
+    rc, msg = _raw_gso(c, big, [1], [])
+    assert rc == -4 and "LD_GSO_MAX_GLOWWORMS" in msg  # LD_ELIMIT
+    rc, ok = _raw_gso(c, np.tile(pos[:1], (1024, 1))[None] + np.linspace(0, 1, 1024)[None, :, None], [1], [2])
+    assert rc == 0 and ok["steps"] == 2 and not ok["failed"].any()
+
+
+def test_device_gso_interleaves_with_ordinary_scoring_calls():
+    """Between two ld_gso_run calls the handle's other entry points stay usable (they share slot 0's buffers and stream)
+    and do not disturb the optimisation."""
+    from ldb200 import host
+    g = os.path.join(GOLDEN, "1azp")
+    c = host.Case(os.path.join(g, "setup.json"), "dna", anm_dir=g)
+    pos = start_positions(g)
+    import ctypes as C
+    import ldb200
+    lib = ldb200.load_library()
+    rc, ref = _raw_gso(c, pos[None], [c.seed], [12])
+    gh = C.c_void_p()
+    seeds = np.array([c.seed], np.uint64)
+    flat = np.ascontiguousarray(pos[None], np.float64)
+    assert lib.ld_gso_create(C.c_void_p(c.ld_handle()), 1, len(pos), flat.ctypes.data, seeds.ctypes.data, C.byref(gh)) == 0
+    e0 = c.energy_batch(pos[:50])
+    assert lib.ld_gso_run(gh, 5) == 0
+    assert np.array_equal(c.energy_batch(pos[:50]), e0)
+    assert lib.ld_gso_run(gh, 7) == 0
+    poses = np.empty((1, len(pos), pos.shape[1]))
+    assert lib.ld_gso_state(gh, poses.ctypes.data, None, None, None, None, None) == 0
+    lib.ld_gso_destroy(gh)
+    assert np.array_equal(poses, ref["poses"])

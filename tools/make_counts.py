@@ -22,9 +22,9 @@ def source_sha():
 
 def main():
     out = {"source_sha256": source_sha(), "how": "ncu --metrics ... --clock-control none, tools/capture_counts.sh: the "
-           "second ld_score_batch call of tools/count_target.py <config> (20,000 poses; 1k4c_bench: the 80,000-pose "
-           "bench step)", "kernels": {}}
-    poses = {"1k4c_bench": 80000}
+           "third ld_score_batch call of tools/count_target.py <config> (20,000 poses; 1k4c_bench: 60,000 poses of "
+           "the bench step)", "kernels": {}}
+    poses = {"1k4c_bench": 60000}
     for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "counts_*.csv"))):
         cfg = os.path.basename(path)[len("counts_"):-4]
         rows = [r for r in csv.reader(open(path)) if r and not r[0].startswith("==")]
@@ -36,6 +36,14 @@ def main():
             kname = d["Kernel Name"]
         if not vals:
             continue
+        # poses of the captured launch: printed by tools/count_target.py ("<config> <n> poses ...")
+        n_poses = poses.get(cfg, 20000)
+        log = os.path.join(ROOT, "gpurun_out", f"counts_{cfg}.log")
+        if os.path.exists(log):
+            for line in open(log, errors="ignore"):
+                w = line.split()
+                if len(w) >= 3 and w[0] == cfg and w[2] == "poses" and w[1].isdigit():
+                    n_poses = int(w[1])
         def v(name, scale=None):
             x, unit = vals[name]
             if scale == "bytes":
@@ -44,7 +52,7 @@ def main():
                 x *= {"ns": 1e-6, "us": 1e-3, "ms": 1, "s": 1e3}[unit]
             return x
         out["kernels"][cfg] = {
-            "kernel": kname.split("(")[0], "poses": poses.get(cfg, 20000),
+            "kernel": kname.split("(")[0], "poses": n_poses,
             "warp_inst": v("smsp__inst_executed.sum"), "thread_inst": v("smsp__thread_inst_executed.sum"),
             "dram_read_bytes": v("dram__bytes_read.sum", "bytes"), "dram_write_bytes": v("dram__bytes_write.sum", "bytes"),
             "smem_wavefronts": v("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
