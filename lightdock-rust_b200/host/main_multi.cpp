@@ -13,6 +13,7 @@
 // steps method` (tests/test_gpu_trajectory.py).  Swarm i of the list goes to device i mod G; devices are
 // $LIGHTDOCK_B200_DEVICES (comma-separated ordinals) or every visible one.  No data crosses GPUs.
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -198,7 +199,8 @@ int main(int argc, char **argv) {
         std::fprintf(stderr, "lightdock-rust-multi: %s failed: %s\n", f.first.c_str(), f.second.c_str());
         ++n_failed;
       }
-    return n_failed ? 1 : 0;
+    std::fflush(nullptr);
+    _exit(n_failed ? 1 : 0);  // skip the tear-down of up to eight CUDA contexts: every file is written
   } catch (const std::exception &e) {
     std::fprintf(stderr, "lightdock-rust-multi: %s\n", e.what());
     return 1;
