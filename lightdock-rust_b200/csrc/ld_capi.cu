@@ -1406,29 +1406,30 @@ extern "C" int ld_gso_destroy(ld_gso *g) {
   return LD_OK;
 }
 
-template <typename T>
-static int gso_alloc(ld_gso *g, T **p, size_t count) {
-  *p = nullptr;
-  CU(cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(count, 1) * sizeof(T)));
-  g->owned.push_back(*p);
-  return LD_OK;
-}
-
 static int gso_create_impl(ld_gso *g, const double *positions, const uint64_t *seeds) {
   GsoState &st = g->st;
   const size_t G = (size_t)st.n_swarms * st.n_glow, pl = (size_t)st.pose_len;
   cudaStream_t stream = g->h->ws[0].stream;
-  int rc;
   double *p0 = nullptr, *p1 = nullptr, *lum = nullptr, *vis = nullptr, *sc = nullptr, *packed = nullptr, *en = nullptr;
   int *nn = nullptr, *slot = nullptr, *np = nullptr, *failed = nullptr;
   uint32_t *keys = nullptr;
   g->cap_steps = 1 << 16;
-  if ((rc = gso_alloc(g, &p0, G * pl)) || (rc = gso_alloc(g, &p1, G * pl)) || (rc = gso_alloc(g, &lum, G)) ||
-      (rc = gso_alloc(g, &vis, G)) || (rc = gso_alloc(g, &sc, G)) || (rc = gso_alloc(g, &packed, G * pl)) ||
-      (rc = gso_alloc(g, &en, G)) || (rc = gso_alloc(g, &nn, G)) || (rc = gso_alloc(g, &slot, G)) ||
-      (rc = gso_alloc(g, &np, (size_t)g->cap_steps)) || (rc = gso_alloc(g, &failed, (size_t)st.n_swarms)) ||
-      (rc = gso_alloc(g, &keys, (size_t)st.n_swarms * 8)))
-    return rc;
+  // one allocation, carved (256-byte aligned pieces): creating and destroying a ld_gso costs one cudaMalloc / cudaFree
+  size_t total = 0;
+  auto reserve = [&](size_t bytes) { const size_t at = total; total += (std::max<size_t>(bytes, 1) + 255) / 256 * 256; return at; };
+  const size_t o_p0 = reserve(G * pl * 8), o_p1 = reserve(G * pl * 8), o_packed = reserve(G * pl * 8), o_lum = reserve(G * 8),
+               o_vis = reserve(G * 8), o_sc = reserve(G * 8), o_en = reserve(G * 8), o_nn = reserve(G * 4), o_slot = reserve(G * 4),
+               o_np = reserve((size_t)g->cap_steps * 4), o_failed = reserve((size_t)st.n_swarms * 4),
+               o_keys = reserve((size_t)st.n_swarms * 32);
+  unsigned char *slab = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void **>(&slab), total));
+  g->owned.push_back(slab);
+  p0 = reinterpret_cast<double *>(slab + o_p0); p1 = reinterpret_cast<double *>(slab + o_p1);
+  packed = reinterpret_cast<double *>(slab + o_packed); lum = reinterpret_cast<double *>(slab + o_lum);
+  vis = reinterpret_cast<double *>(slab + o_vis); sc = reinterpret_cast<double *>(slab + o_sc);
+  en = reinterpret_cast<double *>(slab + o_en); nn = reinterpret_cast<int *>(slab + o_nn);
+  slot = reinterpret_cast<int *>(slab + o_slot); np = reinterpret_cast<int *>(slab + o_np);
+  failed = reinterpret_cast<int *>(slab + o_failed); keys = reinterpret_cast<uint32_t *>(slab + o_keys);
   CU(cudaHostAlloc(reinterpret_cast<void **>(&g->h_counts), (size_t)g->cap_steps * sizeof(int), cudaHostAllocDefault));
   st.poses[0] = p0; st.poses[1] = p1; st.luciferin = lum; st.vision = vis; st.scoring = sc; st.packed = packed;
   st.energies = en; st.n_neighbors = nn; st.slot = slot; st.n_packed = np; st.failed = failed; st.keys = keys;

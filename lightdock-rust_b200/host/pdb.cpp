@@ -1,5 +1,6 @@
 #include "pdb.hpp"
 
+#include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <map>
@@ -71,6 +72,8 @@ PDB open_pdb(const std::string &path) {
     a.y = parse_f64(cols(line, 38, 46), "y", lineno);
     a.z = parse_f64(cols(line, 46, 54), "z", lineno);
     a.res_name = res_name;
+    a.record = line;
+    while (!a.record.empty() && (a.record.back() == '\r' || a.record.back() == '\n')) a.record.pop_back();
     // chain: first with the same id, else a new one
     Chain *ch = nullptr;
     for (auto &c : chains)
@@ -99,6 +102,15 @@ PDB open_pdb(const std::string &path) {
         for (auto &a : cf.atoms) pdb.atoms.push_back(a);
     }
   return pdb;
+}
+
+std::string atom_record_at(const Atom &a, double x, double y, double z) {
+  std::string r = a.record;
+  if (r.size() < 54) r.resize(54, ' ');
+  char buf[32];
+  std::snprintf(buf, sizeof buf, "%8.3f%8.3f%8.3f", x, y, z);
+  r.replace(30, 24, std::string(buf).substr(0, 24));
+  return r;
 }
 
 std::string residue_id(const Atom &a) {

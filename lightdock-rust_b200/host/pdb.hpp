@@ -16,6 +16,7 @@ struct Atom {
   std::string icode;    // column 27, empty if blank
   double x = 0, y = 0, z = 0;
   bool hetero = false;
+  std::string record;   // the ATOM/HETATM line as read (for writing the atom back with new coordinates)
 };
 
 struct PDB {
@@ -28,5 +29,8 @@ PDB open_pdb(const std::string &path);
 
 // "{chain}.{res_name}.{serial}{icode}", src/dfire.rs:138-141
 std::string residue_id(const Atom &a);
+
+// The atom's record with columns 31-54 replaced by the given coordinates (%8.3f each), padded to 54 columns at least.
+std::string atom_record_at(const Atom &a, double x, double y, double z);
 
 }  // namespace lightdock

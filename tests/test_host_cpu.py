@@ -240,3 +240,14 @@ def test_pdb_reader_edge_cases_agree_between_host_and_oracle(tmp_path):
     # active restraint groups, each with the atoms of ITS residue only (2 and 2A are distinct)
     groups = {tuple(m["rst_atoms"][m["rst_offsets"][k]:m["rst_offsets"][k + 1]].tolist()) for k in range(len(m["rst_offsets"]) - 1)}
     assert groups == {(6, 7, 8), (9, 10), (13, 14)}
+
+
+def test_conformations_cli_usage_and_record_rewriting(tmp_path):
+    """bin/lightdock-rust-conformations: usage error without a GPU; the record writer keeps every column but 31-54."""
+    import subprocess
+    from ldb200 import host
+    exe = os.path.join(os.path.dirname(host.CLI_PATH), "lightdock-rust-conformations")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 2 and "Usage:" in r.stderr
+    r = subprocess.run([exe, "nope.json", "gso_1.out", "dfire"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "lightdock-rust-conformations:" in r.stderr
