@@ -43,6 +43,11 @@ extern "C" {
     fn ld_pose_len(h: *const c_void) -> c_int;
     fn ld_score_batch(h: *mut c_void, n_poses: i64, poses: *const f64, energies: *mut f64) -> c_int;
     fn ld_last_error() -> *const c_char;
+    // optional: the whole GSO loop on the device (see `DeviceGso` at the end of this file)
+    fn ld_gso_create(h: *mut c_void, n_swarms: i32, n_glowworms: i32, positions: *const f64, seeds: *const u64, out: *mut *mut c_void) -> c_int;
+    fn ld_gso_run(g: *mut c_void, n_steps: i32) -> c_int;
+    fn ld_gso_state(g: *mut c_void, poses: *mut f64, luciferin: *mut f64, vision_range: *mut f64, scoring: *mut f64, n_neighbors: *mut i32, failed_step: *mut i32) -> c_int;
+    fn ld_gso_destroy(g: *mut c_void) -> c_int;
 }
 
 /// Numeric view of one docking model (what DFIREDockingModel / DNADockingModel already hold).
@@ -137,5 +142,55 @@ impl Score for CudaScore {
 impl Drop for CudaScore {
     fn drop(&mut self) {
         unsafe { ld_destroy(self.handle) };
+    }
+}
+
+
+/// Optional: `GSO::run` (src/lib.rs:46-58) with the whole step on the device.  One swarm per `positions` chunk of
+/// `n_glowworms * pose_len` values, each seeded like `StdRng::seed_from_u64(seed)`.  `run(steps)` advances every swarm;
+/// `state()` returns what `Swarm::save` prints.  Trajectories equal the host loop's to the last bit or two (CUDA's
+/// acos/sin inside slerp), so upstream would keep `GSO::run` as the default and offer this behind a flag.
+pub struct DeviceGso {
+    gso: *mut c_void,
+    n: usize,
+    pose_len: usize,
+}
+
+impl DeviceGso {
+    pub fn new(score: &CudaScore, n_swarms: usize, n_glowworms: usize, positions: &[f64], seeds: &[u64]) -> DeviceGso {
+        assert_eq!(positions.len(), n_swarms * n_glowworms * score.pose_len);
+        assert_eq!(seeds.len(), n_swarms);
+        let mut gso: *mut c_void = std::ptr::null_mut();
+        let rc = unsafe { ld_gso_create(score.handle, n_swarms as i32, n_glowworms as i32, positions.as_ptr(), seeds.as_ptr(), &mut gso) };
+        if rc != 0 {
+            panic!("ld_gso_create: {}", last_error());
+        }
+        DeviceGso { gso, n: n_swarms * n_glowworms, pose_len: score.pose_len }
+    }
+
+    pub fn run(&mut self, steps: u32) {
+        if unsafe { ld_gso_run(self.gso, steps as i32) } != 0 {
+            panic!("ld_gso_run: {}", last_error());
+        }
+    }
+
+    /// (poses, luciferin, vision_range, scoring, n_neighbors)
+    pub fn state(&self) -> (Vec<f64>, Vec<f64>, Vec<f64>, Vec<f64>, Vec<i32>) {
+        let mut poses = vec![0.0; self.n * self.pose_len];
+        let (mut lum, mut vis, mut sc) = (vec![0.0; self.n], vec![0.0; self.n], vec![0.0; self.n]);
+        let mut nn = vec![0i32; self.n];
+        let rc = unsafe {
+            ld_gso_state(self.gso, poses.as_mut_ptr(), lum.as_mut_ptr(), vis.as_mut_ptr(), sc.as_mut_ptr(), nn.as_mut_ptr(), std::ptr::null_mut())
+        };
+        if rc != 0 {
+            panic!("ld_gso_state: {}", last_error());
+        }
+        (poses, lum, vis, sc, nn)
+    }
+}
+
+impl Drop for DeviceGso {
+    fn drop(&mut self) {
+        unsafe { ld_gso_destroy(self.gso) };
     }
 }
