@@ -74,3 +74,41 @@ for name, n in (("1ppe", 60000), ("1k4c", 12000)):
     err = np.abs(e_gpu - e_ref) / np.maximum(np.abs(e_ref), 1.0)
     assert err.max() < 1e-9, err.max()
     print(f"{name}: {n} poses, rigid kernel vs oracle ({ncores} threads, {dt:.0f} s): max |dE|/max(|E|,1) = {err.max():.1e}", flush=True)
+
+# ---- third leg (round 2): the FLEX instance (ligand with ANM modes) against the generic kernel and the oracle ----------
+NF = int(os.environ.get("FLEX_POSES", str(N // 4)))
+flex_pairs = 0
+for name in ("2uuy", "1czy", "ab_icode"):
+    cx, pos, _ = case(name, O.DFIRE)
+    sc = scorer_from_oracle(cx)
+    assert sc.path_info().startswith("rigid path on (flexible ligand"), sc.path_info()
+    rng = np.random.default_rng(99)
+    poses = np.tile(pos, (NF // len(pos) + 1, 1))[:NF].copy()
+    poses[:, :3] += rng.normal(0, 2.0, size=(NF, 3))
+    q = poses[:, 3:7] + rng.normal(0, 0.15, size=(NF, 4))
+    poses[:, 3:7] = q / np.linalg.norm(q, axis=1, keepdims=True)
+    poses[:, 7:] *= rng.uniform(0.3, 1.6, size=(NF, 1))  # ANM extents from a third of to 1.6x the shipped ones
+    worst_f = 0.0
+    for lo in range(0, NF, 4000):
+        chunk = np.ascontiguousarray(poses[lo:lo + 4000])
+        sc.set_path(ldb200.PATH_RIGID)
+        e_f, d_f = sc.energy_detail(chunk)
+        sc.set_path(ldb200.PATH_GENERIC)
+        e_g, d_g = sc.energy_detail(chunk)
+        for k in ("n_in_cutoff", "n_interface_pairs", "bin_hist", "rec_rst_hit", "lig_rst_hit", "membrane_hit",
+                  "iface_rec", "iface_lig"):
+            if not np.array_equal(d_f[k], d_g[k]):
+                bad = np.where((d_f[k] != d_g[k]).reshape(len(chunk), -1).any(axis=1))[0]
+                raise SystemExit(f"MISMATCH in {k} for {name} (FLEX), poses {lo + bad[:5]}")
+        scale = np.maximum(np.abs(d_g["raw_sum"]) * 0.0157, 1.0)
+        worst_f = max(worst_f, float((np.abs(e_f - e_g) / scale).max()))
+        flex_pairs += int(d_f["n_in_cutoff"].sum())
+    assert worst_f < 1e-9, worst_f
+    n_or = min(NF, 20000)
+    e_ref = cx.energy_mt(poses[:n_or], ncores)
+    sc.set_path(ldb200.PATH_RIGID)
+    err = np.abs(sc.energy(poses[:n_or]) - e_ref) / np.maximum(np.abs(e_ref), 1.0)
+    assert err.max() < 1e-9, err.max()
+    print(f"{name}: FLEX vs generic on {NF} poses identical (cumulative in-cut-off pairs {flex_pairs:,}, largest energy "
+          f"difference {worst_f:.1e} of the summed magnitude); FLEX vs oracle on {n_or} poses: max |dE|/max(|E|,1) = "
+          f"{err.max():.1e}; {sc.path_info().split('tile slack')[-1].strip()}", flush=True)
