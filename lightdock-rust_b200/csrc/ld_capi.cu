@@ -60,6 +60,7 @@ struct Options {
   int default_path = LD_PATH_AUTO;
   int flex = 1;                   // 0: ligands with ANM modes stay on the generic kernel (no FLEX instance of the ligand-frame path)
   int cells_on_host = 0;          // 1: build the ligand-frame cell lists with host threads (the round-1 builder; cross-check)
+  int compact_tiles = 1;          // 0: keep the plain bisection order of the atoms (tiles less compact; A/B aid)
 };
 Options g_opt;
 }  // namespace
@@ -72,6 +73,7 @@ extern "C" int ld_set_option(const char *key, double value) {
   else if (k == "units_per_sm") g_opt.units_per_sm = std::max(1, (int)value);
   else if (k == "cells_on_host") g_opt.cells_on_host = value != 0.0;
   else if (k == "flex") g_opt.flex = value != 0.0;
+  else if (k == "compact_tiles") g_opt.compact_tiles = value != 0.0;
   else if (k == "default_path") {
     if (value != LD_PATH_AUTO && value != LD_PATH_GENERIC) return fail(LD_EINVAL, "ld_set_option: default_path is AUTO or GENERIC");
     g_opt.default_path = (int)value;
@@ -190,10 +192,145 @@ static void bisect(std::vector<int> &idx, int lo, int hi, const double *xyz, int
   bisect(idx, lo, mid, xyz, tile);
   bisect(idx, mid, hi, xyz, tile);
 }
-static std::vector<int> spatial_order(const double *xyz, int n, int tile) {
+// Makes the tiles of a bisection order more COMPACT.  A tile enters a cell's list (ligand-frame path) or survives the
+// sphere culling (generic paths) as soon as ONE of its atoms is in reach, and then all of its atoms are tested: the
+// executed pair tests follow the tiles' radii.  Bisection leaves 1k4c's 8-atom ligand tiles with a mean radius of
+// 4.2 A; a capacity-constrained k-means started from those tiles (atoms claim their nearest centroid in order of
+// decreasing regret) followed by pairwise swaps that lower the sum of squared distances brings it to 3.3 A, which is
+// 6 % fewer executed pair tests on the bench workload.  Deterministic (no random numbers, ties by index); tile k
+// stays where bisection put it, so consecutive tile ids remain neighbours.
+static void compact_tiles(std::vector<int> &idx, const double *xyz, int n, int tile) {
+  const int K = (n + tile - 1) / tile;
+  if (K < 2) return;
+  std::vector<int> cap(K, tile), assign(n);
+  cap[K - 1] = n - (K - 1) * tile;
+  for (int i = 0; i < n; ++i) assign[idx[i]] = i / tile;
+  std::vector<double> cent(3 * (size_t)K);
+  auto centroids = [&] {
+    std::fill(cent.begin(), cent.end(), 0.0);
+    std::vector<int> cnt(K, 0);
+    for (int a = 0; a < n; ++a) {
+      for (int d = 0; d < 3; ++d) cent[3 * (size_t)assign[a] + d] += xyz[3 * (size_t)a + d];
+      ++cnt[assign[a]];
+    }
+    for (int k = 0; k < K; ++k)
+      for (int d = 0; d < 3; ++d) cent[3 * (size_t)k + d] /= std::max(1, cnt[k]);
+  };
+  auto dist2 = [&](int a, int k) {
+    double v = 0.0;
+    for (int d = 0; d < 3; ++d) {
+      const double e = xyz[3 * (size_t)a + d] - cent[3 * (size_t)k + d];
+      v += e * e;
+    }
+    return v;
+  };
+  // candidate tiles of an atom: the MC tiles nearest to it at the start (centroids move by a fraction of a tile, so the
+  // set is searched once, in full, and only re-ranked afterwards)
+  const int MC = std::min(16, K), M = std::min(12, K);
+  std::vector<int> candk((size_t)n * MC), nb((size_t)n * M);
+  std::vector<double> nd((size_t)n * M);
+  {
+    centroids();
+    std::vector<std::pair<double, int>> all(K);
+    for (int a = 0; a < n; ++a) {
+      for (int k = 0; k < K; ++k) all[k] = {dist2(a, k), k};
+      std::partial_sort(all.begin(), all.begin() + MC, all.end());
+      for (int j = 0; j < MC; ++j) candk[(size_t)a * MC + j] = all[j].second;
+    }
+  }
+  auto nearest = [&] {  // the M nearest of the candidate centroids of every atom, ascending
+    std::pair<double, int> c[16];
+    for (int a = 0; a < n; ++a) {
+      for (int j = 0; j < MC; ++j) c[j] = {dist2(a, candk[(size_t)a * MC + j]), candk[(size_t)a * MC + j]};
+      std::sort(c, c + MC);
+      for (int j = 0; j < M; ++j) { nd[(size_t)a * M + j] = c[j].first; nb[(size_t)a * M + j] = c[j].second; }
+    }
+  };
+  std::vector<int> order(n), load(K), next(n);
+  for (int it = 0; it < 12; ++it) {  // capacity-constrained k-means
+    centroids();
+    nearest();
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {  // largest regret (second best - best) first
+      const double ra = M > 1 ? nd[(size_t)a * M + 1] - nd[(size_t)a * M] : 0.0;
+      const double rb = M > 1 ? nd[(size_t)b * M + 1] - nd[(size_t)b * M] : 0.0;
+      return ra > rb;
+    });
+    std::fill(load.begin(), load.end(), 0);
+    std::fill(next.begin(), next.end(), -1);
+    for (int a : order)
+      for (int j = 0; j < M; ++j) {
+        const int k = nb[(size_t)a * M + j];
+        if (load[k] < cap[k]) { next[a] = k; ++load[k]; break; }
+      }
+    for (int a : order)
+      if (next[a] < 0) {  // its M nearest tiles were full: the nearest one with room
+        int best = -1;
+        double bd = 0.0;
+        for (int k = 0; k < K; ++k)
+          if (load[k] < cap[k]) {
+            const double d2 = dist2(a, k);
+            if (best < 0 || d2 < bd) { best = k; bd = d2; }
+          }
+        next[a] = best;
+        ++load[best];
+      }
+    if (next == assign) break;
+    assign = next;
+  }
+  std::vector<std::vector<int>> members(K);
+  for (int a = 0; a < n; ++a) members[assign[a]].push_back(a);
+  std::vector<double> own(n), rad2(K);
+  for (int pass = 0; pass < 20; ++pass) {  // pairwise swaps between neighbouring tiles
+    centroids();
+    nearest();
+    std::fill(rad2.begin(), rad2.end(), 0.0);
+    for (int a = 0; a < n; ++a) {
+      own[a] = dist2(a, assign[a]);
+      rad2[assign[a]] = std::max(rad2[assign[a]], own[a]);
+    }
+    int moved = 0;
+    for (int a = 0; a < n; ++a) {
+      const int ka = assign[a];
+      const double da = dist2(a, ka);
+      for (int j = 0; j < std::min(4, M); ++j) {
+        const int kb = nb[(size_t)a * M + j];
+        if (kb == ka) continue;
+        // gain of swapping a with b of tile kb = [d(a,ka) - d(a,kb)] + [d(b,kb) - d(b,ka)]; the second bracket is at
+        // most the squared radius of tile kb
+        const double ga = da - nd[(size_t)a * M + j];
+        if (ga + rad2[kb] <= 1e-9) continue;
+        int bj = -1;
+        double bg = 1e-9;
+        for (size_t t = 0; t < members[kb].size(); ++t) {
+          const int b = members[kb][t];
+          const double gain = ga + dist2(b, kb) - dist2(b, ka);
+          if (gain > bg) { bg = gain; bj = (int)t; }
+        }
+        if (bj >= 0) {
+          const int b = members[kb][bj];
+          members[kb][bj] = a;
+          *std::find(members[ka].begin(), members[ka].end(), a) = b;
+          assign[a] = kb;
+          assign[b] = ka;
+          ++moved;
+          break;
+        }
+      }
+    }
+    if (moved * 200 < n) break;  // converged: fewer than 0.5 % of the atoms still move
+  }
+  int pos = 0;
+  for (int k = 0; k < K; ++k) {
+    std::sort(members[k].begin(), members[k].end());
+    for (int a : members[k]) idx[pos++] = a;
+  }
+}
+static std::vector<int> spatial_order(const double *xyz, int n, int tile, bool compact) {
   std::vector<int> idx(n);
   std::iota(idx.begin(), idx.end(), 0);
   bisect(idx, 0, n, xyz, tile);
+  if (compact && g_opt.compact_tiles) compact_tiles(idx, xyz, n, tile);
   return idx;
 }
 
@@ -234,12 +371,13 @@ struct SortedMol {
   std::vector<int> rst_off, rst_idx, mem_idx;
   int n = 0, n_pad = 0, n_tiles = 0;
 };
-static SortedMol sort_molecule(const ld_molecule_desc &m, int method, int tile, double pad, int n_modes_eff) {
+static SortedMol sort_molecule(const ld_molecule_desc &m, int method, int tile, double pad, int n_modes_eff,
+                               bool compact) {
   SortedMol s;
   s.n = m.n_atoms;
   s.n_tiles = (m.n_atoms + tile - 1) / tile;
   s.n_pad = s.n_tiles * tile;
-  s.perm = spatial_order(m.coords, m.n_atoms, tile);
+  s.perm = spatial_order(m.coords, m.n_atoms, tile, compact);
   s.inv.assign(m.n_atoms, 0);
   for (int i = 0; i < m.n_atoms; ++i) s.inv[s.perm[i]] = i;
   s.x.assign(s.n_pad, pad); s.y.assign(s.n_pad, pad); s.z.assign(s.n_pad, pad);
@@ -717,10 +855,21 @@ extern "C" int ld_get_create_ms(const ld_handle *h, double *out4) {
 }
 
 static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
-  const auto t_start = std::chrono::steady_clock::now();
+  const auto t_sort = std::chrono::steady_clock::now();
   const int method = desc->method == LD_METHOD_DFIRE ? 0 : 1;
   h->device = desc->device;
   h->use_anm = desc->use_anm ? 1 : 0;
+  // Host-only work first: a driver that creates the CUDA context on a helper thread (ld_init_device) is still waiting
+  // for it at this point, so sorting the atoms into compact tiles costs it nothing.  The ligand's tiles of 8 are always
+  // compacted (they carry the culling of every path); the receptor's tiles of 32 only where a kernel uses them as
+  // culling units (DNA/pyDock; the DFIRE ligand-frame path groups the receptor by type instead).
+  const int nrm = h->use_anm ? desc->receptor.n_modes : 0, nlm = h->use_anm ? desc->ligand.n_modes : 0;
+  SortedMol R = sort_molecule(desc->receptor, desc->method == LD_METHOD_DFIRE ? LD_METHOD_DFIRE : LD_METHOD_DNA,
+                              REC_TILE, REC_PAD, nrm, method != 0);
+  SortedMol L = sort_molecule(desc->ligand, desc->method == LD_METHOD_DFIRE ? LD_METHOD_DFIRE : LD_METHOD_DNA,
+                              LIG_TILE, LIG_PAD, nlm, true);
+  const double sort_ms = ms_since(t_sort);
+  const auto t_start = std::chrono::steady_clock::now();
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
@@ -745,11 +894,6 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
     CU(cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
   }
 
-  const int nrm = h->use_anm ? desc->receptor.n_modes : 0, nlm = h->use_anm ? desc->ligand.n_modes : 0;
-  SortedMol R = sort_molecule(desc->receptor, desc->method == LD_METHOD_DFIRE ? LD_METHOD_DFIRE : LD_METHOD_DNA,
-                              REC_TILE, REC_PAD, nrm);
-  SortedMol L = sort_molecule(desc->ligand, desc->method == LD_METHOD_DFIRE ? LD_METHOD_DFIRE : LD_METHOD_DNA,
-                              LIG_TILE, LIG_PAD, nlm);
   h->rec_perm = R.perm;
   h->lig_perm = L.perm;
   // DNA/pyDock: sqrt(eps_r * eps_l) (src/dna.rs:496) as sqrt(eps_r) * sqrt(eps_l) with the roots taken once here;
@@ -871,7 +1015,7 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
   CU(cudaFuncSetAttribute(dna_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CU(cudaFuncSetAttribute(dna_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   h->path_mode = g_opt.default_path;
-  h->create_ms[1] = ms_since(t_complex);
+  h->create_ms[1] = ms_since(t_complex) + sort_ms;
   const auto t_rigid = std::chrono::steady_clock::now();
   const int rrc = build_rigid(desc, h, L);
   h->create_ms[2] = ms_since(t_rigid) - h->create_ms[3];
