@@ -154,7 +154,8 @@ int ld_score_batch_device(ld_handle *h, int64_t n_poses, const double *d_poses, 
  *
  * positions: [n_swarms][n_glowworms][ld_pose_len(h)] start poses (src/swarm.rs:26-64); seeds: [n_swarms].
  * One ld_gso per handle at a time; between ld_gso_create and ld_gso_destroy the handle's other scoring calls may be
- * used only while no ld_gso_run is executing (they share the handle's slot-0 work buffers and stream). */
+ * used only while no ld_gso_run is executing (they share the handle's slot-0 work buffers and stream).  Destroy the
+ * ld_gso before its handle. */
 typedef struct ld_gso ld_gso;
 #define LD_GSO_MAX_GLOWWORMS 1024
 int ld_gso_create(ld_handle *h, int32_t n_swarms, int32_t n_glowworms, const double *positions, const uint64_t *seeds,

@@ -220,3 +220,40 @@ def test_device_gso_interleaves_with_ordinary_scoring_calls():
     assert lib.ld_gso_state(gh, poses.ctypes.data, None, None, None, None, None) == 0
     lib.ld_gso_destroy(gh)
     assert np.array_equal(poses, ref["poses"])
+
+
+def test_multi_cli_with_device_gso(tmp_path):
+    """lightdock-rust-multi with LIGHTDOCK_GSO=device: three swarms of 1azp, 12 steps, against the same run with the host
+    loop -- same files, same discrete columns, poses / scores to print precision."""
+    from ldb200 import host
+    g = os.path.join(GOLDEN, "1azp")
+    multi_cli = os.path.join(os.path.dirname(host.CLI_PATH), "lightdock-rust-multi")
+    base = open(os.path.join(g, "initial_positions_0.dat")).read().splitlines()
+    rng = np.random.default_rng(3)
+    texts = {}
+    for k in (0, 3, 11):
+        rows = [[float(x) for x in l.split(" ")] for l in base]
+        if k:
+            for r in rows:
+                r[0] += rng.normal(0, 0.5); r[1] += rng.normal(0, 0.5); r[2] += rng.normal(0, 0.5)
+        texts[k] = "\n".join(" ".join(repr(v) for v in r) for r in rows) + "\n"
+    files = [f"init/initial_positions_{k}.dat" for k in texts]
+    for mode in ("host", "device"):
+        d = tmp_path / mode
+        os.makedirs(d / "init")
+        for f in ("rec_nm.npy", "lig_nm.npy"):
+            shutil.copy(os.path.join(g, f), d / f)
+        for k, text in texts.items():
+            (d / "init" / f"initial_positions_{k}.dat").write_text(text)
+        env = dict(os.environ)
+        if mode == "device":
+            env["LIGHTDOCK_GSO"] = "device"
+        r = subprocess.run([multi_cli, os.path.join(g, "setup.json"), "12", "dna"] + files, cwd=d, capture_output=True,
+                           text=True, timeout=600, env=env)
+        assert r.returncode == 0, r.stderr
+        assert "3 swarms, 12 steps" in r.stdout and "Done:" in r.stdout
+    for k in texts:
+        for step in (1, 10):
+            compare_gso_files(str(tmp_path / "device" / f"swarm_{k}" / f"gso_{step}.out"),
+                              str(tmp_path / "host" / f"swarm_{k}" / f"gso_{step}.out"))
+        assert sorted(os.listdir(tmp_path / "device" / f"swarm_{k}")) == ["gso_1.out", "gso_10.out"]
