@@ -202,6 +202,8 @@ static void bisect(std::vector<int> &idx, int lo, int hi, const double *xyz, int
 static void compact_tiles(std::vector<int> &idx, const double *xyz, int n, int tile) {
   const int K = (n + tile - 1) / tile;
   if (K < 2) return;
+  if ((size_t)n * (size_t)K > (size_t)40000000) return;  // the one full atom x tile search below is quadratic: beyond
+                                                          // ~18,000 atoms (seconds) the bisection order is kept
   std::vector<int> cap(K, tile), assign(n);
   cap[K - 1] = n - (K - 1) * tile;
   for (int i = 0; i < n; ++i) assign[idx[i]] = i / tile;
