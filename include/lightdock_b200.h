@@ -216,7 +216,9 @@ int ld_probe_peaks(int32_t device, double *fp64_nonfma_tflops, double *fp32_nonf
  * (0.5..8), "units_per_sm" rigid-kernel work units per SM, "default_path" LD_PATH_AUTO | LD_PATH_GENERIC, "flex" 0 keeps
  * ligands with ANM modes on the generic kernel, "cells_on_host" 1 builds the ligand-frame cell lists with host threads
  * (the cross-check of the device builder), "compact_tiles" 0 keeps the plain bisection order of the atoms (the tiles of 8 / 32
- * atoms are otherwise made more compact by a capacity-constrained k-means: fewer executed pair tests). */
+ * atoms are otherwise made more compact by a capacity-constrained k-means: fewer executed pair tests), "dna_fused" 0 sends
+ * DNA/pyDock poses through the separate transform kernel and per-pose coordinate blocks (the cross-check of the pair kernel's
+ * own pose transform). */
 int ld_set_option(const char *key, double value);
 
 /* Creates the CUDA context of `device` (cudaSetDevice + first runtime call).  Optional: ld_create does it too; a

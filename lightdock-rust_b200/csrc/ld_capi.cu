@@ -61,6 +61,7 @@ struct Options {
   int flex = 1;                   // 0: ligands with ANM modes stay on the generic kernel (no FLEX instance of the ligand-frame path)
   int cells_on_host = 0;          // 1: build the ligand-frame cell lists with host threads (the round-1 builder; cross-check)
   int compact_tiles = 1;          // 0: keep the plain bisection order of the atoms (tiles less compact; A/B aid)
+  int dna_fused = 1;              // 0: DNA/pyDock poses go through transform_kernel and per-pose coordinate blocks (cross-check)
 };
 Options g_opt;
 }  // namespace
@@ -74,6 +75,7 @@ extern "C" int ld_set_option(const char *key, double value) {
   else if (k == "cells_on_host") g_opt.cells_on_host = value != 0.0;
   else if (k == "flex") g_opt.flex = value != 0.0;
   else if (k == "compact_tiles") g_opt.compact_tiles = value != 0.0;
+  else if (k == "dna_fused") g_opt.dna_fused = value != 0.0;
   else if (k == "default_path") {
     if (value != LD_PATH_AUTO && value != LD_PATH_GENERIC) return fail(LD_EINVAL, "ld_set_option: default_path is AUTO or GENERIC");
     g_opt.default_path = (int)value;
@@ -147,6 +149,7 @@ struct ld_handle {
   float *d_tile_slack = nullptr;
   int *d_need = nullptr, *h_need = nullptr;  // running max of the tile displacements seen (float bits), device / pinned
   int max_smem_optin = 0;
+  bool dna_fused = false;               // DNA/pyDock: the pair kernel transforms its pose itself (option at ld_create time)
   int sm_count = 0;
   double create_ms[4] = {0, 0, 0, 0};   // ld_create: CUDA context, complex (sort + upload), rigid groups, cell lists
   bool profiling = false;
@@ -1017,6 +1020,7 @@ static int create_impl(const ld_complex_desc *desc, ld_handle *h) {
   CU(cudaFuncSetAttribute(dna_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   CU(cudaFuncSetAttribute(dna_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem_optin));
   h->path_mode = g_opt.default_path;
+  h->dna_fused = method != 0 && g_opt.dna_fused && h->cx.n_rec_modes + h->cx.n_lig_modes <= 64;
   h->create_ms[1] = ms_since(t_complex) + sort_ms;
   const auto t_rigid = std::chrono::steady_clock::now();
   const int rrc = build_rigid(desc, h, L);
@@ -1153,6 +1157,7 @@ static int64_t chunk_limit(const ld_handle *h, bool rigid) {
   if (rigid && h->flex)  // per-pose f32 ligand blocks, read once per receptor group: keep a chunk's worth L2-resident
     return std::max<int64_t>(256, std::min<int64_t>((int64_t)1 << 20, ((int64_t)64 << 20) / ((int64_t)h->cx.n_lig_pad * 16)));
   if (rigid) return (int64_t)1 << 20;  // no per-pose coordinate blocks on this path (~2 KB per pose)
+  if (h->dna_fused) return (int64_t)1 << 18;  // DNA/pyDock, pose transform inside the pair kernel: no coordinate blocks either
   const size_t per_pose = h->lig_block + h->rec_block + 64;
   int64_t c = (int64_t)((size_t)1 << 30) / (int64_t)per_pose;  // <= 1 GiB of coordinate blocks in flight
   return std::max<int64_t>(1, std::min<int64_t>(c, 16384));
@@ -1228,7 +1233,10 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
     const int splits = choose_splits(h, nc);
     int rc;
     const bool rigid = use_rigid(h);
-    if ((rc = ensure_chunk(h, nc, rigid ? 1 : splits, !rigid)) != LD_OK) return rc;
+    // DNA/pyDock: the pair kernel transforms its pose itself (pair_prologue, dna_pair_kernel): no transform kernel, no
+    // per-pose coordinate blocks
+    const bool dna_fused = !rigid && h->dna_fused;
+    if ((rc = ensure_chunk(h, nc, rigid ? 1 : splits, !rigid && !dna_fused)) != LD_OK) return rc;
     if (rigid) {
       const RigidComplex &rg = h->rc;
       BatchBuffers bb{};
@@ -1313,8 +1321,8 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
     h->w->stats.path = LD_PATH_GENERIC;
     BatchBuffers bb{};
     bb.poses = d_poses + (size_t)p0 * cx.pose_len;
-    bb.lig_blocks = h->w->d_lig_blocks;
-    bb.rec_blocks = h->w->d_rec_blocks;
+    bb.lig_blocks = dna_fused ? nullptr : h->w->d_lig_blocks;
+    bb.rec_blocks = dna_fused ? nullptr : h->w->d_rec_blocks;
     bb.partials = h->w->d_partials;
     bb.iface_rec = h->w->d_iface_rec;
     bb.iface_lig = h->w->d_iface_lig;
@@ -1327,9 +1335,11 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
     bb.n_live_off = (int)p0;
     h->w->stats.rec_splits = splits;
     if ((rc = prof_mark(h, st)) != LD_OK) return rc;
-    transform_kernel<<<(unsigned)((nc + TRANSFORM_PP - 1) / TRANSFORM_PP), 256,
-                       (size_t)TRANSFORM_PP * (cx.n_rec_modes + cx.n_lig_modes) * sizeof(double), st>>>(cx, bb, (int)nc);
-    ++launches;
+    if (!dna_fused) {
+      transform_kernel<<<(unsigned)((nc + TRANSFORM_PP - 1) / TRANSFORM_PP), 256,
+                         (size_t)TRANSFORM_PP * (cx.n_rec_modes + cx.n_lig_modes) * sizeof(double), st>>>(cx, bb, (int)nc);
+      ++launches;
+    }
     if ((rc = prof_mark(h, st)) != LD_OK) return rc;
     if (cx.n_rec_tiles > 0) {
       const size_t smem = pair_smem_bytes(cx.method, cx.n_lig_pad, cx.n_lig_tiles, lig_words, bb.tiles_per_split, cx.vdw_nr * cx.vdw_nl);

@@ -284,7 +284,9 @@ struct PairSmem {
   unsigned *rings;               // DFIRE: [warps][64]
   const unsigned char *vtab;     // DNA: (A, B) pairs, row = ligand type, column = receptor type
   const int *lig_vt;             // DNA: [n_lig_pad] byte offset of the atom's row in vtab
+  double *pose;                  // DNA: tx ty tz | q | q^-1 | receptor extents | ligand extents of the CTA's pose
 };
+__host__ __device__ inline size_t dna_pose_doubles(int n_rec_modes, int n_lig_modes) { return 11 + n_rec_modes + n_lig_modes; }
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 constexpr int RING = 64;
 __host__ __device__ inline size_t pair_smem_bytes(int method, int n_lig_pad, int n_lig_tiles, int lig_words,
@@ -299,7 +301,7 @@ __host__ __device__ inline size_t pair_smem_bytes(int method, int n_lig_pad, int
   o += align16((size_t)lig_words * 4);
   o += align16((size_t)tiles_per_split * 8 * (method == 0 ? 1 : 2));
   if (method == 0) o += (size_t)(PAIR_THREADS / 32) * RING * 4;  // work-item rings
-  else o += (size_t)vdw_pairs * 16 + align16((size_t)n_lig_pad * 4);
+  else o += (size_t)vdw_pairs * 16 + align16((size_t)n_lig_pad * 4) + 11 * 8 + 64 * 8;  // + pose scratch (<= 64 extents)
   return o;
 }
 __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceComplex &cx, const BatchBuffers &bb) {
@@ -311,6 +313,7 @@ __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceCompl
   unsigned char *o = base + 144;
   s.tma = o;
   s.l4 = nullptr; s.lxyzq = nullptr; s.lig_static = nullptr; s.rings = nullptr; s.vtab = nullptr; s.lig_vt = nullptr;
+  s.pose = nullptr;
   if (cx.method == 0) {
     s.l4 = reinterpret_cast<const float4 *>(o);
     o += (size_t)cx.n_lig_pad * 16;
@@ -336,6 +339,8 @@ __device__ __forceinline__ PairSmem carve(unsigned char *base, const DeviceCompl
     s.vtab = o;
     o += (size_t)cx.vdw_nr * cx.vdw_nl * 16;
     s.lig_vt = reinterpret_cast<const int *>(o);
+    o += align16((size_t)cx.n_lig_pad * 4);
+    s.pose = reinterpret_cast<double *>(o);
   }
   return s;
 }
@@ -369,7 +374,68 @@ __device__ __forceinline__ void pair_prologue(const DeviceComplex &cx, const Bat
     *s.next_tile = 0;
   }
   __syncthreads();
-  if (tid == 0) {
+  const bool fused = METHOD != 0 && bb.lig_blocks == nullptr;  // DNA/pyDock: the CTA transforms its pose's ligand itself
+  if (fused) {
+    // The pose transform of src/dna.rs:426-446 for this CTA's pose, straight into the staging area the pair loop reads
+    // -- the same operations in the same order as transform_kernel (rotate = q (0,v) q^-1 with the reference's term order,
+    // + translation, then mode k = 0, 1, ... each as multiply-then-add), so the coordinates are the same bits; what is saved
+    // is a kernel, 56 bytes per atom and pose of HBM writes and the read back.
+    const double *row = bb.poses + (size_t)pose * cx.pose_len;
+    const int n_ext = cx.n_rec_modes + cx.n_lig_modes;
+    if (tid == 0) {
+      const Quat q = {row[3], row[4], row[5], row[6]};
+      const double n2 = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(q.w, q.w), __dmul_rn(q.x, q.x)), __dmul_rn(q.y, q.y)),
+                                  __dmul_rn(q.z, q.z));
+      double *o = s.pose;
+      o[0] = row[0]; o[1] = row[1]; o[2] = row[2];
+      o[3] = q.w; o[4] = q.x; o[5] = q.y; o[6] = q.z;
+      o[7] = __ddiv_rn(q.w, n2); o[8] = __ddiv_rn(-q.x, n2); o[9] = __ddiv_rn(-q.y, n2); o[10] = __ddiv_rn(-q.z, n2);
+    }
+    for (int i = tid; i < n_ext; i += blockDim.x) s.pose[11 + i] = row[7 + i];
+    __syncthreads();
+    const double *o = s.pose;
+    const Quat q = {o[3], o[4], o[5], o[6]}, qi = {o[7], o[8], o[9], o[10]};
+    double2 *dst = reinterpret_cast<double2 *>(const_cast<double *>(s.lxyzq));
+    for (int i = tid; i < cx.n_lig_pad; i += blockDim.x) {
+      double x = LIG_PAD, y = LIG_PAD, z = LIG_PAD, lq = 0.0;  // pads: never within a cut-off, charge 0
+      if (i < cx.n_lig) {
+        const Quat v = {0.0, cx.lig_x[i], cx.lig_y[i], cx.lig_z[i]};
+        const Quat r = qmul(qmul(q, v), qi);
+        x = __dadd_rn(r.x, o[0]); y = __dadd_rn(r.y, o[1]); z = __dadd_rn(r.z, o[2]);
+        for (int k = 0; k < cx.n_lig_modes; ++k) {
+          const double *m = cx.lig_modes + (size_t)k * 3 * cx.n_lig_pad;
+          const double e = o[11 + cx.n_rec_modes + k];
+          x = __dadd_rn(x, __dmul_rn(m[i], e));
+          y = __dadd_rn(y, __dmul_rn(m[cx.n_lig_pad + i], e));
+          z = __dadd_rn(z, __dmul_rn(m[2 * cx.n_lig_pad + i], e));
+        }
+        lq = cx.lig_q[i];
+      }
+      dst[2 * i] = make_double2(x, y);
+      dst[2 * i + 1] = make_double2(z, lq);
+    }
+    __syncthreads();
+    float4 *sph = const_cast<float4 *>(s.lsph);
+    for (int t = tid; t < cx.n_lig_tiles; t += blockDim.x) {  // tile_sphere() on the interleaved layout
+      const int a = t * LIG_TILE, b = min(a + LIG_TILE, cx.n_lig);
+      double lo[3] = {dst[2 * a].x, dst[2 * a].y, dst[2 * a + 1].x}, hi[3] = {lo[0], lo[1], lo[2]};
+      for (int i = a + 1; i < b; ++i) {
+        const double c[3] = {dst[2 * i].x, dst[2 * i].y, dst[2 * i + 1].x};
+        for (int d = 0; d < 3; ++d) { lo[d] = c[d] < lo[d] ? c[d] : lo[d]; hi[d] = c[d] > hi[d] ? c[d] : hi[d]; }
+      }
+      float4 sp;
+      sp.x = (float)(0.5 * (lo[0] + hi[0])); sp.y = (float)(0.5 * (lo[1] + hi[1])); sp.z = (float)(0.5 * (lo[2] + hi[2]));
+      double r2 = 0.0;
+      for (int i = a; i < b; ++i) {
+        const double dx = dst[2 * i].x - (double)sp.x, dy = dst[2 * i].y - (double)sp.y, dz = dst[2 * i + 1].x - (double)sp.z;
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        r2 = d2 > r2 ? d2 : r2;
+      }
+      sp.w = (float)(sqrt(r2) * 1.000001 + 1.0e-6);
+      sph[t] = sp;
+    }
+  }
+  if (!fused && tid == 0) {
     const unsigned char *lb = bb.lig_blocks + (size_t)pose * lig_block_bytes(cx.n_lig_pad, cx.n_lig_tiles, cx.method);
     // xyzt (DFIRE) or xyzq (DNA) | spheres | meta are contiguous: one bulk copy
     const uint32_t bytes = (uint32_t)cx.n_lig_pad * (uint32_t)lig_wide(METHOD) + (uint32_t)(cx.n_lig_tiles * 16 + 16);
@@ -393,7 +459,7 @@ __device__ __forceinline__ void pair_prologue(const DeviceComplex &cx, const Bat
   if (tid < 4) s.counters[tid] = 0ull;
   if (tid < 24) s.hist[tid] = 0u;
   __syncthreads();
-  mbar_wait(s.bar, 0);
+  if (!fused) mbar_wait(s.bar, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -894,7 +960,8 @@ __global__ void __launch_bounds__(DNA_THREADS, DNA_CTAS_PER_SM)
   const int lane = threadIdx.x & 31;
   const double *gx = cx.rec_x, *gy = cx.rec_y, *gz = cx.rec_z;
   const float4 *gsph = cx.rec_sphere;
-  if (cx.n_rec_modes > 0) {
+  const bool rec_anm_here = cx.n_rec_modes > 0 && bb.rec_blocks == nullptr;  // fused: the warp deforms its own tile
+  if (cx.n_rec_modes > 0 && !rec_anm_here) {
     const unsigned char *rb = bb.rec_blocks + (size_t)pose * rec_block_bytes(cx.n_rec_pad, cx.n_rec_tiles);
     gx = reinterpret_cast<const double *>(rb); gy = gx + cx.n_rec_pad; gz = gy + cx.n_rec_pad;
     gsph = reinterpret_cast<const float4 *>(gz + cx.n_rec_pad);
@@ -908,9 +975,41 @@ __global__ void __launch_bounds__(DNA_THREADS, DNA_CTAS_PER_SM)
     if (t >= t1) break;
     const int ia = t * REC_TILE + lane;
     DnaLane r = {gx[ia], gy[ia], gz[ia], cx.rec_q[ia], cx.rec_seps[ia], cx.rec_rad[ia], 0, TAB ? cx.rec_vt[ia] : 0};
+    float4 rs_here = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rec_anm_here) {
+      // receptor ANM (src/dna.rs:448-464) for the 32 atoms of this tile, k ascending, multiply-then-add: the same bits
+      // as transform_kernel writes; then tile_sphere() of the deformed tile by warp reductions (pads excluded)
+      const bool real = ia < cx.n_rec;
+      if (real)
+        for (int k = 0; k < cx.n_rec_modes; ++k) {
+          const double *m = cx.rec_modes + (size_t)k * 3 * cx.n_rec_pad;
+          const double e = s.pose[11 + k];
+          r.x = __dadd_rn(r.x, __dmul_rn(m[ia], e));
+          r.y = __dadd_rn(r.y, __dmul_rn(m[cx.n_rec_pad + ia], e));
+          r.z = __dadd_rn(r.z, __dmul_rn(m[2 * cx.n_rec_pad + ia], e));
+        }
+      double lo[3] = {real ? r.x : 1.0e300, real ? r.y : 1.0e300, real ? r.z : 1.0e300};
+      double hi[3] = {real ? r.x : -1.0e300, real ? r.y : -1.0e300, real ? r.z : -1.0e300};
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+          hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+      rs_here.x = (float)(0.5 * (lo[0] + hi[0])); rs_here.y = (float)(0.5 * (lo[1] + hi[1])); rs_here.z = (float)(0.5 * (lo[2] + hi[2]));
+      double d2 = 0.0;
+      if (real) {
+        const double dx = r.x - (double)rs_here.x, dy = r.y - (double)rs_here.y, dz = r.z - (double)rs_here.z;
+        d2 = dx * dx + dy * dy + dz * dz;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) d2 = fmax(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+      rs_here.w = (float)(sqrt(d2) * 1.000001 + 1.0e-6);
+    }
     // ELEC_MAX_CUTOFF / |q_r| (src/dna.rs:21); q_r == 0 gives +inf: no clamp, and every term is 0 * q_l/d2 = 0
     r.clamp_bits = __double_as_longlong(__ddiv_rn(1.0 * 4.0 / 332.0, fabs(r.q)));
-    const float4 rs = gsph[t];
+    const float4 rs = rec_anm_here ? rs_here : gsph[t];
     DnaAcc acc = {0.0, 0.0, 0.0, 0.0, 0u, 0u, 0u, false};
     unsigned n_tested = 0;
 

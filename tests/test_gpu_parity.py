@@ -312,3 +312,34 @@ def test_dna_many_vdw_types_takes_the_per_atom_form():
     e_ref, d_ref = cx2.energy(poses, detail=True)
     assert_parity(e_gpu, d_gpu, e_ref, d_ref, O.DNA)
     assert np.array_equal(sc.energy(poses), e_gpu)
+
+
+@pytest.mark.parametrize("method", [O.DNA, O.PYDOCK])
+def test_dna_fused_transform_equals_the_transform_kernel(method):
+    """DNA/pyDock: the pair kernel transforms its pose itself (ligand in the prologue, receptor ANM per tile); with
+    ld_set_option("dna_fused", 0) the poses go through transform_kernel and per-pose coordinate blocks instead.  Same
+    operations in the same order: every output identical, energies BIT FOR BIT -- large batch, one swarm (receptor
+    splits) and single poses."""
+    import ldb200
+    cx, pos, _ = case("1azp", method)
+    rng = np.random.default_rng(23)
+    poses = np.tile(pos, (6, 1))
+    poses[:, :3] += rng.normal(0, 1.5, size=(len(poses), 3))
+    poses[:, 7:] *= rng.uniform(0.5, 1.5, size=(len(poses), 1))
+    fused = scorer_from_oracle(cx)
+    ldb200.set_option("dna_fused", 0)
+    try:
+        plain = scorer_from_oracle(cx)  # the option is read by ld_create
+    finally:
+        ldb200.set_option("dna_fused", 1)
+    e_p, d_p = plain.energy_detail(poses)
+    e_p200 = plain.energy(poses[:200])
+    e_f, d_f = fused.energy_detail(poses)
+    for k in d_f:
+        np.testing.assert_array_equal(d_f[k], d_p[k], err_msg=k)
+    assert np.array_equal(e_f, e_p)
+    assert np.array_equal(fused.energy(poses), e_f)
+    assert np.array_equal(plain.energy(poses), e_p)
+    assert plain.stats()["kernel_launches"] == 3 and fused.stats()["kernel_launches"] == 2
+    assert np.array_equal(fused.energy(poses[:200]), e_p200)
+    assert np.array_equal(np.array([fused.energy(poses[i:i + 1])[0] for i in range(8)]), e_f[:8])
