@@ -150,6 +150,9 @@ struct ld_handle {
   int *d_need = nullptr, *h_need = nullptr;  // running max of the tile displacements seen (float bits), device / pinned
   int max_smem_optin = 0;
   bool dna_fused = false;               // DNA/pyDock: the pair kernel transforms its pose itself (option at ld_create time)
+  unsigned char *gso_slab = nullptr;    // device memory of the handle's ld_gso, kept across ld_gso_create/_destroy (an
+  size_t gso_slab_bytes = 0;            // allocation per optimisation run costs up to 100+ ms now and then)
+  bool gso_live = false;                // an ld_gso exists on this handle
   int sm_count = 0;
   double create_ms[4] = {0, 0, 0, 0};   // ld_create: CUDA context, complex (sort + upload), rigid groups, cell lists
   bool profiling = false;
@@ -437,6 +440,7 @@ extern "C" int ld_destroy(ld_handle *h) {
     if (w.stream) cudaStreamDestroy(w.stream);
   }
   for (void *p : h->owned) cudaFree(p);
+  cudaFree(h->gso_slab);
   cudaFree(h->d_rc);
   cudaFree(h->d_cells); cudaFree(h->d_cell_tiles); cudaFree(h->d_tile_slack); cudaFree(h->d_need);
   cudaFreeHost(h->h_need);
@@ -1549,7 +1553,7 @@ struct ld_gso {
   int cap_steps = 0;           // entries of st.n_packed
   int64_t energy_calls = 0;
   std::vector<void *> owned;
-  int *h_counts = nullptr;     // pinned: n_packed of the steps of one ld_gso_run call
+  std::vector<int> h_counts;   // n_packed of the steps of one ld_gso_run call
 };
 
 extern "C" int ld_gso_destroy(ld_gso *g) {
@@ -1557,7 +1561,7 @@ extern "C" int ld_gso_destroy(ld_gso *g) {
   cudaSetDevice(g->h->device);
   if (g->h->ws[0].stream) cudaStreamSynchronize(g->h->ws[0].stream);
   for (void *p : g->owned) cudaFree(p);
-  cudaFreeHost(g->h_counts);
+  g->h->gso_live = false;  // the slab stays with the handle for its next ld_gso
   delete g;
   return LD_OK;
 }
@@ -1577,16 +1581,21 @@ static int gso_create_impl(ld_gso *g, const double *positions, const uint64_t *s
                o_vis = reserve(G * 8), o_sc = reserve(G * 8), o_en = reserve(G * 8), o_nn = reserve(G * 4), o_slot = reserve(G * 4),
                o_np = reserve((size_t)g->cap_steps * 4), o_failed = reserve((size_t)st.n_swarms * 4),
                o_keys = reserve((size_t)st.n_swarms * 32);
-  unsigned char *slab = nullptr;
-  CU(cudaMalloc(reinterpret_cast<void **>(&slab), total));
-  g->owned.push_back(slab);
+  ld_handle *h = g->h;
+  if (total > h->gso_slab_bytes) {
+    cudaFree(h->gso_slab);
+    h->gso_slab = nullptr;
+    h->gso_slab_bytes = 0;
+    CU(cudaMalloc(reinterpret_cast<void **>(&h->gso_slab), total));
+    h->gso_slab_bytes = total;
+  }
+  unsigned char *slab = h->gso_slab;
   p0 = reinterpret_cast<double *>(slab + o_p0); p1 = reinterpret_cast<double *>(slab + o_p1);
   packed = reinterpret_cast<double *>(slab + o_packed); lum = reinterpret_cast<double *>(slab + o_lum);
   vis = reinterpret_cast<double *>(slab + o_vis); sc = reinterpret_cast<double *>(slab + o_sc);
   en = reinterpret_cast<double *>(slab + o_en); nn = reinterpret_cast<int *>(slab + o_nn);
   slot = reinterpret_cast<int *>(slab + o_slot); np = reinterpret_cast<int *>(slab + o_np);
   failed = reinterpret_cast<int *>(slab + o_failed); keys = reinterpret_cast<uint32_t *>(slab + o_keys);
-  CU(cudaHostAlloc(reinterpret_cast<void **>(&g->h_counts), (size_t)g->cap_steps * sizeof(int), cudaHostAllocDefault));
   st.poses[0] = p0; st.poses[1] = p1; st.luciferin = lum; st.vision = vis; st.scoring = sc; st.packed = packed;
   st.energies = en; st.n_neighbors = nn; st.slot = slot; st.n_packed = np; st.failed = failed; st.keys = keys;
   // Glowworm::new (src/glowworm.rs:29-59): luciferin 5, vision range 0.2, scoring 0, no neighbours; step 0 = every
@@ -1630,6 +1639,7 @@ extern "C" int ld_gso_create(ld_handle *h, int32_t n_swarms, int32_t n_glowworms
     return fail(LD_ELIMIT, "ld_gso_create: more than LD_GSO_MAX_GLOWWORMS glowworms per swarm");
   if ((int64_t)n_swarms * n_glowworms > (int64_t)1 << 30) return fail(LD_ELIMIT, "ld_gso_create: too many glowworms");
   if (h->ws[0].pending >= 0) return fail(LD_EINVAL, "ld_gso_create: slot 0 has a batch pending");
+  if (h->gso_live) return fail(LD_EINVAL, "ld_gso_create: the handle already has an ld_gso (one at a time)");
   CU(cudaSetDevice(h->device));
   ld_gso *g = new ld_gso();
   g->h = h;
@@ -1638,6 +1648,7 @@ extern "C" int ld_gso_create(ld_handle *h, int32_t n_swarms, int32_t n_glowworms
   g->st.pose_len = h->cx.pose_len;
   g->st.n_rec_ext = h->cx.n_rec_modes;
   g->st.n_lig_ext = h->cx.n_lig_modes;
+  h->gso_live = true;
   const int rc = gso_create_impl(g, positions, seeds);
   if (rc != LD_OK) {
     const std::string keep = g_err;
@@ -1674,7 +1685,8 @@ extern "C" int ld_gso_run(ld_gso *g, int32_t n_steps) {
     g->cur ^= 1;
     g->step = step;
   }
-  CU(cudaMemcpyAsync(g->h_counts, st.n_packed + first, (size_t)n_steps * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  g->h_counts.resize((size_t)n_steps);  // pageable on purpose: no pinned allocation per ld_gso (they cost up to 100 ms now and then)
+  CU(cudaMemcpyAsync(g->h_counts.data(), st.n_packed + first, (size_t)n_steps * sizeof(int), cudaMemcpyDeviceToHost, stream));
   const bool flex = h->flex && use_rigid(h);
   if (flex) CU(cudaMemcpyAsync(h->h_need, h->d_need, (size_t)h->cx.n_lig_tiles * sizeof(int), cudaMemcpyDeviceToHost, stream));
   CU(cudaStreamSynchronize(stream));

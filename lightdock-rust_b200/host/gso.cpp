@@ -538,9 +538,30 @@ struct GsoGuard {  // ld_gso_destroy on every exit path
 };
 }  // namespace
 
+// One swarm of a flat state as Swarm objects (neighbour lists hold the right COUNT of placeholder ids: the count is
+// what Swarm::save prints)
+template <typename P>
+static Swarm swarm_of(const DeviceGSO::State &b, size_t s, const P &p, const Score *scoring) {
+  const size_t n = b.n_glowworms, pl = b.pose_len;
+  Swarm sw;
+  std::vector<std::vector<double>> pos(n);
+  for (size_t i = 0; i < n; ++i) pos[i].assign(b.poses.begin() + (s * n + i) * pl, b.poses.begin() + (s * n + i + 1) * pl);
+  sw.add_glowworms(pos, scoring, p.use_anm, p.rec_num_anm, p.lig_num_anm);
+  for (size_t i = 0; i < n; ++i) {
+    Glowworm &g = sw.glowworms[i];
+    g.luciferin = b.luciferin[s * n + i];
+    g.vision_range = b.vision[s * n + i];
+    g.scoring = b.scoring[s * n + i];
+    g.neighbors.assign((size_t)b.n_neighbors[s * n + i], 0u);
+  }
+  return sw;
+}
+
+Swarm DeviceGSO::swarm(size_t s) const { return swarm_of(state, s, pending_.at(s), scoring); }
+
 void DeviceGSO::run(uint32_t steps, int host_threads) {
   const size_t S = pending_.size();
-  swarms.clear();
+  state = State{};
   failures_.clear();
   energy_calls_ = 0;
   if (S == 0) return;
@@ -569,29 +590,15 @@ void DeviceGSO::run(uint32_t steps, int host_threads) {
     throw std::runtime_error(std::string("ld_gso_create: ") + ld_last_error());
 
   // swarm state on the host, double-buffered: one copy is being written to disk while the next is fetched
-  struct Snapshot {
-    std::vector<double> poses, luciferin, vision, scoring;
-    std::vector<int32_t> n_neighbors, failed;
-  } snap[2];
-  for (Snapshot &b : snap) {
+  State snap[2];
+  for (State &b : snap) {
+    b.n_swarms = S; b.n_glowworms = n; b.pose_len = pl;
     b.poses.resize(S * n * pl); b.luciferin.resize(S * n); b.vision.resize(S * n); b.scoring.resize(S * n);
     b.n_neighbors.resize(S * n); b.failed.resize(S);
   }
-  auto materialise = [&](const Snapshot &b, size_t s) {
-    const Pending &p = pending_[s];
-    Swarm sw;
-    std::vector<std::vector<double>> pos(n);
-    for (size_t i = 0; i < n; ++i) pos[i].assign(b.poses.begin() + (s * n + i) * pl, b.poses.begin() + (s * n + i + 1) * pl);
-    sw.add_glowworms(pos, scoring, p.use_anm, p.rec_num_anm, p.lig_num_anm);
-    for (size_t i = 0; i < n; ++i) {
-      Glowworm &g = sw.glowworms[i];
-      g.luciferin = b.luciferin[s * n + i];
-      g.vision_range = b.vision[s * n + i];
-      g.scoring = b.scoring[s * n + i];
-      g.neighbors.assign((size_t)b.n_neighbors[s * n + i], 0u);  // the count is what Swarm::save prints
-    }
-    return sw;
-  };
+  auto materialise = [&](const State &b, size_t s) { return swarm_of(b, s, pending_[s], scoring); };
+  bool any_output = false;
+  for (const Pending &p : pending_) any_output = any_output || !p.output_directory.empty();
   std::vector<std::string> save_error(S);
   std::vector<int32_t> failed_at(S, 0);
   std::thread writer;
@@ -611,16 +618,16 @@ void DeviceGSO::run(uint32_t steps, int host_threads) {
     }
     done = next;
     const bool save_step = done % 10 == 0 || done == 1;
-    if (!save_step && done < steps) continue;
+    if ((!save_step || !any_output) && done < steps) continue;  // nothing to write: the state is fetched at the end only
     join_writer();  // the previous snapshot's files are on disk; its buffer is two saves old after the flip
-    Snapshot &b = snap[which];
+    State &b = snap[which];
     which ^= 1;
     if (ld_gso_state(guard.g, b.poses.data(), b.luciferin.data(), b.vision.data(), b.scoring.data(), b.n_neighbors.data(),
                      b.failed.data()) != LD_OK)
       throw std::runtime_error(std::string("ld_gso_state: ") + ld_last_error());
     for (size_t s = 0; s < S; ++s)
       if (b.failed[s] && !failed_at[s]) failed_at[s] = b.failed[s];
-    if (!save_step) break;
+    if (!save_step || !any_output) break;  // (only reached at the last step)
     const uint32_t step = done;
     writer = std::thread([&, step, nt, bp = &b] {
       NvtxRange r("save (overlaps the next device steps)");
@@ -646,9 +653,7 @@ void DeviceGSO::run(uint32_t steps, int host_threads) {
       throw std::runtime_error(std::string("ld_gso_state: ") + ld_last_error());
     which = 1;
   }
-  const Snapshot &last = snap[which ^ 1];
-  swarms.reserve(S);
-  for (size_t s = 0; s < S; ++s) swarms.push_back(materialise(last, s));
+  state = std::move(snap[which ^ 1]);
   energy_calls_ = (uint64_t)ld_gso_energy_calls(guard.g);
   for (size_t s = 0; s < S; ++s) {
     if (failed_at[s])  // src/glowworm.rs:114-126: the reference indexes past its probabilities and panics

@@ -119,7 +119,13 @@ struct MultiGSO {
 // in the drivers) and the byte-identical host loop stays the default.  All swarms must have the same glowworm count.
 struct DeviceGSO {
   const Score *scoring;
-  std::vector<Swarm> swarms;  // state after run(): poses, luciferin, scoring, vision range, neighbour COUNT per glowworm
+  // state after run(), flat, [swarm][glowworm]: pose rows (pose_len each), luciferin, vision range, scoring, neighbour COUNT
+  struct State {
+    size_t n_swarms = 0, n_glowworms = 0, pose_len = 0;
+    std::vector<double> poses, luciferin, vision, scoring;
+    std::vector<int32_t> n_neighbors, failed;
+  } state;
+  Swarm swarm(size_t s) const;  // swarm s of `state` as a Swarm (what Swarm::save prints)
   explicit DeviceGSO(const Score *s);  // throws unless `s` scores on the GPU (CudaScore)
   void add(const std::vector<std::vector<double>> &positions, uint64_t seed, bool use_anm, size_t rec_num_anm,
            size_t lig_num_anm, std::string output_directory);

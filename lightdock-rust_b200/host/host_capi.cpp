@@ -200,14 +200,14 @@ int ldh_case_device_gso(ldh_case *c, int n_swarms, int n_glowworms, const double
   multi.run(steps, host_threads);
   if (energy_calls) *energy_calls = multi.energy_calls();
   const auto failures = multi.failures();
-  if (final_state)
-    for (int w = 0; w < n_swarms; ++w)
-      for (int i = 0; i < n_glowworms; ++i) {
-        const Glowworm &g = multi.swarms[w].glowworms[i];
-        double *r = final_state + ((size_t)w * n_glowworms + i) * (4 + pl);
-        r[0] = g.luciferin; r[1] = g.scoring; r[2] = (double)g.neighbors.size(); r[3] = g.vision_range;
-        g.write_pose(r + 4);
-      }
+  if (final_state) {
+    const DeviceGSO::State &st = multi.state;
+    for (size_t k = 0; k < (size_t)n_swarms * n_glowworms; ++k) {
+      double *r = final_state + k * (4 + pl);
+      r[0] = st.luciferin[k]; r[1] = st.scoring[k]; r[2] = (double)st.n_neighbors[k]; r[3] = st.vision[k];
+      std::copy(st.poses.begin() + k * pl, st.poses.begin() + (k + 1) * pl, r + 4);
+    }
+  }
   if (!failures.empty()) {
     std::string msg = std::to_string(failures.size()) + " swarm(s) stopped early:";
     for (const auto &f : failures) msg += " [" + std::to_string(f.first) + "] " + f.second + ";";
