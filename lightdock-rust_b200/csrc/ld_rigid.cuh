@@ -95,6 +95,13 @@ extern __shared__ __align__(128) unsigned char smem_rigid[];
 __device__ __forceinline__ double lds_f64(uint32_t off) { return *reinterpret_cast<const double *>(smem_rigid + off); }
 __device__ __forceinline__ long long lds_i64(uint32_t off) { return *reinterpret_cast<const long long *>(smem_rigid + off); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16-byte asynchronous global -> shared copy (LDGSTS) to a byte offset of the kernel's dynamic shared memory
+__device__ __forceinline__ void cp_async16(uint32_t smem_off, const void *gmem) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_rigid + smem_off);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Per-pose quantities shared by the 100+ (group, pose) work items of a pose, computed once per batch:
 //   prep[0..8]  M = R^T (row major), R the rotation of q: q v q^-1 is a rotation for any q != 0 (src/qt.rs:57-61)
@@ -428,12 +435,26 @@ __device__ __forceinline__ void rg_score_group(const RigidComplex &rc, const Bat
     double ax = rc.rec_x[pos_base + lane], ay = rc.rec_y[pos_base + lane], az = rc.rec_z[pos_base + lane];
     if (rc.n_rec_modes > 0) {  // src/dfire.rs:304-320 (lab frame)
       const double *pose = bb.poses + (size_t)p * rc.pose_len;
-      for (int k = 0; k < rc.n_rec_modes; ++k) {
-        const double e = pose[7 + k];
-        const double *m = rc.rec_modes + (size_t)k * 3 * rc.n_rec_pos + pos_base + lane;
-        ax = __dadd_rn(ax, __dmul_rn(m[0], e));
-        ay = __dadd_rn(ay, __dmul_rn(m[rc.n_rec_pos], e));
-        az = __dadd_rn(az, __dmul_rn(m[2 * rc.n_rec_pos], e));
+      if (FLEX) {
+        // a FLEX task is latency bound (ncu: long_scoreboard 2.5 per issued instruction): keep the loads of five modes
+        // in flight; the additions stay in k order.  Only in this instantiation: the same pragma in the rigid one
+        // changes nothing it executes on 1k4c / 1ppe (no receptor modes) and still costs it 2.4 % (code generation).
+#pragma unroll 5
+        for (int k = 0; k < rc.n_rec_modes; ++k) {
+          const double e = pose[7 + k];
+          const double *m = rc.rec_modes + (size_t)k * 3 * rc.n_rec_pos + pos_base + lane;
+          ax = __dadd_rn(ax, __dmul_rn(m[0], e));
+          ay = __dadd_rn(ay, __dmul_rn(m[rc.n_rec_pos], e));
+          az = __dadd_rn(az, __dmul_rn(m[2 * rc.n_rec_pos], e));
+        }
+      } else {
+        for (int k = 0; k < rc.n_rec_modes; ++k) {
+          const double e = pose[7 + k];
+          const double *m = rc.rec_modes + (size_t)k * 3 * rc.n_rec_pos + pos_base + lane;
+          ax = __dadd_rn(ax, __dmul_rn(m[0], e));
+          ay = __dadd_rn(ay, __dmul_rn(m[rc.n_rec_pos], e));
+          az = __dadd_rn(az, __dmul_rn(m[2 * rc.n_rec_pos], e));
+        }
       }
     }
     fx = (float)(fma(prep[0], ax, fma(prep[1], ay, fma(prep[2], az, -prep[9]))));
@@ -514,6 +535,10 @@ __device__ __forceinline__ void rg_score_group(const RigidComplex &rc, const Bat
     return false;
   };
   bool have = produce();
+  if (FLEX) {  // the pose's ligand block (cp.async copies issued by the caller) has to be in this warp's slice now
+    cp_async_wait_all();
+    __syncwarp();
+  }
   while (have) {
     act = act_nxt; o = o_nxt; lt = lt_nxt;
     have = produce();
@@ -606,8 +631,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
       float thr_out = rc.thr_out, hme = rc.half_minus_eps, delta102 = rc.delta, reach_abs = 3.0e38f;
       if (FLEX) {
         // this pose's ligand block (ligand frame, f32) into the warp's slice of shared memory
+        // asynchronous copies (LDGSTS: no registers, all in flight at once), waited for right before the first row, so
+        // they land while the warp moves its receptor atoms into the pose's frame and looks their cells up
         const float4 *src = lig4p + (size_t)p * rc.n_lig_pad;
-        for (int i = lane; i < rc.n_lig_pad; i += 32) l4[i] = __ldg(src + i);
+        for (int i = lane; i < rc.n_lig_pad; i += 32) cp_async16(l4_addr + (uint32_t)i * 16u, src + i);
+        cp_async_commit();
         const float dmax = pose_flag[p];
         brute = dmax != 0.f;
         if (brute) {
@@ -620,7 +648,6 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
           delta102 = 1.02f * d;
           hme = d < 0.01f ? rc.half_minus_eps : -1.0f;
         }
-        __syncwarp();
       }
       acc_t acc0 = 0, acc1 = 0;
       unsigned ifr_mask = 0u;
