@@ -754,6 +754,10 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   for (int r = 0; r < R.n_restraints; ++r)
     for (int k = R.rst_offsets[r]; k < R.rst_offsets[r + 1]; ++k) rst_idx.push_back(inv[R.rst_atoms[k]]);
   for (int k = 0; k < R.n_membrane; ++k) mem_idx.push_back(inv[R.membrane[k]]);
+  // the receptor positions whose interface flag finalize_kernel reads (active restraints, membrane beads)
+  std::vector<unsigned> gneed(ng, 0u);
+  for (int pos : rst_idx) gneed[pos >> 5] |= 1u << (pos & 31);
+  for (int pos : mem_idx) gneed[pos >> 5] |= 1u << (pos & 31);
 
   // ligand, local frame, f32 + column offset
   std::vector<float4> l4(cx.n_lig_pad);
@@ -772,8 +776,9 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   if ((rcode = upload(h, vec, &rc.field)) != LD_OK) return rcode
   UPR(x, rec_x); UPR(y, rec_y); UPR(z, rec_z); UPR(slot, rec_slot); UPR(toff, rec_toff);
   UPR(gtypes, group_types); UPR(order, group_order); UPR(modes, rec_modes);
-  UPR(l4, lig4);
+  UPR(l4, lig4); UPR(gneed, group_need);
 #undef UPR
+  rc.lig_need = desc->ligand.n_restraints > 0 ? 1 : 0;
   rc.n_groups = ng; rc.n_rec_pos = npos;
   rc.n_lig = cx.n_lig; rc.n_lig_pad = cx.n_lig_pad; rc.n_lig_tiles = cx.n_lig_tiles;
   rc.n_rec_modes = nrm; rc.pose_len = cx.pose_len; rc.rows_max = rows_max;

@@ -82,6 +82,11 @@ struct RigidComplex {
   double fx_scale;                      // 2^k
   const float *tile_slack;              // [n_lig_tiles] slack the current lists were built with
   float grid_maxabs;                    // largest |coordinate| inside the cell grid (the M of the FP32 error bound)
+  // Who reads the interface flags (src/dfire.rs:339-342): finalize_kernel looks at the receptor atoms of the ACTIVE
+  // restraints and the membrane beads, and at the ligand atoms of the active ligand restraints (src/dfire.rs:351-357,
+  // src/scoring.rs:21-47); nothing else of the flag arrays can reach the energy.
+  const unsigned *group_need;           // [n_groups] lanes whose receptor atom is in an active restraint or a bead
+  int lig_need;                         // the ligand has active restraints: every contact's ligand flag matters
 };
 
 // ligand copies: 1 (rigid: shared by the CTA) or one per warp (FLEX: each warp works on its own pose)
@@ -90,6 +95,7 @@ __host__ __device__ inline size_t rigid_smem_bytes(int n_lig_pad, int rows, int 
 }
 
 extern __shared__ __align__(128) unsigned char smem_rigid[];
+constexpr uint32_t RG_NEED_OFF = 16;  // header: mbarrier (8 B), unit, next pose, then the current group's interface-need mask
 // Loads at byte offsets of the kernel's dynamic shared memory (plain C++ so the scheduler may interleave the
 // eight pairs of an item; the array is known to live in shared memory, so these are LDS with 32-bit addresses).
 __device__ __forceinline__ double lds_f64(uint32_t off) { return *reinterpret_cast<const double *>(smem_rigid + off); }
@@ -355,7 +361,9 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
       }
     }
   }
-  if (mind2 <= 6.0025f + delta) {  // rare: a contact near or below the 2.45 A interface edge (src/dfire.rs:339-342)
+  // rare: a contact near or below the 2.45 A interface edge (src/dfire.rs:339-342) -- looked at only where a flag it
+  // could set is read by someone (RG_NEED_OFF: the group's mask of such lanes; all ones with DETAIL or ligand restraints)
+  if (mind2 <= 6.0025f + delta && (FLEX || ((*reinterpret_cast<const unsigned *>(smem_rigid + RG_NEED_OFF) >> o) & 1u))) {
     const double *pose = bb.poses + (size_t)p * rc_dev->pose_len;
     for (int k = 0; k < LIG_TILE; ++k) {
       if ((slow_bits >> k) & 1u) continue;  // the exact path below owns this pair entirely
@@ -583,8 +591,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
   for (;;) {
     __syncthreads();  // every warp is done with the previous unit: rows and counters may be rewritten
     if (threadIdx.x == 0) {
-      *s_unit = (int)atomicAdd(unit_counter, 1u);
+      const unsigned un = atomicAdd(unit_counter, 1u);
+      *s_unit = (int)un;
       *s_pose_next = 0;
+      *reinterpret_cast<unsigned *>(smem_raw + RG_NEED_OFF) =
+          (DETAIL || rc.lig_need || un >= (unsigned)n_units) ? 0xffffffffu : rc.group_need[rc.group_order[un / (unsigned)n_chunks]];
     }
     __syncthreads();
     const int u = *s_unit;
