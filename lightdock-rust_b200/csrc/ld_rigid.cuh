@@ -300,13 +300,32 @@ __device__ __noinline__ int rigid_exact_pair(const RigidComplex *__restrict__ rc
 // the hot loop: a per-item min(d2f) sends the rare items with a contact below 2.45 A + to a second pass
 // that decides it in FP32 outside 6.0025 +- delta and with rigid_exact_pair inside.
 __device__ __forceinline__ float4 lds_f4(uint32_t off) { return *reinterpret_cast<const float4 *>(smem_rigid + off); }
+// The hot loop's loads take ABSOLUTE shared-window addresses (base of smem_rigid folded into the per-lane tile / row
+// address once): with `smem_rigid + off` the compiler adds the window base to every address (one IADD per LDS, two
+// LDS per pair).  Deliberately not volatile and without a memory clobber, so that the eight pairs of an item are
+// still interleaved freely; what orders them after the copies that fill the memory they read is rg_after_copy() on
+// the address they are computed from.
+__device__ __forceinline__ uint32_t rg_smem_base() { return (uint32_t)__cvta_generic_to_shared(smem_rigid); }
+__device__ __forceinline__ float4 lds_f4_abs(uint32_t a) {
+  float4 v;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_f64_abs(uint32_t a) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+// an address "produced" after the wait that made the data behind it visible: no load computed from it can be moved
+// above that wait by the compiler
+__device__ __forceinline__ void rg_after_copy(uint32_t &addr) { asm volatile("" : "+r"(addr) : : "memory"); }
 
 // Accumulator of the table values: f64 (rigid ligand: lists are static, so the order of a pose's additions is a
 // function of the pose alone) or 64-bit fixed point (FLEX: exact whatever the order).
 template <bool FLEX> struct RgAcc { typedef double type; };
 template <> struct RgAcc<true> { typedef long long type; };
-__device__ __forceinline__ void rg_add(double &acc, uint32_t addr) { acc = __dadd_rn(acc, lds_f64(addr)); }
-__device__ __forceinline__ void rg_add(long long &acc, uint32_t addr) { acc += lds_i64(addr); }
+__device__ __forceinline__ void rg_add(double &acc, uint32_t addr) { acc = __dadd_rn(acc, lds_f64_abs(addr)); }
+__device__ __forceinline__ void rg_add(long long &acc, uint32_t addr) { acc += lds_i64(addr); }  // FLEX: relative
 __device__ __forceinline__ double rg_join(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ long long rg_join(long long a, long long b) { return a + b; }
 __device__ __forceinline__ void rg_add_exact(double &acc, double v, double) { acc = __dadd_rn(acc, v); }
@@ -335,7 +354,7 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
   float mind2 = 3.0e38f;
 #pragma unroll
   for (int k = 0; k < LIG_TILE; ++k) {
-    const float4 a = lds_f4(tile_addr ^ (uint32_t)(k << 4));
+    const float4 a = FLEX ? lds_f4(tile_addr ^ (uint32_t)(k << 4)) : lds_f4_abs(tile_addr ^ (uint32_t)(k << 4));
     const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
     const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
     mind2 = fminf(mind2, d2);
@@ -367,7 +386,9 @@ __device__ __forceinline__ void rigid_row(const RigidComplex &rc, const BatchBuf
     const double *pose = bb.poses + (size_t)p * rc_dev->pose_len;
     for (int k = 0; k < LIG_TILE; ++k) {
       if ((slow_bits >> k) & 1u) continue;  // the exact path below owns this pair entirely
-      const float4 a = lds_f4(tile_addr ^ (uint32_t)(k << 4));
+      // (a plain load at the relative offset: an asm load of the same address would be merged with the one above and
+      // keep the eight atoms of the item in registers across the hot loop)
+      const float4 a = lds_f4((tile_addr - (FLEX ? 0u : rg_smem_base())) ^ (uint32_t)(k << 4));
       const float dx = ax - a.x, dy = ay - a.y, dz = az - a.z;
       const float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));  // same operations as above: same bits
       if (d2 > 6.0025f + delta) continue;
@@ -570,8 +591,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
   const int lane = threadIdx.x & 31;
   const int n_warps = blockDim.x >> 5;
   // rigid: one ligand block for the CTA; FLEX: one per warp (the pose it is working on)
-  const uint32_t l4_addr = 128u + (FLEX ? (uint32_t)(threadIdx.x >> 5) * (uint32_t)rc.n_lig_pad * 16u : 0u);
-  float4 *l4 = reinterpret_cast<float4 *>(smem_raw + l4_addr);
+  const uint32_t l4_off = 128u + (FLEX ? (uint32_t)(threadIdx.x >> 5) * (uint32_t)rc.n_lig_pad * 16u : 0u);
+  // rigid: absolute (shared window) addresses, see lds_f4_abs; the FLEX instance keeps offsets relative to smem_rigid
+  // (with absolute ones ptxas spills in its row loop: 2uuy 3.94 -> 4.45 ms)
+  const uint32_t abs_base = FLEX ? 0u : rg_smem_base();
+  uint32_t l4_addr = abs_base + l4_off;
+  float4 *l4 = reinterpret_cast<float4 *>(smem_raw + l4_off);
   unsigned char *rows = smem_raw + 128 + (size_t)(FLEX ? n_warps : 1) * rc.n_lig_pad * 16;
   const uint32_t lane_sw = (uint32_t)(lane & 7) << 4;
   const int n_units = rc.n_groups * n_chunks;
@@ -594,15 +619,21 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
       const unsigned un = atomicAdd(unit_counter, 1u);
       *s_unit = (int)un;
       *s_pose_next = 0;
-      *reinterpret_cast<unsigned *>(smem_raw + RG_NEED_OFF) =
-          (DETAIL || rc.lig_need || un >= (unsigned)n_units) ? 0xffffffffu : rc.group_need[rc.group_order[un / (unsigned)n_chunks]];
+      if (!FLEX)  // (the FLEX instance looks at every contact: its code generation does not take the extra test well)
+        *reinterpret_cast<unsigned *>(smem_raw + RG_NEED_OFF) =
+            (DETAIL || rc.lig_need || un >= (unsigned)n_units) ? 0xffffffffu : rc.group_need[rc.group_order[un / (unsigned)n_chunks]];
     }
     __syncthreads();
     const int u = *s_unit;
     if (u >= n_units) break;
     const int g = rc.group_order[u / n_chunks];
-    const int p0 = (u % n_chunks) * poses_per_unit;
-    const int p1 = min(p0 + poses_per_unit, n_poses);
+    // rigid: the unit's poses are p0, p0 + n_chunks, p0 + 2 n_chunks, ...  A batch is a sequence of swarms (200 similar
+    // poses each) whose cost differs by up to 5x, and a strided unit holds the batch's mix of them instead of two or
+    // three swarms: a rank's 50 swarms of the 1k4c bench 3.73 -> 3.65 ms (profiles/r2_rigid_ab_run4_units.txt).  FLEX
+    // keeps contiguous ranges: its per-pose ligand blocks stream better that way (2uuy 3.94 against 3.99 ms).
+    const int pstep = FLEX ? 1 : n_chunks;
+    const int p0 = FLEX ? (u % n_chunks) * poses_per_unit : u % n_chunks;
+    const int p1 = FLEX ? min(p0 + poses_per_unit, n_poses) : n_poses;
     if (p0 >= p1) continue;  // CTA-uniform: a unit beyond the live rows (device-resident callers)
     if (g != cur_g) {  // CTA-uniform
       if (threadIdx.x == 0) {
@@ -623,8 +654,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
       // byte address of (row, ligand type 0, index 4) minus what the magic-number index carries
       const int slot = rc.rec_slot[ia];  // -1 = pad lane
       rowoff = slot < 0 ? 0xffffffffu
-                        : (unsigned)(rows - smem_rigid) + (unsigned)slot * RG_ROW_BYTES - ((RG_MAGIC_BITS + (unsigned)RG_SLOT0) << 3);
+                        : abs_base + (unsigned)(rows - smem_rigid) + (unsigned)slot * RG_ROW_BYTES -
+                              ((RG_MAGIC_BITS + (unsigned)RG_SLOT0) << 3);
       mbar_wait(bar, phase);
+      if (!FLEX) {
+        rg_after_copy(rowoff);
+        rg_after_copy(l4_addr);
+      }
       phase ^= 1u;
       lig_loaded = true;
       cur_g = g;
@@ -634,7 +670,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
     for (;;) {
       int p = 0;
       if (lane == 0) p = atomicAdd(s_pose_next, 1);
-      p = __shfl_sync(0xffffffffu, p, 0) + p0;
+      p = __shfl_sync(0xffffffffu, p, 0) * pstep + p0;
       if (p >= p1) break;
       const double *prep = prep_all + (size_t)p * RG_PREP;
       bool brute = false;
@@ -645,7 +681,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
         // asynchronous copies (LDGSTS: no registers, all in flight at once), waited for right before the first row, so
         // they land while the warp moves its receptor atoms into the pose's frame and looks their cells up
         const float4 *src = lig4p + (size_t)p * rc.n_lig_pad;
-        for (int i = lane; i < rc.n_lig_pad; i += 32) cp_async16(l4_addr + (uint32_t)i * 16u, src + i);
+        for (int i = lane; i < rc.n_lig_pad; i += 32) cp_async16(l4_off + (uint32_t)i * 16u, src + i);
         cp_async_commit();
         const float dmax = pose_flag[p];
         brute = dmax != 0.f;

@@ -43,6 +43,19 @@ for n in (10000, 80000):
         sc.energy(poses)
         ts.append(sc.stats()["pair_ms"])
     print(f"{tag}: 1k4c {len(poses)} poses: pair ms {np.round(ts, 3)} -> {len(poses) / np.median(ts) * 1e3 / 1e6:.3f} M poses/s")
+# what one rank of an 8-GPU run scores: 50 whole swarms under the cost-aware map (contiguous blocks of 200 similar poses)
+all_sw = workload.synthetic_1k4c_swarms(400, 200)
+rec_xyz = workload.read_pdb_coords(os.path.join(workload.GOLDEN_1K4C, "lightdock_receptor_membrane.pdb"))
+lig_xyz = workload.read_pdb_coords(os.path.join(workload.GOLDEN_1K4C, "lightdock_ligand.pdb"))
+for world, rank in ((8, 0), (8, 5), (4, 1)):
+    mine = workload.shard_swarms_cost_aware(all_sw, rec_xyz, lig_xyz, rank, world)
+    poses = np.ascontiguousarray(all_sw[mine].reshape(-1, 7))
+    sc.energy(poses)
+    ts = []
+    for _ in range(5):
+        sc.energy(poses)
+        ts.append(sc.stats()["pair_ms"])
+    print(f"{tag}: 1k4c rank {rank} of {world} ({len(poses)} poses, whole swarms): pair ms {np.round(ts, 3)} -> x{world} = {np.median(ts) * world:.3f} ms")
 sc.close()
 for name in ("1ppe", "2uuy", "1czy"):
     cxc, poses = config_poses(name)
