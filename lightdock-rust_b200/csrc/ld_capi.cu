@@ -55,7 +55,7 @@ extern "C" const char *ld_version(void) { return "lightdock_b200 0.2 (sm_100a)";
 namespace {
 struct Options {
   int rigid_rows = RG_MAX_ROWS;   // table rows a receptor group may span (1..RG_MAX_ROWS)
-  double cell_size = 1.0;         // ligand-frame cell size in A
+  double cell_size = 0.0;         // ligand-frame cell size in A; 0 = chosen per complex (build_cells)
   int units_per_sm = 16;          // rigid kernel: work units per SM
   int default_path = LD_PATH_AUTO;
   int flex = 1;                   // 0: ligands with ANM modes stay on the generic kernel (no FLEX instance of the ligand-frame path)
@@ -70,7 +70,7 @@ extern "C" int ld_set_option(const char *key, double value) {
   if (!key) return fail(LD_EINVAL, "ld_set_option: NULL key");
   const std::string k(key);
   if (k == "rigid_rows") g_opt.rigid_rows = std::max(1, std::min(RG_MAX_ROWS, (int)value));
-  else if (k == "cell_size") g_opt.cell_size = std::max(0.5, std::min(8.0, value));
+  else if (k == "cell_size") g_opt.cell_size = value <= 0.0 ? 0.0 : std::max(0.5, std::min(8.0, value));
   else if (k == "units_per_sm") g_opt.units_per_sm = std::max(1, (int)value);
   else if (k == "cells_on_host") g_opt.cells_on_host = value != 0.0;
   else if (k == "flex") g_opt.flex = value != 0.0;
@@ -498,6 +498,18 @@ static int build_cells(ld_handle *h) {
   RigidComplex &rc = h->rc;
   const std::vector<double> &LX = h->lig_sx, &LY = h->lig_sy, &LZ = h->lig_sz;
   double cell = g_opt.cell_size;
+  if (cell <= 0.0) {
+    // Finer cells = tighter lists (fewer pair tests that cannot be in range), as long as the grid and its lists stay a
+    // modest share of L2: ~27,000 A^3 of cells list a tile (its atoms' 15 A spheres), 2 bytes per entry, 8 bytes per
+    // cell.  Measured (profiles/r2_rigid_ab_run5_cell.txt): 1k4c (409 tiles) 1.0 A 28.06 ms, 0.75 A 27.78, 0.6 A 28.14;
+    // 1ppe (28 tiles) 2.133 / 2.094 / 2.073.  The FLEX instance keeps 1 A (2uuy: 3.95 / 3.98 / 4.07 ms).
+    cell = 1.0;
+    if (!h->flex) {
+      cell = 0.75;
+      const double foot06 = (double)cx.n_lig_tiles * 27000.0 / (0.6 * 0.6 * 0.6) * 2.0;
+      if (foot06 < 24.0e6) cell = 0.6;
+    }
+  }
   double max_slack = 0.0;
   for (float v : h->tile_slack) max_slack = std::max(max_slack, (double)v);
   const double base_reach = 15.0 + 0.01, reach_max = base_reach + max_slack;

@@ -80,6 +80,50 @@ def test_random_close_poses_parity_rigid(name):
     assert d_ref["n_interface_pairs"].max() > 0
 
 
+def _with_restraints(cx, rec_groups, lig_groups):
+    """A copy of the oracle complex whose ACTIVE restraint groups are the given lists of atom indices."""
+    def mol(m, groups):
+        m2 = copy.copy(m)
+        off, idx = [0], []
+        for g in groups:
+            idx.extend(int(i) for i in g)
+            off.append(len(idx))
+        m2.rst_offsets = np.array(off, dtype=np.int32)
+        m2.rst_atoms = np.array(idx, dtype=np.int32)
+        return m2
+    return O.Complex(mol(cx.rec, rec_groups), mol(cx.lig, lig_groups), cx.method, cx.use_anm, cx.potential)
+
+
+@pytest.mark.parametrize("name", RIGID_CASES)
+@pytest.mark.parametrize("which", ["none", "receptor", "ligand", "both"])
+def test_interface_pass_runs_wherever_a_flag_is_read(name, which):
+    """The plain (non-detail) instantiation looks for contacts below 3.9 A only on behalf of atoms whose interface flag
+    finalize_kernel reads (active restraints, membrane beads; every contact once the ligand has active restraints,
+    ld_rigid.cuh RG_NEED_OFF).  Whatever the restraint sets are, its energies must be the detail instantiation's bits
+    and the oracle's values: the restraint and membrane terms multiply the score, so one missed flag shows at 1e-2."""
+    cx0, _, _ = case(name, O.DFIRE)
+    rng = np.random.default_rng(29)
+    def groups(n_atoms, k):
+        starts = rng.choice(n_atoms - 12, size=k, replace=False)
+        return [np.arange(a, a + int(rng.integers(4, 12))) for a in sorted(starts)]
+    rec_g = groups(cx0.rec.n, 9) if which in ("receptor", "both") else []
+    lig_g = groups(cx0.lig.n, 7) if which in ("ligand", "both") else []
+    cx = _with_restraints(cx0, rec_g, lig_g)
+    sc = _rigid(cx)
+    n = 48 if cx.rec.n * cx.lig.n < 2_000_000 else 12
+    poses = random_poses(rng, n, cx.pose_len, centre=cx.rec.coords.mean(axis=0), spread=9.0)
+    e_plain = sc.energy(poses)
+    e_gpu, d_gpu = sc.energy_detail(poses)
+    e_ref, d_ref = cx.energy(poses, detail=True)
+    assert_parity(e_gpu, d_gpu, e_ref, d_ref, cx.method)
+    assert np.array_equal(e_plain, e_gpu), "plain and detail instantiations must give the same bits"
+    if which in ("receptor", "both"):
+        assert d_ref["rec_rst_hit"].max() > 0
+    if which in ("ligand", "both"):
+        assert d_ref["lig_rst_hit"].max() > 0
+    sc.close()
+
+
 def test_rigid_equals_generic_on_bench_workload():
     """2,000 poses of the bench workload (synthetic 1k4c swarms): every discrete output identical between the
     two kernels, energies equal to 1e-9 relative (they differ only in summation order)."""
