@@ -499,15 +499,30 @@ static int build_cells(ld_handle *h) {
   const std::vector<double> &LX = h->lig_sx, &LY = h->lig_sy, &LZ = h->lig_sz;
   double cell = g_opt.cell_size;
   if (cell <= 0.0) {
-    // Finer cells = tighter lists (fewer pair tests that cannot be in range), as long as the grid and its lists stay a
-    // modest share of L2: ~27,000 A^3 of cells list a tile (its atoms' 15 A spheres), 2 bytes per entry, 8 bytes per
-    // cell.  Measured (profiles/r2_rigid_ab_run5_cell.txt): 1k4c (409 tiles) 1.0 A 28.06 ms, 0.75 A 27.78, 0.6 A 28.14;
-    // 1ppe (28 tiles) 2.133 / 2.094 / 2.073.  The FLEX instance keeps 1 A (2uuy: 3.95 / 3.98 / 4.07 ms).
+    // Finer cells = tighter lists (fewer pair tests that cannot be in range), as long as the grid and its lists stay
+    // well inside L2: ~27,000 A^3 of cells list a tile (its atoms' 15 A spheres), 2 bytes per entry, 8 bytes per cell of
+    // the ligand's box grown by the reach.  The finest of 0.6 / 0.75 / 0.85 / 1 A whose estimate stays below 50 MB:
+    // 1k4c (409 tiles) 0.85 A, 1ppe (28 tiles) 0.6 A.  Measured (profiles/r2_rigid_ab_run5_cell.txt): 1k4c 28.06 ms per
+    // 80,000 poses at 1 A, 27.81 at 0.85, 27.78 at 0.75 -- but with 59 MB of lists at 0.75 A the L2 hit rate of the list
+    // reads falls from 94 % to 85 % and the launch moves 1.4 GB through DRAM instead of 0.45 -- 28.14 at 0.6; 1ppe 2.13 /
+    // 2.09 / 2.07 ms at 1 / 0.75 / 0.6 A.  The FLEX instance keeps 1 A (2uuy: 3.95 / 3.98 / 4.07 ms).
     cell = 1.0;
     if (!h->flex) {
-      cell = 0.75;
-      const double foot06 = (double)cx.n_lig_tiles * 27000.0 / (0.6 * 0.6 * 0.6) * 2.0;
-      if (foot06 < 24.0e6) cell = 0.6;
+      double vol = 1.0;
+      {
+        double lo3[3] = {1e300, 1e300, 1e300}, hi3[3] = {-1e300, -1e300, -1e300};
+        const std::vector<double> *C3[3] = {&LX, &LY, &LZ};
+        for (int j = 0; j < cx.n_lig; ++j)
+          for (int d = 0; d < 3; ++d) {
+            lo3[d] = std::min(lo3[d], (*C3[d])[j]);
+            hi3[d] = std::max(hi3[d], (*C3[d])[j]);
+          }
+        for (int d = 0; d < 3; ++d) vol *= hi3[d] - lo3[d] + 30.1;
+      }
+      for (double c : {0.6, 0.75, 0.85}) {
+        const double est = ((double)cx.n_lig_tiles * 27000.0 * 2.0 + vol * 8.0) / (c * c * c);
+        if (est < 50.0e6) { cell = c; break; }
+      }
     }
   }
   double max_slack = 0.0;
