@@ -649,7 +649,8 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 0-3 leg reported at N=1")
     ap.add_argument("--no-single-swarm-runs", action="store_true",
                     help="skip the five 100-step single-swarm CLI runs (BASELINE configs 0-3) reported at N=1")
-    ap.add_argument("--gso-steps", type=int, default=20, help="steps of the real GSO loop for the gso_run figure (0 = skip)")
+    ap.add_argument("--gso-steps", type=int, default=100,
+                    help="steps of the real GSO loop for the gso_run figures (BASELINE configs[4]: 100; 0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
