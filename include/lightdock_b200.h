@@ -213,7 +213,8 @@ int ld_probe_peaks(int32_t device, double *fp64_nonfma_tflops, double *fp32_nonf
 
 /* Process-wide tuning defaults for handles created afterwards (benchmark / experiment aid; the library never reads
  * the environment): "rigid_rows" 1..4 table rows per receptor group, "cell_size" ligand-frame cell edge in A
- * (0.5..8; 0, the default: chosen per complex so that grid + lists stay well inside L2), "units_per_sm" rigid-kernel work units per SM, "default_path" LD_PATH_AUTO | LD_PATH_GENERIC, "flex" 0 keeps
+ * (0.5..8; 0, the default: chosen per complex so that grid + lists stay well inside L2), "units_per_sm" rigid-kernel work units per SM, "flex_min_warps" warps per CTA the FLEX instance wants before a receptor
+ * group may span one more table row, "default_path" LD_PATH_AUTO | LD_PATH_GENERIC, "flex" 0 keeps
  * ligands with ANM modes on the generic kernel, "cells_on_host" 1 builds the ligand-frame cell lists with host threads
  * (the cross-check of the device builder), "compact_tiles" 0 keeps the plain bisection order of the atoms (the tiles of 8 / 32
  * atoms are otherwise made more compact by a capacity-constrained k-means: fewer executed pair tests), "dna_fused" 0 sends

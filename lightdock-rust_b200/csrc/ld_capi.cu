@@ -57,6 +57,7 @@ struct Options {
   int rigid_rows = RG_MAX_ROWS;   // table rows a receptor group may span (1..RG_MAX_ROWS)
   double cell_size = 0.0;         // ligand-frame cell size in A; 0 = chosen per complex (build_cells)
   int units_per_sm = 16;          // rigid kernel: work units per SM
+  int flex_min_warps = 18;        // FLEX: warps per CTA wanted before a receptor group may span one more table row
   int default_path = LD_PATH_AUTO;
   int flex = 1;                   // 0: ligands with ANM modes stay on the generic kernel (no FLEX instance of the ligand-frame path)
   int cells_on_host = 0;          // 1: build the ligand-frame cell lists with host threads (the round-1 builder; cross-check)
@@ -72,6 +73,7 @@ extern "C" int ld_set_option(const char *key, double value) {
   if (k == "rigid_rows") g_opt.rigid_rows = std::max(1, std::min(RG_MAX_ROWS, (int)value));
   else if (k == "cell_size") g_opt.cell_size = value <= 0.0 ? 0.0 : std::max(0.5, std::min(8.0, value));
   else if (k == "units_per_sm") g_opt.units_per_sm = std::max(1, (int)value);
+  else if (k == "flex_min_warps") g_opt.flex_min_warps = std::max(8, std::min(RG_WARPS, (int)value));
   else if (k == "cells_on_host") g_opt.cells_on_host = value != 0.0;
   else if (k == "flex") g_opt.flex = value != 0.0;
   else if (k == "compact_tiles") g_opt.compact_tiles = value != 0.0;
@@ -698,7 +700,7 @@ static int build_cells(ld_handle *h) {
            "%zu non-empty cells, %zu list entries (longest %zu), delta %.2e, smem %zu B",
            h->flex ? " (flexible ligand: per-pose ligand blocks, slack lists, fixed-point sums)" : "", rc.n_groups,
            (double)cx.n_rec / rc.n_groups, rc.rows_max, hh, nc[0], nc[1], nc[2], nonempty, total, longest, delta,
-           rigid_smem_bytes(cx.n_lig_pad, rc.rows_max, h->flex ? h->flex_warps : 1));
+           rigid_smem_bytes(cx.n_lig_pad, rc.rows_max, rc.row_bytes, h->flex ? h->flex_warps : 1));
   h->rigid_info = buf;
   if (h->flex) {
     snprintf(buf, sizeof buf, ", %d warps per CTA, tile slack max %.2f A (rebuilt %d times)", h->flex_warps, max_slack,
@@ -716,10 +718,27 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   if (cx.method != 0) { h->rigid_info = "rigid path off: not DFIRE"; return LD_OK; }
   if (cx.n_rec == 0 || cx.n_lig == 0) { h->rigid_info = "rigid path off: empty partner"; return LD_OK; }
   if (cx.n_lig_tiles > 65535) { h->rigid_info = "rigid path off: ligand tile ids exceed 16 bits"; return LD_OK; }
+  // FLEX: a table row holds only the DFIRE types the ligand has (1czy: 36 of 169, 2uuy 140): smaller rows leave room for
+  // more rows per receptor group (fuller groups, fewer (group, pose) tasks: 1czy 48 -> 42 groups) or for more warps next to
+  // them (2uuy 16 -> 18), and there is less to copy on a group switch.  The rigid instance keeps full rows of a
+  // compile-time size: its ligands are large (1k4c has 167 of the types) and a run-time row size costs its code
+  // generation 1 % (profiles/r2_flex_latency_ab.txt, run 52).
+  std::vector<int> ctype(169, -1);
+  int n_ct = 0;
+  if (cx.n_lig_modes > 0) {
+    std::vector<char> present(169, 0);
+    for (int j = 0; j < cx.n_lig; ++j) present[L.tb20[j] / 20] = 1;
+    for (int t = 0; t < 169; ++t)
+      if (present[t]) ctype[t] = n_ct++;
+  } else {
+    for (int t = 0; t < 169; ++t) ctype[t] = t;
+    n_ct = 169;
+  }
+  const int row_bytes = cx.n_lig_modes > 0 ? n_ct * RG_TB_BYTES : RG_ROW_BYTES;  // multiples of 16 (RG_TB_BYTES = 240)
   int rows_max = 0;
   if (cx.n_lig_modes == 0) {
-    const long avail = (long)h->max_smem_optin - (long)rigid_smem_bytes(cx.n_lig_pad, 0);
-    rows_max = (int)std::min<long>(RG_MAX_ROWS, avail / RG_ROW_BYTES);
+    const long avail = (long)h->max_smem_optin - (long)rigid_smem_bytes(cx.n_lig_pad, 0, row_bytes);
+    rows_max = (int)std::min<long>(4, avail / row_bytes);  // rigid: as measured in round 2 (4 x 40,560 B next to the ligand)
     rows_max = std::min(rows_max, g_opt.rigid_rows);
     if (rows_max < 1) { h->rigid_info = "rigid path off: ligand + one table row exceed shared memory"; return LD_OK; }
   } else if (!g_opt.flex) {
@@ -727,13 +746,15 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
     return LD_OK;
   } else {
     // FLEX: one ligand block per warp next to the table rows; prefer many rows (fewer, fuller receptor groups) as
-    // long as enough warps fit to keep the SM busy
+    // long as enough warps fit to keep the SM busy -- the FLEX instance is latency bound, so warps come first.  Measured
+    // (20,000 poses, profiles/r2_flex_latency_ab.txt run 53): 2uuy 4 rows / 14 warps 4.18 ms, 3 / 19 3.57 ms, 2 / 20 3.96 ms;
+    // ab_icode 6 / 17 4.34 ms, 5 / 20 3.93 ms; 1czy fits 8 rows and 20 warps (1.55 ms; 4 rows: 1.63 ms)
     const long lig_bytes = (long)cx.n_lig_pad * 16;
     int best_w = 0;
     for (int r = std::min(RG_MAX_ROWS, g_opt.rigid_rows); r >= 1 && rows_max == 0; --r) {
-      const long avail = (long)h->max_smem_optin - 128 - (long)r * RG_ROW_BYTES;
+      const long avail = (long)h->max_smem_optin - 128 - (long)r * row_bytes;
       const int w = (int)std::min<long>(RG_WARPS, avail / lig_bytes);
-      if (w >= 12 || (r <= 2 && w >= 8)) { rows_max = r; best_w = w; }
+      if (w >= g_opt.flex_min_warps || (r <= 2 && w >= 8)) { rows_max = r; best_w = w; }
     }
     if (rows_max == 0) {
       h->rigid_info = "rigid path off: the ligand has ANM modes and its per-warp blocks do not fit in shared memory";
@@ -790,7 +811,7 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   std::vector<float4> l4(cx.n_lig_pad);
   for (int j = 0; j < cx.n_lig_pad; ++j) {
     if (j < cx.n_lig) {
-      l4[j] = make_float4((float)L.x[j], (float)L.y[j], (float)L.z[j], (float)((L.tb20[j] / 20) * RG_SLOTS));
+      l4[j] = make_float4((float)L.x[j], (float)L.y[j], (float)L.z[j], (float)(ctype[L.tb20[j] / 20] * RG_SLOTS));
     } else {
       l4[j] = make_float4(1.0e6f, 1.0e6f, 1.0e6f, 0.f);
     }
@@ -806,10 +827,24 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
   UPR(l4, lig4); UPR(gneed, group_need);
 #undef UPR
   rc.lig_need = desc->ligand.n_restraints > 0 ? 1 : 0;
+  // the table re-indexed by the truncated bin-space value idx = -1..28 (as cx.potx, create_impl) for the ligand's types only
+  const size_t row8 = (size_t)row_bytes / 8;
+  std::vector<double> potx(169 * row8, 0.0);
+  for (int ta = 0; ta < 169; ++ta)
+    for (int tb = 0; tb < 169; ++tb) {
+      if (ctype[tb] < 0) continue;
+      for (int sidx = 0; sidx < RG_SLOTS; ++sidx) {
+        const int idx = sidx + RG_SLOT0;
+        if (idx > 28) continue;
+        const int bin = idx <= 2 ? 0 : (idx <= 15 ? idx - 2 : 13 + ((idx - 15) >> 1));
+        potx[ta * row8 + (size_t)ctype[tb] * RG_SLOTS + sidx] = desc->dfire_potential[(size_t)ta * DFIRE_ROW + tb * 20 + bin];
+      }
+    }
+  if ((rcode = upload(h, potx, &rc.potx)) != LD_OK) return rcode;
   rc.n_groups = ng; rc.n_rec_pos = npos;
   rc.n_lig = cx.n_lig; rc.n_lig_pad = cx.n_lig_pad; rc.n_lig_tiles = cx.n_lig_tiles;
-  rc.n_rec_modes = nrm; rc.pose_len = cx.pose_len; rc.rows_max = rows_max;
-  rc.lig_x = cx.lig_x; rc.lig_y = cx.lig_y; rc.lig_z = cx.lig_z; rc.lig_tb20 = cx.lig_tb20; rc.pot = cx.pot; rc.potx = cx.potx;
+  rc.n_rec_modes = nrm; rc.pose_len = cx.pose_len; rc.rows_max = rows_max; rc.row_bytes = row_bytes;
+  rc.lig_x = cx.lig_x; rc.lig_y = cx.lig_y; rc.lig_z = cx.lig_z; rc.lig_tb20 = cx.lig_tb20; rc.pot = cx.pot;
   rc.flex = h->flex ? 1 : 0;
   rc.n_lig_modes = cx.n_lig_modes;
   rc.lig_modes = cx.lig_modes;
@@ -824,9 +859,7 @@ static int build_rigid(const ld_complex_desc *desc, ld_handle *h, const SortedMo
     // fixed-point copy of the re-indexed table: scale 2^k with 32 atoms x n_lig_pad pairs x max|value| x 2^k < 2^61, so
     // that the sum over one (receptor group, pose) cannot overflow; finalize_kernel converts each group's sum back
     // and adds the groups in order
-    const size_t n_potx = 169 * (size_t)(RG_ROW_BYTES / 8);
-    std::vector<double> potx(n_potx);
-    CU(cudaMemcpy(potx.data(), cx.potx, n_potx * sizeof(double), cudaMemcpyDeviceToHost));
+    const size_t n_potx = potx.size();
     double vmax = 1.0;
     for (double v : potx) vmax = std::max(vmax, std::fabs(v));
     const int k = 61 - (int)std::ceil(std::log2(32.0 * cx.n_lig_pad * vmax));
@@ -1320,7 +1353,7 @@ static int run_device(ld_handle *h, int64_t n, const double *d_poses, double *d_
       const int n_chunks = (int)((nc + ppu - 1) / ppu);
       const int64_t n_units = (int64_t)n_chunks * rg.n_groups;
       const unsigned grid = (unsigned)std::min<int64_t>(h->sm_count, n_units);
-      const size_t smem = rigid_smem_bytes(rg.n_lig_pad, rg.rows_max, h->flex ? cta_warps : 1);
+      const size_t smem = rigid_smem_bytes(rg.n_lig_pad, rg.rows_max, rg.row_bytes, h->flex ? cta_warps : 1);
       const unsigned threads = (unsigned)cta_warps * 32u;
       if (h->flex) {
         if (detail)

@@ -49,13 +49,14 @@ namespace ldb200 {
 #endif
 constexpr int RG_THREADS = LDB200_RG_THREADS;
 constexpr int RG_WARPS = RG_THREADS / 32;
-constexpr int RG_MAX_ROWS = 4;
+constexpr int RG_MAX_ROWS = 8;
 
 struct RigidComplex {
   int n_groups, n_rec_pos;  // n_rec_pos = n_groups * 32 (type-grouped receptor positions, pads interspersed)
   int n_lig, n_lig_pad, n_lig_tiles;
   int n_rec_modes, pose_len;
   int rows_max;
+  int row_bytes;                        // one table row: FLEX n_lig_types x RG_TB_BYTES (only the ligand's own types), rigid RG_ROW_BYTES
   const double *rec_x, *rec_y, *rec_z;  // [n_rec_pos] lab frame, pads at REC_PAD
   const int *rec_slot;                  // [n_rec_pos] which of the group's rows this atom indexes (0..3)
   const int *rec_toff;                  // [n_rec_pos] type * 3380 (exact path)
@@ -65,7 +66,7 @@ struct RigidComplex {
   const float4 *lig4;                   // [n_lig_pad] local f32 x,y,z + (float)(type * RG_SLOTS)
   const double *lig_x, *lig_y, *lig_z;  // [n_lig_pad] local f64 (exact path)
   const unsigned short *lig_tb20;       // type * 20 (exact path)
-  const double *potx;                   // [169][RG_ROW_BYTES/8]: row ta = [tb][slot], slot s <-> index s+4
+  const double *potx;                   // [169][row_bytes/8]: row ta = [compact ligand type][slot], slot s <-> index s-1
   const double *pot;                    // the reference's table (exact path)
   float gx0, gy0, gz0, inv_h;           // cell grid in the ligand frame
   int nx, ny, nz;
@@ -90,8 +91,8 @@ struct RigidComplex {
 };
 
 // ligand copies: 1 (rigid: shared by the CTA) or one per warp (FLEX: each warp works on its own pose)
-__host__ __device__ inline size_t rigid_smem_bytes(int n_lig_pad, int rows, int lig_copies = 1) {
-  return 128 + (size_t)lig_copies * n_lig_pad * 16 + (size_t)rows * RG_ROW_BYTES;
+__host__ __device__ inline size_t rigid_smem_bytes(int n_lig_pad, int rows, int row_bytes, int lig_copies = 1) {
+  return 128 + (size_t)lig_copies * n_lig_pad * 16 + (size_t)rows * row_bytes;
 }
 
 extern __shared__ __align__(128) unsigned char smem_rigid[];
@@ -600,6 +601,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
   unsigned char *rows = smem_raw + 128 + (size_t)(FLEX ? n_warps : 1) * rc.n_lig_pad * 16;
   const uint32_t lane_sw = (uint32_t)(lane & 7) << 4;
   const int n_units = rc.n_groups * n_chunks;
+  // rigid: full rows, a compile-time size (a run-time one costs the rigid instance 1 % in code generation); FLEX: rows of the
+  // ligand's own types only
+  const uint32_t row_bytes = FLEX ? (uint32_t)rc.row_bytes : (uint32_t)RG_ROW_BYTES;
   const unsigned char *rows_src = FLEX ? reinterpret_cast<const unsigned char *>(rc.potx_fx)
                                        : reinterpret_cast<const unsigned char *>(rc.potx);
 
@@ -641,20 +645,20 @@ __global__ void __launch_bounds__(RG_THREADS, 1)
         uint32_t bytes = lig_loaded ? 0u : (uint32_t)rc.n_lig_pad * 16u;
         int n_rows = 0;
         for (int r = 0; r < rc.rows_max; ++r) n_rows += rc.group_types[g * RG_MAX_ROWS + r] >= 0;
-        bytes += (uint32_t)n_rows * RG_ROW_BYTES;
+        bytes += (uint32_t)n_rows * row_bytes;
         mbar_expect_tx(bar, bytes);
         if (!lig_loaded) bulk_g2s(l4, rc.lig4, (uint32_t)rc.n_lig_pad * 16u, bar);
         for (int r = 0; r < rc.rows_max; ++r) {
           const int ty = rc.group_types[g * RG_MAX_ROWS + r];
           if (ty >= 0)
-            bulk_g2s(rows + (size_t)r * RG_ROW_BYTES, rows_src + (size_t)ty * RG_ROW_BYTES, RG_ROW_BYTES, bar);
+            bulk_g2s(rows + (size_t)r * row_bytes, rows_src + (size_t)ty * row_bytes, row_bytes, bar);
         }
       }
       const int ia = g * 32 + lane;
       // byte address of (row, ligand type 0, index 4) minus what the magic-number index carries
       const int slot = rc.rec_slot[ia];  // -1 = pad lane
       rowoff = slot < 0 ? 0xffffffffu
-                        : abs_base + (unsigned)(rows - smem_rigid) + (unsigned)slot * RG_ROW_BYTES -
+                        : abs_base + (unsigned)(rows - smem_rigid) + (unsigned)slot * row_bytes -
                               ((RG_MAGIC_BITS + (unsigned)RG_SLOT0) << 3);
       mbar_wait(bar, phase);
       if (!FLEX) {

@@ -101,7 +101,7 @@ def load_library():
         # experiment knobs of the tools (tools/units_sweep.py, ...): forwarded through the API, the library itself
         # never reads the environment
         for env, key in (("LDB200_ROWS", "rigid_rows"), ("LDB200_CELL", "cell_size"),
-                         ("LDB200_UNITS_PER_SM", "units_per_sm"), ("LDB200_COMPACT_TILES", "compact_tiles"), ("LDB200_DNA_FUSED", "dna_fused")):
+                         ("LDB200_UNITS_PER_SM", "units_per_sm"), ("LDB200_FLEX_MIN_WARPS", "flex_min_warps"), ("LDB200_COMPACT_TILES", "compact_tiles"), ("LDB200_DNA_FUSED", "dna_fused")):
             if os.environ.get(env):
                 _check(lib, lib.ld_set_option(key.encode(), float(os.environ[env])))
         if os.environ.get("LDB200_PATH") == "generic":
