@@ -575,7 +575,7 @@ def run_b200(args, rank, world, local_rank):
 README_M3_SECONDS = {"1k4c": 112.132, "1ppe": 4.252, "2uuy": 8.108, "1czy": 1.580, "1azp": 14.228}
 
 
-def single_swarm_runs(dc_dir, repeats=3):
+def single_swarm_runs(dc_dir, repeats=5):
     """BASELINE configs 0-3 as a reference user runs them: the drop-in CLI, one swarm, 100 steps, whole-process wall
     clock (process start, CUDA context, model building and the 11 output files included), next to the README's M3 Pro
     times, with the CLI's own account of where the time went (LDB200_TIMING=1: one line on stderr).  Each configuration

@@ -28,15 +28,18 @@ constexpr int REC_TILE = 32;  // receptor atoms per tile = lanes of a warp
 constexpr int LIG_TILE = 8;   // ligand atoms per tile (unit of sphere culling)
 constexpr int PAIR_THREADS = 512;  // generic DFIRE pair kernel
 #ifndef LDB200_DNA_THREADS
-#define LDB200_DNA_THREADS 256
+#define LDB200_DNA_THREADS 192
 #endif
 #ifndef LDB200_DNA_CTAS
-#define LDB200_DNA_CTAS 4
+#define LDB200_DNA_CTAS 6
 #endif
-constexpr int DNA_CTAS_PER_SM = LDB200_DNA_CTAS;  // measured on 1azp (20,000 poses): 4 x 256 threads (64 registers, a few
-                                                  // spilled words) 11.6 ms, 3 x 256 (80 registers) 12.6 ms, 2 x 256 (126) 12.0 ms
-constexpr int DNA_THREADS = LDB200_DNA_THREADS;  // DNA/pyDock pair kernel: small complexes (1azp: 35 receptor tiles), so
-                                                 // smaller CTAs (more per SM) balance the tiles over the warps better
+// DNA/pyDock pair kernel: small complexes (1azp: 35 receptor tiles), so small CTAs, many per SM.  Measured on 1azp (20,000
+// poses, pair kernel): 6 x 192 threads (56 registers; 35 tiles on 6 warps = 6 rounds, 97 % of the warp slots used) 11.31 ms;
+// 4 x 256 (64 registers; 8 warps = 5 rounds, 87.5 %) 11.57; 5 x 256 (48) 11.51; 8 x 128 (64) 11.75; 3 x 256 (80) 12.6;
+// 2 x 256 (126) 12.0.  The landscape is flat: the kernel sits at the dispatch rate of its instruction mix (an FP64
+// instruction holds the dispatch port for two cycles), not at an occupancy or latency limit.
+constexpr int DNA_CTAS_PER_SM = LDB200_DNA_CTAS;
+constexpr int DNA_THREADS = LDB200_DNA_THREADS;
 constexpr int DFIRE_ROW = 169 * 20;  // src/dfire.rs:338  atoma*169*20
 constexpr double REC_PAD = 1.0e30;   // coordinates of padding atoms: never within any cut-off
 constexpr double LIG_PAD = -1.0e30;
