@@ -212,7 +212,7 @@ int ld_probe_peaks(int32_t device, double *fp64_nonfma_tflops, double *fp32_nonf
                    double *l2_gather_gloads);
 
 /* Process-wide tuning defaults for handles created afterwards (benchmark / experiment aid; the library never reads
- * the environment): "rigid_rows" 1..4 table rows per receptor group, "cell_size" ligand-frame cell edge in A
+ * the environment): "rigid_rows" 1..8 table rows per receptor group at most (the rigid instance takes up to 4, the FLEX instance up to 8), "cell_size" ligand-frame cell edge in A
  * (0.5..8; 0, the default: chosen per complex so that grid + lists stay well inside L2), "units_per_sm" rigid-kernel work units per SM, "flex_min_warps" warps per CTA the FLEX instance wants before a receptor
  * group may span one more table row, "default_path" LD_PATH_AUTO | LD_PATH_GENERIC, "flex" 0 keeps
  * ligands with ANM modes on the generic kernel, "cells_on_host" 1 builds the ligand-frame cell lists with host threads
